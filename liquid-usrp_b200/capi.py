@@ -1,0 +1,184 @@
+"""ctypes bindings of include/b200_ofdm.h (libb200ofdm.so)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib_path():
+    return os.path.join(HERE, "libb200ofdm.so")
+
+
+class B2Error(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("b200ofdm error %d: %s" % (code, text))
+        self.code = code
+
+
+# numpy view of b2_frame_rec
+FRAME_DTYPE = np.dtype([("channel", "<u4"), ("header_valid", "<i4"), ("payload_valid", "<i4"),
+                        ("payload_len", "<u4"), ("header", "u1", (8,)),
+                        ("evm", "<f4"), ("rssi", "<f4"), ("cfo", "<f4"),
+                        ("mod_scheme", "<u4"), ("mod_bps", "<u4"), ("check", "<u4"),
+                        ("fec0", "<u4"), ("fec1", "<u4"),
+                        ("detect_index", "<u8"), ("complete_index", "<u8"),
+                        ("payload_offset", "<u8")], align=True)
+
+_sz = C.c_size_t
+_vp = C.c_void_p
+
+_PROTOS = {
+    "b2_last_error": (C.c_char_p, []),
+    "b2_version": (C.c_char_p, []),
+    "b2_device_count": (C.c_int, []),
+    "b2_mcrx_create": (C.c_int, [C.c_uint, C.c_uint, C.c_uint, C.c_uint, _vp, C.c_int, _sz, C.POINTER(_vp)]),
+    "b2_mcrx_destroy": (C.c_int, [_vp]),
+    "b2_mcrx_reset": (C.c_int, [_vp]),
+    "b2_mcrx_execute": (C.c_int, [_vp, _vp, _sz]),
+    "b2_mcrx_execute_device": (C.c_int, [_vp, _vp, _sz]),
+    "b2_mcrx_poll": (C.c_int, [_vp, _vp, _sz, C.POINTER(_sz), _vp, _sz, C.POINTER(_sz)]),
+    "b2_mcrx_tap_symbols": (C.c_int, [_vp, C.c_int, _sz]),
+    "b2_mcrx_read_symbols": (C.c_int, [_vp, _vp, _vp, _vp, _sz, C.POINTER(_sz)]),
+    "b2_mcrx_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float * 4)]),
+    "b2_mcrx_read_channelizer": (C.c_int, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "b2_mcrx_stream": (_vp, [_vp]),
+    "b2_ofdmsync_create": (C.c_int, [C.c_uint, C.c_uint, C.c_uint, _vp, C.c_uint, C.c_int, _sz, C.POINTER(_vp)]),
+    "b2_ofdmsync_destroy": (C.c_int, [_vp]),
+    "b2_ofdmsync_reset": (C.c_int, [_vp]),
+    "b2_ofdmsync_execute": (C.c_int, [_vp, _vp, _sz]),
+    "b2_ofdmsync_execute_device": (C.c_int, [_vp, _vp, _sz, _sz]),
+    "b2_ofdmsync_poll": (C.c_int, [_vp, _vp, _sz, C.POINTER(_sz), _vp, _sz, C.POINTER(_sz)]),
+    "b2_ofdmsync_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float * 4)]),
+}
+
+
+def lib():
+    """load libb200ofdm.so; fails loudly when the CUDA library has not been built"""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)" % path)
+        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in _PROTOS.items():
+            if hasattr(L, name):
+                f = getattr(L, name)
+                f.restype = res
+                f.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise B2Error(rc, lib().b2_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(x):
+    """host numpy array or raw device pointer (int) -> void*"""
+    if isinstance(x, (int, np.integer)):
+        return C.c_void_p(int(x))
+    return C.c_void_p(x.ctypes.data)
+
+
+class _FrameSource:
+    _prefix = None
+
+    def _fn(self, name):
+        return getattr(lib(), self._prefix + name)
+
+    def poll(self):
+        """-> (records as a FRAME_DTYPE array, payload bytes); clears the queue"""
+        n, nb = _sz(0), _sz(0)
+        _check(self._fn("poll")(self.h, None, 0, C.byref(n), None, 0, C.byref(nb)))
+        recs = np.zeros(n.value, FRAME_DTYPE)
+        pl = np.zeros(max(nb.value, 1), np.uint8)
+        if n.value:
+            _check(self._fn("poll")(self.h, recs.ctypes.data, n.value, C.byref(n), pl.ctypes.data, len(pl), C.byref(nb)))
+        return recs, pl[:nb.value]
+
+    def last_timing(self):
+        ms = (C.c_float * 4)()
+        _check(self._fn("last_timing")(self.h, C.byref(ms)))
+        return [float(v) for v in ms]
+
+    def reset(self):
+        _check(self._fn("reset")(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._fn("destroy")(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultichannelRx(_FrameSource):
+    """b2_mcrx_*: N-channel OFDM receiver (multichannelrx, lib/multichannelrx.cc)"""
+    _prefix = "b2_mcrx_"
+
+    def __init__(self, num_channels, M, cp_len, taper_len, p=None, device=0, max_batch=0):
+        self.N, self.M, self.cp, self.taper = num_channels, M, cp_len, taper_len
+        h = _vp()
+        pp = None if p is None else np.ascontiguousarray(p, np.uint8).ctypes.data
+        _check(lib().b2_mcrx_create(num_channels, M, cp_len, taper_len, pp, device, max_batch, C.byref(h)))
+        self.h = h
+
+    def execute(self, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        _check(lib().b2_mcrx_execute(self.h, x.ctypes.data, len(x)))
+
+    def execute_device(self, dev_ptr, n):
+        _check(lib().b2_mcrx_execute_device(self.h, _ptr(dev_ptr), n))
+
+    def tap_symbols(self, enable=True, max_symbols=1 << 16):
+        _check(lib().b2_mcrx_tap_symbols(self.h, int(enable), max_symbols))
+
+    def read_symbols(self):
+        n = _sz(0)
+        _check(lib().b2_mcrx_read_symbols(self.h, None, None, None, 0, C.byref(n)))
+        ch = np.zeros(n.value, np.uint32)
+        idx = np.zeros(n.value, np.uint64)
+        X = np.zeros((n.value, self.M), np.complex64)
+        if n.value:
+            _check(lib().b2_mcrx_read_symbols(self.h, ch.ctypes.data, idx.ctypes.data, X.ctypes.data, n.value, C.byref(n)))
+        return ch, idx, X
+
+    def read_channelizer(self):
+        nb = _sz(0)
+        _check(lib().b2_mcrx_read_channelizer(self.h, None, 0, C.byref(nb)))
+        out = np.zeros((self.N, nb.value), np.complex64)
+        if nb.value:
+            _check(lib().b2_mcrx_read_channelizer(self.h, out.ctypes.data, out.size, C.byref(nb)))
+        return out
+
+    def stream(self):
+        return lib().b2_mcrx_stream(self.h)
+
+
+class OfdmSync(_FrameSource):
+    """b2_ofdmsync_*: `streams` independent ofdmflexframesync instances (lib/ofdmtxrx.cc:91,625)"""
+    _prefix = "b2_ofdmsync_"
+
+    def __init__(self, M, cp_len, taper_len, p=None, streams=1, device=0, max_batch=0):
+        self.M, self.cp, self.taper, self.streams = M, cp_len, taper_len, streams
+        h = _vp()
+        pp = None if p is None else np.ascontiguousarray(p, np.uint8).ctypes.data
+        _check(lib().b2_ofdmsync_create(M, cp_len, taper_len, pp, streams, device, max_batch, C.byref(h)))
+        self.h = h
+
+    def execute(self, x):
+        """x: [streams, n] complex64"""
+        x = np.ascontiguousarray(x, np.complex64).reshape(self.streams, -1)
+        _check(lib().b2_ofdmsync_execute(self.h, x.ctypes.data, x.shape[1]))
+
+    def execute_device(self, dev_ptr, n, stride):
+        _check(lib().b2_ofdmsync_execute_device(self.h, _ptr(dev_ptr), n, stride))

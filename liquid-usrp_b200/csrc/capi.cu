@@ -1,0 +1,611 @@
+// capi.cu -- implementation of the C ABI declared in include/b200_ofdm.h (receive side):
+// handle objects, device memory, kernel sequencing on one CUDA stream per handle, and the
+// device -> host hand-off of decoded frame records.
+//
+//   b2_mcrx_*     multichannelrx   (lib/multichannelrx.cc:45-195)
+//   b2_ofdmsync_* ofdmflexframesync as used by ofdmtxrx (lib/ofdmtxrx.cc:91,482,625), batched
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "b200_ofdm.h"
+#include "design.h"
+#include "kernels.h"
+#include "capi_util.h"
+
+using namespace b2;
+
+static_assert(sizeof(FrameRec) == sizeof(b2_frame_rec), "FrameRec must mirror b2_frame_rec");
+
+// ================================================================== synchroniser core
+// everything downstream of the channelizer: per-stream state, tables, frame output
+struct SyncCore {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    OfdmPlan plan;
+    FftPlan fftM;
+    unsigned int streams = 0;
+    size_t tmax = 0;                     // max samples per stream per launch
+    // tables
+    DevBuf t_sctype, t_S0, t_S1, t_data, t_pilot, t_pilotx, t_active, t_seq, t_walk, t_B, t_perm, t_tw;
+    // state
+    DevBuf d_st, d_ring, d_G0, d_R, d_penc;
+    size_t penc_cap = 0;
+    // outputs
+    DevBuf d_recs, d_aux, d_arena, d_scratch, d_decoded, d_counters;
+    unsigned int recs_cap = 0;
+    unsigned long long arena_cap = 0;
+    // tap
+    DevBuf d_tapX, d_tapc, d_tapi;
+    unsigned int tap_cap = 0;
+    std::vector<uint32_t> tap_chan; std::vector<uint64_t> tap_index; std::vector<float> tap_X;
+    // host mirrors
+    unsigned int * h_counters = nullptr; // pinned, 8 uints
+    FrameRec * h_recs = nullptr;         // pinned
+    uint8_t * h_payload = nullptr;       // pinned
+    // results waiting for poll()
+    std::vector<FrameRec> ready;
+    std::vector<uint8_t> ready_payloads;
+    // kernel config
+    int sync_threads = 128;
+    size_t sync_smem = 0;
+    int decode_grid = 148;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float last_ms[4] = {0, 0, 0, 0};
+    SyncParams sp;
+
+    int init(unsigned int M, unsigned int cp, unsigned int taper, const unsigned char * p, unsigned int streams_,
+             size_t tmax_, int device_, cudaStream_t st);
+    void destroy();
+    int reset_state();
+    // run sync + decode over in[s*stride + t], t < nsamples; appends results to `ready`
+    int run(const cf * in, size_t in_stride, unsigned int nsamples, bool record_events);
+    int collect();
+    int poll(b2_frame_rec * recs, size_t recs_cap, size_t * n_recs, uint8_t * payloads, size_t payloads_cap, size_t * n_payload_bytes);
+    int set_tap(int enable, size_t max_symbols);
+};
+
+int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const unsigned char * p, unsigned int streams_,
+                   size_t tmax_, int device_, cudaStream_t st)
+{
+    device = device_; stream = st; streams = streams_; tmax = tmax_;
+    if (M < 8 || (M & 1) || cp < 1 || cp > M || taper > cp) return b2_fail(B2_ERR_ARG, "invalid OFDM configuration (M=%u cp=%u taper=%u)", M, cp, taper);
+    if (ofdm_plan(plan, M, cp, taper, p) != 0) return b2_fail(B2_ERR_ARG, "invalid subcarrier allocation");
+    if (M < 16 || M > 4096 || fft_plan(fftM, M) != 0)
+        return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA path needs a power-of-two number of subcarriers in [16, 4096] (got %u)", M);
+    // tables
+    std::vector<cf> B(M);
+    {
+        float phi = (float)plan.backoff * 2.0f * M_PI / (float)M;
+        for (unsigned int i = 0; i < M; i++) { float a = (float)i * phi; B[i] = make_float2(cosf(a), sinf(a)); }
+    }
+    std::vector<uint16_t> walk(4 * 18);
+    {
+        unsigned int Mi, Ni;
+        interleaver_dims(36, Mi, Ni);
+        const unsigned int extra[4] = {0, 2, 4, 8};
+        for (int v = 0; v < 4; v++) {
+            std::vector<uint16_t> w = interleaver_walk(36, Mi, Ni + extra[v]);
+            memcpy(&walk[18 * v], w.data(), 18 * sizeof(uint16_t));
+        }
+    }
+    B2_TRY(t_sctype.upload(plan.p)); B2_TRY(t_S0.upload(plan.S0)); B2_TRY(t_S1.upload(plan.S1));
+    B2_TRY(t_data.upload(plan.data_idx)); B2_TRY(t_pilot.upload(plan.pilot_idx)); B2_TRY(t_pilotx.upload(plan.pilot_x));
+    B2_TRY(t_active.upload(plan.active_idx)); B2_TRY(t_seq.upload(plan.pilot_seq)); B2_TRY(t_walk.upload(walk));
+    B2_TRY(t_B.upload(B)); B2_TRY(t_perm.upload(fftM.perm)); B2_TRY(t_tw.upload(fftM.tw));
+    // state
+    const size_t W = M + cp;
+    penc_cap = ((size_t)fec_enc_len(FEC_HAMMING128, fec_enc_len(FEC_CONV_V27, 65535 + 4)) + 64 + 15) & ~(size_t)15;
+    if (const char * e = getenv("B2_MAX_PAYLOAD")) {
+        unsigned long v = strtoul(e, nullptr, 10);
+        if (v >= 1 && v <= 65535) penc_cap = ((size_t)fec_enc_len(FEC_HAMMING128, fec_enc_len(FEC_CONV_V27, (unsigned int)v + 4)) + 64 + 15) & ~(size_t)15;
+    }
+    B2_TRY(d_st.alloc(sizeof(SyncState) * streams)); B2_TRY(d_ring.alloc(sizeof(cf) * W * streams));
+    B2_TRY(d_G0.alloc(sizeof(cf) * M * streams)); B2_TRY(d_R.alloc(sizeof(cf) * M * streams));
+    B2_TRY(d_penc.alloc(penc_cap * streams));
+    // outputs: a frame needs at least 4 OFDM symbols; payload bits <= 8 per sample
+    recs_cap = (unsigned int)(streams * (tmax / (2 * W) + 4));
+    arena_cap = (unsigned long long)streams * (tmax + 64) + 16ull * recs_cap;
+    B2_TRY(d_recs.alloc(sizeof(FrameRec) * recs_cap)); B2_TRY(d_aux.alloc(sizeof(FrameAux) * recs_cap));
+    B2_TRY(d_arena.alloc(arena_cap)); B2_TRY(d_scratch.alloc(arena_cap)); B2_TRY(d_decoded.alloc(arena_cap));
+    B2_TRY(d_counters.alloc(8 * sizeof(unsigned int)));
+    B2_CUDA(cudaMallocHost(&h_counters, 8 * sizeof(unsigned int)));
+    B2_CUDA(cudaMallocHost(&h_recs, sizeof(FrameRec) * recs_cap));
+    B2_CUDA(cudaMallocHost(&h_payload, arena_cap));
+    for (int i = 0; i < 5; i++) B2_CUDA(cudaEventCreate(&ev[i]));
+
+    memset(&sp, 0, sizeof(sp));
+    sp.M = M; sp.cp = cp; sp.M2 = M / 2; sp.backoff = plan.backoff;
+    sp.M_pilot = plan.M_pilot; sp.M_data = plan.M_data; sp.M_S0 = plan.M_S0; sp.M_S1 = plan.M_S1;
+    sp.thresh = plan.thresh; sp.pilot_sx = plan.pilot_sx; sp.pilot_sxx = plan.pilot_sxx;
+    for (int i = 0; i < 9; i++) sp.qam_alpha[i] = 1.0f;
+    sp.qam_alpha[2] = 1.0f / sqrtf(2.0f); sp.qam_alpha[4] = 1.0f / sqrtf(10.0f);
+    sp.qam_alpha[6] = 1.0f / sqrtf(42.0f); sp.qam_alpha[8] = 1.0f / sqrtf(170.0f);
+    sp.streams = streams;
+    sp.st = d_st.as<SyncState>(); sp.ring = d_ring.as<cf>(); sp.G0 = d_G0.as<cf>(); sp.R = d_R.as<cf>();
+    sp.penc = d_penc.as<uint8_t>(); sp.penc_cap = penc_cap;
+    sp.recs = d_recs.as<FrameRec>(); sp.aux = d_aux.as<FrameAux>(); sp.recs_cap = recs_cap;
+    sp.arena = d_arena.as<uint8_t>(); sp.arena_cap = arena_cap;
+    sp.counters = d_counters.as<unsigned int>();
+    sp.tb.sctype = t_sctype.as<uint8_t>(); sp.tb.S0 = t_S0.as<float>(); sp.tb.S1 = t_S1.as<float>();
+    sp.tb.data_idx = t_data.as<uint16_t>(); sp.tb.pilot_idx = t_pilot.as<uint16_t>(); sp.tb.pilot_x = t_pilotx.as<float>();
+    sp.tb.active_idx = t_active.as<uint16_t>(); sp.tb.pilot_seq = t_seq.as<uint8_t>(); sp.tb.hdr_walk = t_walk.as<uint16_t>();
+    sp.tb.B = t_B.as<cf>();
+    sp.fft.n = fftM.n; sp.fft.npass = fftM.npass;
+    for (unsigned int i = 0; i < fftM.npass; i++) sp.fft.radix[i] = fftM.radix[i];
+    sp.fft.perm = t_perm.as<uint16_t>(); sp.fft.tw = t_tw.as<cf>();
+    sync_smem = sync_smem_bytes(sp);
+    if (sync_smem > 227 * 1024) return b2_fail(B2_ERR_UNSUPPORTED, "M=%u needs %zu bytes of shared memory per stream", M, sync_smem);
+    B2_CUDA(sync_configure(sync_smem));
+    sync_threads = (M >= 512) ? 256 : 128;
+    if (const char * e = getenv("B2_SYNC_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) sync_threads = v; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    decode_grid = sms * 2;
+    return reset_state();
+}
+
+void SyncCore::destroy()
+{
+    if (h_counters) cudaFreeHost(h_counters);
+    if (h_recs) cudaFreeHost(h_recs);
+    if (h_payload) cudaFreeHost(h_payload);
+    h_counters = nullptr; h_recs = nullptr; h_payload = nullptr;
+    for (int i = 0; i < 5; i++) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+}
+
+int SyncCore::reset_state()
+{
+    // ofdmflexframesync_reset on every stream; the sample window is NOT cleared by liquid's
+    // reset, but a freshly created object starts from zeros -- reset_state() is also create
+    std::vector<SyncState> st(streams);
+    for (auto & s : st) sync_state_init(s, plan.M, plan.cp);
+    B2_CUDA(cudaMemcpyAsync(d_st.p, st.data(), sizeof(SyncState) * streams, cudaMemcpyHostToDevice, stream));
+    B2_CUDA(cudaMemsetAsync(d_ring.p, 0, d_ring.bytes, stream));
+    B2_CUDA(cudaMemsetAsync(d_G0.p, 0, d_G0.bytes, stream));
+    B2_CUDA(cudaMemsetAsync(d_R.p, 0, d_R.bytes, stream));
+    B2_CUDA(cudaStreamSynchronize(stream));
+    return B2_OK;
+}
+
+int SyncCore::set_tap(int enable, size_t max_symbols)
+{
+    tap_cap = 0;
+    if (!enable) return B2_OK;
+    B2_TRY(d_tapX.alloc(sizeof(cf) * plan.M * max_symbols));
+    B2_TRY(d_tapc.alloc(sizeof(uint32_t) * max_symbols));
+    B2_TRY(d_tapi.alloc(sizeof(uint64_t) * max_symbols));
+    tap_cap = (unsigned int)max_symbols;
+    return B2_OK;
+}
+
+int SyncCore::run(const cf * in, size_t in_stride, unsigned int nsamples, bool record_events)
+{
+    if (nsamples == 0) return B2_OK;
+    if (nsamples > tmax) return b2_fail(B2_ERR_ARG, "internal: launch of %u samples exceeds tmax %zu", nsamples, tmax);
+    B2_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(unsigned int), stream));
+    SyncParams q = sp;
+    q.in = in; q.in_stride = in_stride; q.nsamples = nsamples;
+    q.tap_cap = tap_cap;
+    q.tap_X = d_tapX.as<cf>(); q.tap_chan = d_tapc.as<uint32_t>(); q.tap_index = d_tapi.as<unsigned long long>();
+    if (record_events) B2_CUDA(cudaEventRecord(ev[1], stream));
+    B2_CUDA(sync_launch(q, sync_threads, sync_smem, stream));
+    if (record_events) B2_CUDA(cudaEventRecord(ev[2], stream));
+    PacketParams pp;
+    pp.recs = d_recs.as<FrameRec>(); pp.aux = d_aux.as<FrameAux>(); pp.counters = d_counters.as<unsigned int>();
+    pp.first_rec = 0;
+    pp.arena = d_arena.as<uint8_t>(); pp.scratch = d_scratch.as<uint8_t>(); pp.decoded = d_decoded.as<uint8_t>();
+    B2_CUDA(packet_decode_launch(pp, decode_grid, stream));
+    if (record_events) B2_CUDA(cudaEventRecord(ev[3], stream));
+    return collect();
+}
+
+int SyncCore::collect()
+{
+    B2_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    B2_CUDA(cudaStreamSynchronize(stream));
+    if (h_counters[1]) return b2_fail(B2_ERR_OVERFLOW, "internal: frame output arena overflow");
+    const unsigned int nrec = h_counters[0];
+    const unsigned long long used = *(const unsigned long long *)(h_counters + 2);
+    const unsigned int ntap = std::min(h_counters[4], tap_cap);
+    if (nrec) {
+        B2_CUDA(cudaMemcpyAsync(h_recs, d_recs.p, sizeof(FrameRec) * nrec, cudaMemcpyDeviceToHost, stream));
+        if (used) B2_CUDA(cudaMemcpyAsync(h_payload, d_decoded.p, used, cudaMemcpyDeviceToHost, stream));
+    }
+    if (ntap) {
+        size_t o = tap_chan.size();
+        tap_chan.resize(o + ntap); tap_index.resize(o + ntap); tap_X.resize((o + ntap) * 2 * (size_t)plan.M);
+        B2_CUDA(cudaMemcpyAsync(&tap_chan[o], d_tapc.p, sizeof(uint32_t) * ntap, cudaMemcpyDeviceToHost, stream));
+        B2_CUDA(cudaMemcpyAsync(&tap_index[o], d_tapi.p, sizeof(uint64_t) * ntap, cudaMemcpyDeviceToHost, stream));
+        B2_CUDA(cudaMemcpyAsync(&tap_X[o * 2 * (size_t)plan.M], d_tapX.p, sizeof(cf) * plan.M * ntap, cudaMemcpyDeviceToHost, stream));
+    }
+    if (nrec || ntap) B2_CUDA(cudaStreamSynchronize(stream));
+    if (nrec) {
+        // the reference fires callbacks in order of completion block, then channel
+        std::vector<unsigned int> order(nrec);
+        for (unsigned int i = 0; i < nrec; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](unsigned int a, unsigned int b) {
+            if (h_recs[a].complete_index != h_recs[b].complete_index) return h_recs[a].complete_index < h_recs[b].complete_index;
+            return h_recs[a].channel < h_recs[b].channel;
+        });
+        for (unsigned int i = 0; i < nrec; i++) {
+            FrameRec r = h_recs[order[i]];
+            size_t o = ready_payloads.size();
+            if (r.header_valid && r.payload_len)
+                ready_payloads.insert(ready_payloads.end(), h_payload + r.payload_offset, h_payload + r.payload_offset + r.payload_len);
+            r.payload_offset = o;
+            ready.push_back(r);
+        }
+    }
+    return B2_OK;
+}
+
+int SyncCore::poll(b2_frame_rec * recs, size_t cap, size_t * n_recs, uint8_t * payloads, size_t payloads_cap, size_t * n_payload_bytes)
+{
+    if (n_recs) *n_recs = ready.size();
+    if (n_payload_bytes) *n_payload_bytes = ready_payloads.size();
+    if (!recs) return B2_OK;
+    if (cap < ready.size() || (payloads_cap < ready_payloads.size())) return b2_fail(B2_ERR_OVERFLOW, "poll buffers too small");
+    if (!ready.empty()) memcpy(recs, ready.data(), ready.size() * sizeof(FrameRec));
+    if (payloads && !ready_payloads.empty()) memcpy(payloads, ready_payloads.data(), ready_payloads.size());
+    ready.clear(); ready_payloads.clear();
+    return B2_OK;
+}
+
+// ================================================================== multichannelrx
+struct b2_mcrx_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    unsigned int N = 0, K = 0, lgK = 0, P = 14, TB = 8;
+    size_t max_batch = 0;
+    FftPlan fftK;
+    DevBuf t_taps, t_perm, t_tw;
+    DevBuf d_stage;                      // [hist (P-1)K][carry < K][new samples <= max_batch]
+    DevBuf d_tail;                       // scratch for moving the stream tail to the front
+    DevBuf d_chan;                       // channelizer output [N][tcap]
+    size_t tcap = 0;
+    size_t hist_len = 0, carry = 0;
+    uint32_t nco_theta = 0, nco_dtheta = 0;      // phase of the next incoming sample
+    size_t an_smem = 0;
+    int an_grid = 148;
+    unsigned int last_blocks = 0;
+    SyncCore core;
+};
+
+static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device);
+
+extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, unsigned int taper, const unsigned char * p,
+                              int device, size_t max_batch, b2_mcrx ** out)
+{
+    if (!out) return b2_fail(B2_ERR_ARG, "null output pointer");
+    *out = nullptr;
+    // same argument checks as multichannelrx::multichannelrx (lib/multichannelrx.cc:54-66)
+    if (N < 1) return b2_fail(B2_ERR_ARG, "must have at least one channel");
+    if (M < 8) return b2_fail(B2_ERR_ARG, "number of subcarriers must be at least 8");
+    if (cp < 1) return b2_fail(B2_ERR_ARG, "cyclic prefix length must be at least 1");
+    if (taper > cp) return b2_fail(B2_ERR_ARG, "taper length cannot exceed cyclic prefix length");
+    unsigned int K = 2 * N;
+    if ((K & (K - 1)) || K > 1024)
+        return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA channelizer needs a power-of-two channel count <= 512 (got %u)", N);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return b2_fail(B2_ERR_CUDA, "no CUDA device available");
+    if (device < 0 || device >= ndev) return b2_fail(B2_ERR_ARG, "invalid device ordinal %d", device);
+    B2_CUDA(cudaSetDevice(device));
+    b2_mcrx * q = new b2_mcrx_s;
+    q->device = device;
+    q->N = N; q->K = K; q->lgK = ceil_log2(K);
+    q->TB = std::max(4u, 4096u / K);
+    if (max_batch == 0) max_batch = (size_t)1 << 22;
+    max_batch = std::max(max_batch, (size_t)4 * K);
+    q->max_batch = max_batch;
+    int rc = B2_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaStreamCreate failed"); break; }
+        // firpfbch_crcf_create_kaiser(LIQUID_ANALYZER, 2N, m=7, As=60): lib/multichannelrx.cc:89-91
+        std::vector<float> h = firpfbch_prototype(K, 7, 60.0f);
+        fft_plan(q->fftK, K);
+        if ((rc = q->t_taps.upload(h)) || (rc = q->t_perm.upload(q->fftK.perm)) || (rc = q->t_tw.upload(q->fftK.tw))) break;
+        q->hist_len = (size_t)(q->P - 1) * K;
+        if ((rc = q->d_stage.alloc(sizeof(cf) * (q->hist_len + K + max_batch + K)))) break;
+        if ((rc = q->d_tail.alloc(sizeof(cf) * (q->hist_len + K)))) break;
+        q->tcap = ((max_batch + K) / K + 2 + 1) & ~(size_t)1;
+        if ((rc = q->d_chan.alloc(sizeof(cf) * q->tcap * N))) break;
+        // NCO: lib/multichannelrx.cc:98-100
+        float offset = -0.5f * (float)(N - 1) / (float)N * M_PI;
+        q->nco_dtheta = nco_constrain(offset);
+        q->nco_theta = 0;
+        AnalyzerParams ap;
+        memset(&ap, 0, sizeof(ap));
+        ap.K = K; ap.P = q->P; ap.TB = q->TB;
+        q->an_smem = analyzer_smem_bytes(ap);
+        if (q->an_smem > 227 * 1024) { rc = b2_fail(B2_ERR_UNSUPPORTED, "channelizer tile does not fit shared memory"); break; }
+        if (analyzer_configure(q->an_smem) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        int per_sm = std::max(1, (int)((227 * 1024) / (q->an_smem + 1024)));
+        q->an_grid = sms * std::min(per_sm, 2);
+        if ((rc = q->core.init(M, cp, taper, p, N, q->tcap, device, q->stream))) break;
+        B2_CUDA(cudaMemsetAsync(q->d_stage.p, 0, q->d_stage.bytes, q->stream));
+        B2_CUDA(cudaStreamSynchronize(q->stream));
+    } while (0);
+    if (rc) { b2_mcrx_destroy(q); return rc; }
+    *out = q;
+    return B2_OK;
+}
+
+extern "C" int b2_mcrx_destroy(b2_mcrx * q)
+{
+    if (!q) return B2_OK;
+    cudaSetDevice(q->device);
+    if (q->stream) cudaStreamSynchronize(q->stream);
+    q->core.destroy();
+    if (q->stream) cudaStreamDestroy(q->stream);
+    delete q;
+    return B2_OK;
+}
+
+// multichannelrx::Reset (lib/multichannelrx.cc:135-153): framesyncs + channelizer windows +
+// buffer_index; the NCO keeps running (its reset is commented out at :144)
+extern "C" int b2_mcrx_reset(b2_mcrx * q)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    B2_CUDA(cudaSetDevice(q->device));
+    B2_CUDA(cudaMemsetAsync(q->d_stage.p, 0, sizeof(cf) * (q->hist_len + q->K), q->stream));
+    q->carry = 0;
+    return q->core.reset_state();
+}
+
+static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device)
+{
+    const unsigned int K = q->K;
+    cf * stage = q->d_stage.as<cf>();
+    const size_t front = q->hist_len + q->carry;             // samples already at the front of the stage
+    const size_t total = q->carry + n;
+    const size_t T = total / K, leftover = total % K;
+    const bool direct = on_device && q->carry == 0 && T > 0 && (((uintptr_t)x) & 15) == 0;
+    if (!direct)
+        B2_CUDA(cudaMemcpyAsync(stage + front, x, sizeof(cf) * n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, q->stream));
+    B2_CUDA(cudaEventRecord(q->core.ev[0], q->stream));
+    if (T > 0) {
+        AnalyzerParams ap;
+        memset(&ap, 0, sizeof(ap));
+        ap.seg0 = stage;
+        ap.rows0 = direct ? q->P - 1 : 0xffffffffu;
+        ap.seg1 = direct ? (const cf *)x : stage;
+        ap.K = K; ap.lgK = q->lgK; ap.N = q->N; ap.P = q->P; ap.TB = q->TB;
+        ap.nblocks = (unsigned int)T;
+        ap.taps = q->t_taps.as<float>();
+        ap.dtheta = q->nco_dtheta;
+        ap.theta0 = q->nco_theta - (uint32_t)(q->hist_len + q->carry) * q->nco_dtheta;
+        ap.out = q->d_chan.as<cf>(); ap.out_stride = q->tcap; ap.out_col0 = 0;
+        ap.fft.n = K; ap.fft.npass = q->fftK.npass;
+        for (unsigned int i = 0; i < q->fftK.npass; i++) ap.fft.radix[i] = q->fftK.radix[i];
+        ap.fft.perm = q->t_perm.as<uint16_t>(); ap.fft.tw = q->t_tw.as<cf>();
+        B2_CUDA(analyzer_launch(ap, q->an_grid, q->an_smem, q->stream));
+    }
+    q->last_blocks = (unsigned int)T;
+    // keep the last (P-1)*K + leftover samples of the stream at the front of the stage
+    {
+        const size_t keep = q->hist_len + leftover;
+        const size_t stream_len = front + n;                  // logical samples in [stage front | new]
+        if (direct) {
+            // logical stream = stage[0..hist_len) ++ x[0..n)
+            if (n >= keep) {
+                B2_CUDA(cudaMemcpyAsync(stage, (const cf *)x + (n - keep), sizeof(cf) * keep, cudaMemcpyDeviceToDevice, q->stream));
+            } else {
+                cf * tail = q->d_tail.as<cf>();
+                size_t from_hist = keep - n;
+                B2_CUDA(cudaMemcpyAsync(tail, stage + (q->hist_len - from_hist), sizeof(cf) * from_hist, cudaMemcpyDeviceToDevice, q->stream));
+                B2_CUDA(cudaMemcpyAsync(tail + from_hist, x, sizeof(cf) * n, cudaMemcpyDeviceToDevice, q->stream));
+                B2_CUDA(cudaMemcpyAsync(stage, tail, sizeof(cf) * keep, cudaMemcpyDeviceToDevice, q->stream));
+            }
+        } else if (T > 0) {
+            const cf * src = stage + (stream_len - keep);
+            if (stream_len - keep >= keep) {
+                B2_CUDA(cudaMemcpyAsync(stage, src, sizeof(cf) * keep, cudaMemcpyDeviceToDevice, q->stream));
+            } else {
+                cf * tail = q->d_tail.as<cf>();
+                B2_CUDA(cudaMemcpyAsync(tail, src, sizeof(cf) * keep, cudaMemcpyDeviceToDevice, q->stream));
+                B2_CUDA(cudaMemcpyAsync(stage, tail, sizeof(cf) * keep, cudaMemcpyDeviceToDevice, q->stream));
+            }
+        }
+        q->carry = leftover;
+        q->nco_theta += (uint32_t)n * q->nco_dtheta;
+    }
+    int rc = q->core.run(q->d_chan.as<cf>(), q->tcap, (unsigned int)T, true);
+    if (rc) return rc;
+    B2_CUDA(cudaEventRecord(q->core.ev[4], q->stream));
+    B2_CUDA(cudaEventSynchronize(q->core.ev[4]));
+    if (T > 0) {
+        cudaEventElapsedTime(&q->core.last_ms[0], q->core.ev[0], q->core.ev[1]);
+        cudaEventElapsedTime(&q->core.last_ms[1], q->core.ev[1], q->core.ev[2]);
+        cudaEventElapsedTime(&q->core.last_ms[2], q->core.ev[2], q->core.ev[3]);
+        cudaEventElapsedTime(&q->core.last_ms[3], q->core.ev[0], q->core.ev[4]);
+    }
+    return B2_OK;
+}
+
+static int mcrx_execute_any(b2_mcrx * q, const float * x, size_t n, bool on_device)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    if (n == 0) return B2_OK;
+    if (!x) return b2_fail(B2_ERR_ARG, "null sample pointer");
+    B2_CUDA(cudaSetDevice(q->device));
+    size_t done = 0;
+    while (done < n) {
+        size_t c = std::min(n - done, q->max_batch);
+        int rc = mcrx_process(q, x + 2 * done, c, on_device);
+        if (rc) return rc;
+        done += c;
+    }
+    return B2_OK;
+}
+extern "C" int b2_mcrx_execute(b2_mcrx * q, const float * x_host, size_t n) { return mcrx_execute_any(q, x_host, n, false); }
+extern "C" int b2_mcrx_execute_device(b2_mcrx * q, const float * x_dev, size_t n) { return mcrx_execute_any(q, x_dev, n, true); }
+
+extern "C" int b2_mcrx_poll(b2_mcrx * q, b2_frame_rec * recs, size_t recs_cap, size_t * n_recs,
+                            uint8_t * payloads, size_t payloads_cap, size_t * n_payload_bytes)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    return q->core.poll(recs, recs_cap, n_recs, payloads, payloads_cap, n_payload_bytes);
+}
+
+extern "C" int b2_mcrx_tap_symbols(b2_mcrx * q, int enable, size_t max_symbols)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    B2_CUDA(cudaSetDevice(q->device));
+    return q->core.set_tap(enable, max_symbols);
+}
+
+static int core_read_symbols(SyncCore & c, uint32_t * channel, uint64_t * index, float * X, size_t cap, size_t * n)
+{
+    size_t have = c.tap_chan.size();
+    if (n) *n = have;
+    if (!channel) return B2_OK;
+    if (cap < have) return b2_fail(B2_ERR_OVERFLOW, "symbol buffers too small");
+    if (have) {
+        memcpy(channel, c.tap_chan.data(), have * sizeof(uint32_t));
+        memcpy(index, c.tap_index.data(), have * sizeof(uint64_t));
+        memcpy(X, c.tap_X.data(), c.tap_X.size() * sizeof(float));
+    }
+    c.tap_chan.clear(); c.tap_index.clear(); c.tap_X.clear();
+    return B2_OK;
+}
+extern "C" int b2_mcrx_read_symbols(b2_mcrx * q, uint32_t * channel, uint64_t * index, float * X, size_t cap, size_t * n)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    return core_read_symbols(q->core, channel, index, X, cap, n);
+}
+
+extern "C" int b2_mcrx_last_timing(b2_mcrx * q, float ms[4])
+{
+    if (!q || !ms) return b2_fail(B2_ERR_ARG, "null argument");
+    for (int i = 0; i < 4; i++) ms[i] = q->core.last_ms[i];
+    return B2_OK;
+}
+
+extern "C" int b2_mcrx_read_channelizer(b2_mcrx * q, float * out, size_t cap_samples, size_t * n_blocks)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    if (n_blocks) *n_blocks = q->last_blocks;
+    if (!out) return B2_OK;
+    if (cap_samples < (size_t)q->last_blocks * q->N) return b2_fail(B2_ERR_OVERFLOW, "buffer too small");
+    B2_CUDA(cudaSetDevice(q->device));
+    if (q->last_blocks)
+        B2_CUDA(cudaMemcpy2D(out, sizeof(cf) * q->last_blocks, q->d_chan.p, sizeof(cf) * q->tcap,
+                             sizeof(cf) * q->last_blocks, q->N, cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+
+extern "C" void * b2_mcrx_stream(b2_mcrx * q) { return q ? (void *)q->stream : nullptr; }
+
+// ================================================================== batched single-link synchroniser
+struct b2_ofdmsync_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    unsigned int streams = 0;
+    size_t max_batch = 0;
+    DevBuf d_in;
+    SyncCore core;
+};
+
+extern "C" int b2_ofdmsync_create(unsigned int M, unsigned int cp, unsigned int taper, const unsigned char * p,
+                                  unsigned int streams, int device, size_t max_batch, b2_ofdmsync ** out)
+{
+    if (!out) return b2_fail(B2_ERR_ARG, "null output pointer");
+    *out = nullptr;
+    if (streams < 1) return b2_fail(B2_ERR_ARG, "need at least one stream");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return b2_fail(B2_ERR_CUDA, "no CUDA device available");
+    if (device < 0 || device >= ndev) return b2_fail(B2_ERR_ARG, "invalid device ordinal %d", device);
+    B2_CUDA(cudaSetDevice(device));
+    b2_ofdmsync * q = new b2_ofdmsync_s;
+    q->device = device; q->streams = streams;
+    if (max_batch == 0) max_batch = (size_t)1 << 20;
+    q->max_batch = max_batch;
+    int rc = B2_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaStreamCreate failed"); break; }
+        if ((rc = q->d_in.alloc(sizeof(cf) * max_batch * streams))) break;
+        if ((rc = q->core.init(M, cp, taper, p, streams, max_batch, device, q->stream))) break;
+    } while (0);
+    if (rc) { b2_ofdmsync_destroy(q); return rc; }
+    *out = q;
+    return B2_OK;
+}
+extern "C" int b2_ofdmsync_destroy(b2_ofdmsync * q)
+{
+    if (!q) return B2_OK;
+    cudaSetDevice(q->device);
+    if (q->stream) cudaStreamSynchronize(q->stream);
+    q->core.destroy();
+    if (q->stream) cudaStreamDestroy(q->stream);
+    delete q;
+    return B2_OK;
+}
+extern "C" int b2_ofdmsync_reset(b2_ofdmsync * q)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    B2_CUDA(cudaSetDevice(q->device));
+    return q->core.reset_state();
+}
+static int ofdmsync_run(b2_ofdmsync * q, const cf * in, size_t stride, size_t n)
+{
+    B2_CUDA(cudaEventRecord(q->core.ev[0], q->stream));
+    int rc = q->core.run(in, stride, (unsigned int)n, true);
+    if (rc) return rc;
+    B2_CUDA(cudaEventRecord(q->core.ev[4], q->stream));
+    B2_CUDA(cudaEventSynchronize(q->core.ev[4]));
+    q->core.last_ms[0] = 0.f;
+    cudaEventElapsedTime(&q->core.last_ms[1], q->core.ev[1], q->core.ev[2]);
+    cudaEventElapsedTime(&q->core.last_ms[2], q->core.ev[2], q->core.ev[3]);
+    cudaEventElapsedTime(&q->core.last_ms[3], q->core.ev[0], q->core.ev[4]);
+    return B2_OK;
+}
+extern "C" int b2_ofdmsync_execute(b2_ofdmsync * q, const float * x_host, size_t n)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    if (n == 0) return B2_OK;
+    if (!x_host) return b2_fail(B2_ERR_ARG, "null sample pointer");
+    B2_CUDA(cudaSetDevice(q->device));
+    size_t done = 0;
+    while (done < n) {
+        size_t c = std::min(n - done, q->max_batch);
+        B2_CUDA(cudaMemcpy2DAsync(q->d_in.p, sizeof(cf) * c, x_host + 2 * done, sizeof(cf) * n, sizeof(cf) * c, q->streams,
+                                  cudaMemcpyHostToDevice, q->stream));
+        int rc = ofdmsync_run(q, q->d_in.as<cf>(), c, c);
+        if (rc) return rc;
+        done += c;
+    }
+    return B2_OK;
+}
+extern "C" int b2_ofdmsync_execute_device(b2_ofdmsync * q, const float * x_dev, size_t n, size_t stride)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    if (n == 0) return B2_OK;
+    if (!x_dev) return b2_fail(B2_ERR_ARG, "null sample pointer");
+    B2_CUDA(cudaSetDevice(q->device));
+    size_t done = 0;
+    while (done < n) {
+        size_t c = std::min(n - done, q->max_batch);
+        int rc = ofdmsync_run(q, (const cf *)x_dev + done, stride, c);
+        if (rc) return rc;
+        done += c;
+    }
+    return B2_OK;
+}
+extern "C" int b2_ofdmsync_poll(b2_ofdmsync * q, b2_frame_rec * recs, size_t recs_cap, size_t * n_recs,
+                                uint8_t * payloads, size_t payloads_cap, size_t * n_payload_bytes)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    return q->core.poll(recs, recs_cap, n_recs, payloads, payloads_cap, n_payload_bytes);
+}
+extern "C" int b2_ofdmsync_last_timing(b2_ofdmsync * q, float ms[4])
+{
+    if (!q || !ms) return b2_fail(B2_ERR_ARG, "null argument");
+    for (int i = 0; i < 4; i++) ms[i] = q->core.last_ms[i];
+    return B2_OK;
+}

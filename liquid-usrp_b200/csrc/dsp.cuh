@@ -1,0 +1,214 @@
+// dsp.cuh -- device-side building blocks shared by the kernels: complex helpers, the uint32-phase
+// NCO (nco_crcf, LIQUID_VCO; lib/multichannelrx.cc:99-100,163-164), a mixed-radix in-place
+// shared-memory FFT (the K-point transform inside firpfbch_crcf_*_execute and the M-point
+// transform inside ofdmframe{gen,sync}), warp/block reductions for the S0/S1 correlators.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2 {
+
+typedef float2 cf;
+
+__device__ __forceinline__ cf cmul(cf a, cf b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cf cmulc(cf a, cf b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); } // a*conj(b)
+__device__ __forceinline__ cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cf cscale(cf a, float s) { return make_float2(a.x * s, a.y * s); }
+
+// e^{+j theta} for a uint32 phase (2*pi <-> 2^32): cos/sin of (int32)theta * pi / 2^31
+__device__ __forceinline__ cf nco_cexp(uint32_t theta)
+{
+    float t = (float)((double)(int32_t)theta * (3.14159265358979323846 / 2147483648.0));
+    float s, c;
+    sincosf(t, &s, &c);
+    return make_float2(c, s);
+}
+// cheaper variant: same phase in half-turns, evaluated by sincospif (exact argument reduction)
+__device__ __forceinline__ cf nco_cexp_pi(uint32_t theta)
+{
+    float s, c;
+    sincospif((float)((double)(int32_t)theta * (1.0 / 2147483648.0)), &s, &c);
+    return make_float2(c, s);
+}
+__device__ __forceinline__ cf mix_down(cf x, cf w) { return make_float2(x.x * w.x + x.y * w.y, x.y * w.x - x.x * w.y); } // x*conj(w)
+__device__ __forceinline__ cf mix_up(cf x, cf w) { return cmul(x, w); }
+
+// radians -> uint32 phase, same rounding as the host (design.h nco_constrain)
+__device__ __forceinline__ uint32_t nco_constrain_dev(float theta)
+{
+    double p = (double)theta * 0.15915494309189535;
+    double f = p - floor(p);
+    double u = rint(f * 4294967296.0);
+    return (uint32_t)((unsigned long long)u & 0xffffffffull);
+}
+__device__ __forceinline__ float nco_freq_dev(uint32_t dtheta)
+{
+    return (float)((double)(int32_t)dtheta * (3.14159265358979323846 / 2147483648.0));
+}
+
+// ------------------------------------------------------------------ small DFT butterflies
+// DIR = -1 forward (e^{-j}), +1 backward (e^{+j}); all unnormalised
+template <int DIR> __device__ __forceinline__ cf mul_j(cf a)   // multiply by DIR*j
+{
+    return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+}
+template <int DIR> __device__ __forceinline__ void dft2(cf & a, cf & b)
+{
+    cf t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+template <int DIR> __device__ __forceinline__ void dft4(cf * v)
+{
+    cf a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+    cf a2 = cadd(v[1], v[3]), a3 = mul_j<DIR>(csub(v[1], v[3]));
+    v[0] = cadd(a0, a2); v[2] = csub(a0, a2);
+    v[1] = cadd(a1, a3); v[3] = csub(a1, a3);
+}
+template <int DIR> __device__ __forceinline__ void dft8(cf * v)
+{
+    const float h = 0.70710678118654752440f;
+    // two interleaved radix-4 on even / odd elements, then combine with w8^k
+    cf e[4] = {v[0], v[2], v[4], v[6]};
+    cf o[4] = {v[1], v[3], v[5], v[7]};
+    dft4<DIR>(e);
+    dft4<DIR>(o);
+    // w8^1 = (1 + DIR*j)/sqrt2, w8^2 = DIR*j, w8^3 = (-1 + DIR*j)/sqrt2
+    cf t1 = DIR < 0 ? make_float2((o[1].x + o[1].y) * h, (o[1].y - o[1].x) * h)
+                    : make_float2((o[1].x - o[1].y) * h, (o[1].y + o[1].x) * h);
+    cf t2 = mul_j<DIR>(o[2]);
+    cf t3 = DIR < 0 ? make_float2((-o[3].x + o[3].y) * h, (-o[3].y - o[3].x) * h)
+                    : make_float2((-o[3].x - o[3].y) * h, (-o[3].y + o[3].x) * h);
+    v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], t1);   v[5] = csub(e[1], t1);
+    v[2] = cadd(e[2], t2);   v[6] = csub(e[2], t2);
+    v[3] = cadd(e[3], t3);   v[7] = csub(e[3], t3);
+}
+
+// skewed shared-memory index (one pad element per 32) used where the access stride is a
+// multiple of the bank count (channelizer FFT rows)
+template <int PAD> __device__ __forceinline__ unsigned int phys(unsigned int i) { return PAD ? i + (i >> 5) : i; }
+
+struct FftDev {
+    unsigned int n, npass;
+    unsigned int radix[12];
+    const uint16_t * perm;     // input permutation (device or shared)
+    const cf * tw;             // forward twiddles e^{-j 2 pi k / n}
+};
+
+// one radix-R pass over `nfft` transforms of length n laid out back to back in `buf` (row
+// stride `ld` elements); L = sub-transform length after this pass
+template <int R, int DIR, int PAD>
+__device__ __forceinline__ void fft_pass(cf * buf, unsigned int ld, unsigned int nfft, unsigned int n, unsigned int L,
+                                         const cf * __restrict__ tw, unsigned int tid, unsigned int nthreads)
+{
+    const unsigned int s = L / R;                 // stride between butterfly inputs
+    const unsigned int per = n / R;               // butterflies per transform
+    const unsigned int tstep = n / L;             // twiddle index step: w_L^j = tw[j * n/L]
+    for (unsigned int w = tid; w < per * nfft; w += nthreads) {
+        unsigned int f = w / per, b = w - f * per;
+        unsigned int blk = b / s, j = b - blk * s;
+        cf * x = buf + (size_t)f * ld;
+        const unsigned int i0 = blk * L + j;
+        cf v[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = x[phys<PAD>(i0 + r * s)];
+        if (s > 1) {
+#pragma unroll
+            for (int r = 1; r < R; r++) {
+                cf t = tw[(j * r * tstep) & (n - 1)];
+                if (DIR > 0) t.y = -t.y;
+                v[r] = cmul(v[r], t);
+            }
+        }
+        if (R == 2) dft2<DIR>(v[0], v[1]);
+        else if (R == 4) dft4<DIR>(v);
+        else dft8<DIR>(v);
+#pragma unroll
+        for (int r = 0; r < R; r++) x[phys<PAD>(i0 + r * s)] = v[r];
+    }
+}
+
+// in-place DIT over data already stored in permuted order; natural-order output.
+// All threads of the CTA must call; ends with a __syncthreads().
+template <int DIR, int PAD>
+__device__ __forceinline__ void fft_inplace(cf * buf, unsigned int ld, unsigned int nfft, const FftDev & f,
+                                            unsigned int tid, unsigned int nthreads)
+{
+    unsigned int L = 1;
+    for (unsigned int t = 0; t < f.npass; t++) {
+        unsigned int R = f.radix[t];
+        L *= R;
+        if (R == 8) fft_pass<8, DIR, PAD>(buf, ld, nfft, f.n, L, f.tw, tid, nthreads);
+        else if (R == 4) fft_pass<4, DIR, PAD>(buf, ld, nfft, f.n, L, f.tw, tid, nthreads);
+        else fft_pass<2, DIR, PAD>(buf, ld, nfft, f.n, L, f.tw, tid, nthreads);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ reductions
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// block-wide sum of a complex value; scratch >= 2*32 floats; result broadcast to all threads.
+// fixed tree: lane butterflies, then warp partials summed in warp order.
+__device__ __forceinline__ cf block_sum_cf(cf v, float * scratch, unsigned int tid, unsigned int nthreads)
+{
+    v.x = warp_sum(v.x);
+    v.y = warp_sum(v.y);
+    unsigned int nw = (nthreads + 31) >> 5;
+    __syncthreads();
+    if ((tid & 31) == 0) { scratch[2 * (tid >> 5)] = v.x; scratch[2 * (tid >> 5) + 1] = v.y; }
+    __syncthreads();
+    cf r = make_float2(0.f, 0.f);
+    for (unsigned int w = 0; w < nw; w++) { r.x += scratch[2 * w]; r.y += scratch[2 * w + 1]; }
+    return r;
+}
+
+// ------------------------------------------------------------------ mbarrier + bulk async copy (TMA unit, 1-D)
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t * bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t * bar, unsigned int parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, unsigned int parity)
+{
+    while (!mbar_try_wait(bar, parity)) { }
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0, 16 B aligned)
+__device__ __forceinline__ void bulk_g2s(void * dst_smem, const void * src_gmem, unsigned int bytes, uint64_t * bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+} // namespace b2

@@ -1,0 +1,125 @@
+// kernels.h -- launch interfaces between the C ABI (capi.cu) and the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "dsp.cuh"
+
+namespace b2 {
+
+// ------------------------------------------------------------------ analysis channelizer
+// NCO mix-down + firpfbch_crcf analyzer (lib/multichannelrx.cc:163-164,188), keeping output
+// channels 0..N-1 (lib/multichannelrx.cc:193-194), written channel-major.
+struct AnalyzerParams {
+    const cf * seg0;            // logical input rows [0, rows0): seg0 + row*K
+    unsigned int rows0;
+    const cf * seg1;            // logical input rows [rows0, ...): seg1 + (row-rows0)*K
+    unsigned int K, lgK, N, P;  // filterbank size (= 1<<lgK), channels kept, taps per branch
+    unsigned int TB;            // blocks per tile (multiple of JB)
+    unsigned int nblocks;       // output blocks this launch; block b reads rows b .. b+P-1
+    const float * taps;         // [P][K]: taps[n*K + i] = h[i + n*K]
+    uint32_t theta0, dtheta;    // NCO phase of logical sample 0, phase step per sample
+    cf * out;                   // out[c*out_stride + out_col0 + b]
+    size_t out_stride, out_col0;
+    FftDev fft;                 // K-point plan (perm / tw in global memory)
+};
+size_t analyzer_smem_bytes(const AnalyzerParams & p);
+cudaError_t analyzer_configure(size_t smem_bytes);
+cudaError_t analyzer_launch(const AnalyzerParams & p, int grid, size_t smem_bytes, cudaStream_t st);
+
+// ------------------------------------------------------------------ per-stream OFDM synchroniser
+// One CTA walks one stream (channel) through the ofdmflexframesync state machine
+// (lib/multichannelrx.cc:194 -> liquid ofdmframesync/ofdmflexframesync).
+enum { ST_SEEK = 0, ST_S0A, ST_S0B, ST_S1, ST_RX };
+enum { FS_HEADER = 0, FS_PAYLOAD };
+
+struct SyncState {              // persistent per stream, lives in global memory
+    int32_t  state, timer;
+    uint32_t num_symbols;
+    uint32_t nco_theta, nco_dtheta;
+    float    g0;
+    float    s_hat0_re, s_hat0_im;
+    float    phi_prime, p1_prime;
+    uint32_t pilot_pos;         // position in the 255-periodic pilot sequence
+    uint32_t ring_head;         // index of the oldest sample in the window ring
+    int32_t  fstate;
+    uint32_t header_sym_idx, payload_sym_idx;
+    float    evm_hat, evm_db;
+    uint32_t ms_payload, bps_payload, payload_len, check, fec0, fec1;
+    uint32_t payload_enc_len, payload_mod_len;
+    uint64_t sample_index;      // index of the next sample to be pushed
+    uint64_t detect_index;
+    uint8_t  header_bits[36];
+    uint8_t  header_dec[20];
+};
+
+struct FrameRec {               // same layout as b2_frame_rec (include/b200_ofdm.h)
+    uint32_t channel;
+    int32_t  header_valid, payload_valid;
+    uint32_t payload_len;
+    uint8_t  header[8];
+    float    evm, rssi, cfo;
+    uint32_t mod_scheme, mod_bps, check, fec0, fec1;
+    uint64_t detect_index, complete_index;
+    uint64_t payload_offset;    // device: byte offset of the encoded payload in the arena
+};
+
+struct FrameAux {               // device-only companion of FrameRec
+    uint32_t enc_len;           // encoded payload bytes in the arena
+    uint32_t pad;
+};
+
+struct SyncTables {             // read-only, global memory
+    const uint8_t * sctype;     // [M]
+    const float * S0, * S1;     // [M] +-1/0
+    const uint16_t * data_idx;  // [M_data]
+    const uint16_t * pilot_idx; // [M_pilot] fft-shifted visiting order
+    const float * pilot_x;      // [M_pilot]
+    const uint16_t * active_idx;// [M_pilot+M_data] fft-shifted visiting order
+    const uint8_t * pilot_seq;  // [255]
+    const uint16_t * hdr_walk;  // [4][18] header de-interleaver walks (n = 36)
+    const cf * B;               // [M] e^{j 2 pi backoff i / M}
+};
+
+struct SyncParams {
+    unsigned int M, cp, M2, backoff;
+    unsigned int M_pilot, M_data, M_S0, M_S1;
+    float thresh, pilot_sx, pilot_sxx;
+    float qam_alpha[9];         // 1/sqrt(2,10,42,170) at index bps = 2,4,6,8
+    unsigned int streams;
+    const cf * in;              // in[s*in_stride + t], t < nsamples
+    size_t in_stride;
+    unsigned int nsamples;
+    SyncState * st;             // [streams]
+    cf * ring;                  // [streams][M+cp]
+    cf * G0;                    // [streams][M]
+    cf * R;                     // [streams][M]
+    uint8_t * penc;             // [streams][penc_cap] in-progress encoded payload
+    size_t penc_cap;
+    // outputs
+    FrameRec * recs; FrameAux * aux; unsigned int recs_cap;
+    uint8_t * arena; unsigned long long arena_cap;
+    unsigned int * counters;    // [0] n_recs, [1] overflow flag, [2..3] arena bytes (u64), [4] n_tap
+    // debug tap
+    cf * tap_X; uint32_t * tap_chan; unsigned long long * tap_index; unsigned int tap_cap;
+    SyncTables tb;
+    FftDev fft;                 // M-point plan
+};
+size_t sync_smem_bytes(const SyncParams & p);
+cudaError_t sync_configure(size_t smem_bytes);
+cudaError_t sync_launch(const SyncParams & p, int threads, size_t smem_bytes, cudaStream_t st);
+void sync_state_init(SyncState & s, unsigned int M, unsigned int cp);
+
+// ------------------------------------------------------------------ packet decode
+// de-interleave + FEC decode + CRC of every completed frame (liquid packetizer_decode, called
+// from inside ofdmflexframesync_execute in the reference)
+struct PacketParams {
+    FrameRec * recs; const FrameAux * aux;
+    const unsigned int * counters;   // [0] = number of records
+    unsigned int first_rec;          // records before this index were decoded by earlier launches
+    uint8_t * arena;                 // encoded payloads (decoded in place / via scratch)
+    uint8_t * scratch;               // same size as arena
+    uint8_t * decoded;               // same size as arena; payload bytes end up at payload_offset
+};
+cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t st);
+
+} // namespace b2

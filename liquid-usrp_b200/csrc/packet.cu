@@ -1,0 +1,347 @@
+// packet.cu -- payload packet decode: 2-stage (de-interleave -> FEC decode), then CRC-32.
+//
+// This is liquid's packetizer_decode(), which the reference reaches from inside
+// ofdmflexframesync_execute (lib/multichannelrx.cc:194, lib/ofdmtxrx.cc:625) once the last
+// payload symbol of a frame has been demodulated.  Integer/bitwise work, HBM/L2 bound:
+// one CTA per completed frame, grid-stride over the frames of a launch.
+//   interleaver : liquid's 4-pass byte/bit-mask permutation.  Each pass is a set of DISJOINT
+//                 swaps (2i <-> 2j+1) whose partner index j follows a column walk of an M x N
+//                 grid; the walk is turned into a parallel prefix count so all swaps of a pass
+//                 run concurrently.
+//   FEC         : none, Hamming(12,8) (thread per codeword pair), Golay(24,12) (thread per
+//                 codeword pair), convolutional r1/2 K=7 (hard-decision Viterbi, one warp per
+//                 frame: lane L owns states 2L, 2L+1; decisions ballot-packed, 64 bit per step).
+//   CRC-32      : 32 lanes x bytewise CRC of a slice, slices merged with x^(8n) mod P products.
+#include "kernels.h"
+#include "fec.cuh"
+
+namespace b2 {
+
+constexpr int PK_THREADS = 256;
+constexpr unsigned int PK_TB_STEPS = 2048;          // traceback staging chunk (steps)
+
+__device__ __forceinline__ unsigned int pk_fec_enc_len(unsigned int scheme, unsigned int n)
+{
+    switch (scheme) {
+    case 6:  return (n * 12 + 7) / 8;
+    case 7:  { unsigned int blocks = (n * 8 + 11) / 12; return (blocks * 24 + 7) / 8; }
+    case 11: return (2 * (8 * n + 6) + 7) / 8;
+    default: return n;
+    }
+}
+
+// ------------------------------------------------------------------ block-wide exclusive scan of small counts
+__device__ __forceinline__ unsigned int block_excl_scan(unsigned int v, unsigned int * scratch, unsigned int tid,
+                                                        unsigned int * total)
+{
+    unsigned int lane = tid & 31, wid = tid >> 5;
+    unsigned int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (unsigned int)o) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) scratch[wid] = x;
+    __syncthreads();
+    unsigned int base = 0, tot = 0;
+    for (unsigned int w = 0; w < PK_THREADS / 32; w++) {
+        unsigned int s = scratch[w];
+        if (w < wid) base += s;
+        tot += s;
+    }
+    *total = tot;
+    return base + x - v;
+}
+
+// one de-interleaver pass over x[0..n): grid Mi x Ni, bit mask `mask`
+__device__ void deinterleave_pass(uint8_t * x, unsigned int n, unsigned int Mi, unsigned int Ni, unsigned int mask,
+                                  unsigned int * scratch, unsigned int tid)
+{
+    const unsigned int n2 = n / 2, c0 = n / 3;
+    unsigned int count = 0, base = 0;
+    while (count < n2) {
+        unsigned int q0 = base + tid * 4;
+        unsigned int jv[4], f = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned int q = q0 + k;
+            unsigned int t = q / Mi, m = q - t * Mi;
+            unsigned int c = (t == 0) ? c0 : (c0 + t) % Ni;
+            unsigned int j = m * Ni + c;
+            jv[k] = j;
+            f += (j < n2) ? 1u : 0u;
+        }
+        unsigned int tot;
+        unsigned int idx = count + block_excl_scan(f, scratch, tid, &tot);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (jv[k] < n2) {
+                if (idx < n2) {
+                    unsigned int a = x[2 * idx], b = x[2 * jv[k] + 1];
+                    x[2 * idx] = (uint8_t)((a & ~mask) | (b & mask));
+                    x[2 * jv[k] + 1] = (uint8_t)((a & mask) | (b & ~mask));
+                }
+                idx++;
+            }
+        }
+        count += tot;
+        base += PK_THREADS * 4;
+        __syncthreads();
+    }
+}
+
+__device__ void deinterleave(uint8_t * x, unsigned int n, unsigned int * scratch, unsigned int tid)
+{
+    if (n < 2) return;
+    unsigned int Mi = 1 + (unsigned int)floorf(sqrtf((float)n));
+    unsigned int Ni = n / Mi;
+    while (n >= Mi * Ni) Ni++;
+    deinterleave_pass(x, n, Mi, Ni + 8, 0x33, scratch, tid);
+    deinterleave_pass(x, n, Mi, Ni + 4, 0x55, scratch, tid);
+    deinterleave_pass(x, n, Mi, Ni + 2, 0x0f, scratch, tid);
+    deinterleave_pass(x, n, Mi, Ni, 0xff, scratch, tid);
+}
+
+// ------------------------------------------------------------------ block codes
+__device__ __forceinline__ unsigned int hamming128_decode(unsigned int r)
+{
+    unsigned int z = 8 * (__popc(r & 0x01f) & 1) + 4 * (__popc(r & 0x1e1) & 1) + 2 * (__popc(r & 0x666) & 1) + (__popc(r & 0xaaa) & 1);
+    if (z) r ^= 1u << (12 - z);
+    return ((r & 0x200) >> 2) | ((r & 0x0e0) >> 1) | (r & 0x00f);
+}
+
+__device__ void hamming128_decode_block(const uint8_t * enc, uint8_t * dec, unsigned int n, unsigned int tid)
+{
+    unsigned int pairs = n / 2;
+    for (unsigned int k = tid; k < pairs; k += PK_THREADS) {
+        unsigned int e0 = enc[3 * k], e1 = enc[3 * k + 1], e2 = enc[3 * k + 2];
+        dec[2 * k] = (uint8_t)hamming128_decode((e0 << 4) | (e1 >> 4));
+        dec[2 * k + 1] = (uint8_t)hamming128_decode(((e1 & 0x0f) << 8) | e2);
+    }
+    if ((n & 1) && tid == 0) {
+        unsigned int j = 3 * pairs;
+        dec[n - 1] = (uint8_t)hamming128_decode(((unsigned int)enc[j] << 4) | (enc[j + 1] >> 4));
+    }
+}
+__device__ void golay2412_decode_block(const uint8_t * enc, uint8_t * dec, unsigned int n, unsigned int tid)
+{
+    unsigned int groups = n / 3, r = n % 3;
+    for (unsigned int k = tid; k < groups; k += PK_THREADS) {
+        const uint8_t * e = enc + 6 * k;
+        unsigned int s0 = golay2412_decode(((unsigned int)e[0] << 16) | ((unsigned int)e[1] << 8) | e[2]);
+        unsigned int s1 = golay2412_decode(((unsigned int)e[3] << 16) | ((unsigned int)e[4] << 8) | e[5]);
+        dec[3 * k] = (s0 >> 4) & 0xff;
+        dec[3 * k + 1] = ((s0 << 4) & 0xf0) | ((s1 >> 8) & 0x0f);
+        dec[3 * k + 2] = s1 & 0xff;
+    }
+    if (tid < r) {
+        const uint8_t * e = enc + 6 * groups + 3 * tid;
+        dec[3 * groups + tid] = golay2412_decode(((unsigned int)e[0] << 16) | ((unsigned int)e[1] << 8) | e[2]) & 0xff;
+    }
+}
+
+// ------------------------------------------------------------------ conv r1/2 K=7 Viterbi (warp 0 of the CTA)
+// libfec metric (|expected - received| with hard bits as 0/255), start metrics 0 / 63,
+// predecessor with the oldest bit set wins only on strictly smaller metric, chain back from 0.
+__device__ void viterbi27_decode(const uint8_t * enc, uint8_t * dec, unsigned int n, uint2 * decisions,
+                                 uint2 * stage, unsigned int tid)
+{
+    const unsigned int nbits = 8 * n + 6;
+    if (tid < 32) {
+        const unsigned int L = tid;
+        // new states 2L (input bit 0) and 2L+1 (input bit 1) both come from old states L and L+32
+        // expected output pair for register value reg = (old << 1) | bit
+        unsigned int ex[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            unsigned int old = (i & 2) ? L + 32 : L, bit = i & 1;
+            unsigned int reg = (old << 1) | bit;
+            ex[i] = ((__popc(reg & 0x6d) & 1) << 1) | (__popc(reg & 0x4f) & 1);
+        }
+        unsigned int me = (L == 0) ? 0u : 63u, mo = 63u;      // metrics of states 2L, 2L+1
+        for (unsigned int t = 0; t < nbits; t++) {
+            unsigned int byte = enc[(2 * t) >> 3];
+            unsigned int r = (byte >> (6 - ((2 * t) & 7))) & 3u;            // (r0 << 1) | r1
+            // old metrics of states L and L+32
+            unsigned int a_e = __shfl_sync(0xffffffffu, me, L >> 1), a_o = __shfl_sync(0xffffffffu, mo, L >> 1);
+            unsigned int b_e = __shfl_sync(0xffffffffu, me, 16 + (L >> 1)), b_o = __shfl_sync(0xffffffffu, mo, 16 + (L >> 1));
+            unsigned int m_lo = (L & 1) ? a_o : a_e;
+            unsigned int m_hi = (L & 1) ? b_o : b_e;
+            unsigned int m0 = m_lo + 255u * __popc(ex[0] ^ r), m1 = m_hi + 255u * __popc(ex[2] ^ r);
+            unsigned int d_e = m1 < m0;
+            unsigned int ne = d_e ? m1 : m0;
+            m0 = m_lo + 255u * __popc(ex[1] ^ r); m1 = m_hi + 255u * __popc(ex[3] ^ r);
+            unsigned int d_o = m1 < m0;
+            unsigned int no = d_o ? m1 : m0;
+            me = ne; mo = no;
+            unsigned int be = __ballot_sync(0xffffffffu, d_e), bo = __ballot_sync(0xffffffffu, d_o);
+            if (L == 0) decisions[t] = make_uint2(be, bo);
+        }
+    }
+    for (unsigned int i = tid; i < n; i += PK_THREADS) dec[i] = 0;
+    __syncthreads();
+    // traceback in chunks staged through shared memory
+    __shared__ unsigned int tb_state;
+    if (tid == 0) tb_state = 0;
+    unsigned int hi = nbits;
+    while (hi > 0) {
+        unsigned int lo = hi > PK_TB_STEPS ? hi - PK_TB_STEPS : 0;
+        __syncthreads();
+        for (unsigned int i = lo + tid; i < hi; i += PK_THREADS) stage[i - lo] = decisions[i];
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int s = tb_state;
+            for (unsigned int t = hi; t-- > lo;) {
+                if (t < 8 * n && (s & 1u)) dec[t >> 3] |= (uint8_t)(0x80u >> (t & 7));
+                uint2 d = stage[t - lo];
+                unsigned int bit = (((s & 1u) ? d.y : d.x) >> (s >> 1)) & 1u;
+                s = (s >> 1) | (bit << 5);
+            }
+            tb_state = s;
+        }
+        hi = lo;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ CRC-32 (reflected 0xEDB88320)
+__device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b)
+{
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) {
+            p ^= b;
+            if ((a & (m - 1)) == 0) break;
+        }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+    }
+    return p;
+}
+// x^(8*nbytes) mod P
+__device__ uint32_t crc_x8n(unsigned int nbytes)
+{
+    uint32_t p = 1u << 31;                   // x^0
+    uint32_t sq = crc_multmodp(1u << 30, 1u << 30);   // x^2
+    sq = crc_multmodp(sq, sq);               // x^4
+    sq = crc_multmodp(sq, sq);               // x^8
+    while (nbytes) {
+        if (nbytes & 1u) p = crc_multmodp(sq, p);
+        sq = crc_multmodp(sq, sq);
+        nbytes >>= 1;
+    }
+    return p;
+}
+// CRC-32 of m[0..n) computed by warp 0; result valid in lane 0
+__device__ uint32_t crc32_warp(const uint8_t * m, unsigned int n, unsigned int lane)
+{
+    unsigned int per = (n + 31) / 32;
+    unsigned int lo = min(n, lane * per), hi = min(n, lo + per);
+    uint32_t key = (lane == 0) ? ~0u : 0u;                 // only the first slice carries the preset
+    for (unsigned int i = lo; i < hi; i++) {
+        key ^= m[i];
+#pragma unroll
+        for (int j = 0; j < 8; j++) key = (key >> 1) ^ (0xEDB88320u & (0u - (key & 1u)));
+    }
+    // merge: reg(A||B) = reg(A) * x^(8|B|) + reg0(B)
+    uint32_t xp = crc_x8n(per);
+    uint32_t acc = 0;
+    for (unsigned int l = 0; l < 32; l++) {
+        uint32_t k = __shfl_sync(0xffffffffu, key, l);
+        unsigned int llo = min(n, l * per), lhi = min(n, llo + per);
+        unsigned int len = lhi - llo;
+        if (lane == 0 && (len || l == 0)) {
+            uint32_t sh = (len == per) ? xp : crc_x8n(len);
+            acc = (l == 0) ? k : (crc_multmodp(sh, acc) ^ k);
+        }
+    }
+    return ~acc;
+}
+
+// ------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketParams p, uint2 * vit_ws, size_t vit_ws_stride)
+{
+    __shared__ unsigned int scratch[PK_THREADS / 32];
+    __shared__ uint2 stage[PK_TB_STEPS];
+    __shared__ int s_valid;
+    const unsigned int tid = threadIdx.x;
+    const unsigned int nrec = p.counters[0];
+    for (unsigned int ri = p.first_rec + blockIdx.x; ri < nrec; ri += gridDim.x) {
+        FrameRec * rec = p.recs + ri;
+        if (!rec->header_valid) continue;
+        const unsigned int plen = rec->payload_len, check = rec->check, fec0 = rec->fec0, fec1 = rec->fec1;
+        const unsigned long long off = rec->payload_offset;
+        const unsigned int crc_len = (check == 6) ? 4u : 0u;
+        const unsigned int n0 = plen + crc_len;
+        const unsigned int e0 = pk_fec_enc_len(fec0, n0);
+        const unsigned int e1 = pk_fec_enc_len(fec1, e0);
+        uint8_t * A = p.arena + off;
+        uint8_t * Bf = p.scratch + off;
+        uint8_t * D = p.decoded + off;
+        uint2 * ws = vit_ws + (size_t)blockIdx.x * vit_ws_stride;
+        int ok = 1;
+        // stage 1 (outer code)
+        uint8_t * s1out = A;
+        if (fec1 != 1) {
+            deinterleave(A, e1, scratch, tid);
+            __syncthreads();
+            if (fec1 == 6) hamming128_decode_block(A, Bf, e0, tid);
+            else if (fec1 == 7) golay2412_decode_block(A, Bf, e0, tid);
+            else if (8ull * e0 + 6 <= vit_ws_stride) viterbi27_decode(A, Bf, e0, ws, stage, tid);
+            else ok = 0;
+            s1out = Bf;
+            __syncthreads();
+        }
+        // stage 0 (inner code)
+        if (fec0 != 1) {
+            deinterleave(s1out, e0, scratch, tid);
+            __syncthreads();
+            if (fec0 == 6) hamming128_decode_block(s1out, D, n0, tid);
+            else if (fec0 == 7) golay2412_decode_block(s1out, D, n0, tid);
+            else if (8ull * n0 + 6 <= vit_ws_stride) viterbi27_decode(s1out, D, n0, ws, stage, tid);
+            else ok = 0;
+        } else {
+            for (unsigned int i = tid; i < n0; i += PK_THREADS) D[i] = s1out[i];
+        }
+        __syncthreads();
+        if (tid < 32) {
+            int valid = ok;
+            if (ok && crc_len) {
+                uint32_t c = crc32_warp(D, plen, tid);
+                if (tid == 0) {
+                    uint32_t key = ((uint32_t)D[plen] << 24) | ((uint32_t)D[plen + 1] << 16) | ((uint32_t)D[plen + 2] << 8) | D[plen + 3];
+                    valid = (c == key);
+                }
+            }
+            if (tid == 0) s_valid = valid;
+        }
+        __syncthreads();
+        if (tid == 0) rec->payload_valid = s_valid;
+        __syncthreads();
+    }
+}
+
+static uint2 * g_vit_ws[16] = {nullptr};
+static size_t g_vit_ws_stride[16] = {0};
+static int g_vit_ws_grid[16] = {0};
+
+cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t st)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) dev = 0;
+    // Viterbi decision workspace: 8 bytes per trellis step per CTA, sized for the largest packet
+    const size_t steps = 8ull * (65535 + 4 + 2) * 2 + 64;       // also covers v27 as outer code over an inner code
+    if (!g_vit_ws[dev] || g_vit_ws_grid[dev] < grid) {
+        if (g_vit_ws[dev]) cudaFree(g_vit_ws[dev]);
+        cudaError_t e = cudaMalloc(&g_vit_ws[dev], (size_t)grid * steps * sizeof(uint2));
+        if (e != cudaSuccess) { g_vit_ws[dev] = nullptr; return e; }
+        g_vit_ws_stride[dev] = steps;
+        g_vit_ws_grid[dev] = grid;
+    }
+    packet_decode_kernel<<<grid, PK_THREADS, 0, st>>>(p, g_vit_ws[dev], g_vit_ws_stride[dev]);
+    return cudaGetLastError();
+}
+
+} // namespace b2
