@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the multichannelrx hot path (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of multichannelrx::Execute over one batch of synthetic wideband input
+(NCO mix-down + 2N-channel polyphase analysis + N x ofdmflexframesync + packet decode + frame
+records back on the host).  Workload at every N: the north-star shape, 256 channels x 512
+subcarriers, cp 64, 64-QAM, no FEC, 1200-byte payloads, every channel transmitting back to back
+(BASELINE.json configs[4] per-GPU share; SURVEY.md 8d "C5").  The input is ONE steady-state frame
+period produced by the CPU oracle's transmitter (the reference's lib/multichanneltx.cc over
+oracle/), tiled on the device; the tiling is seamless because every frame ends in > 500 samples of
+silence and the NCO phase is periodic in the period length.
+
+  value     wideband Msamples/s, input resident in HBM, whole job (all ranks)
+  e2e       same through the C ABI with HOST (pinned) input: H2D + kernels + D2H of the records
+  roofline  dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM peak
+  cpu_baseline   the reference's lib/multichannelrx.cc over the oracle, on this box's host CPU
+
+Multi-GPU (--gpus N under torchrun): weak scaling, every rank channelizes and synchronises its own
+wideband stream (independent receivers; no data-path collective), rank 0 gathers the counts.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOAD = dict(name="multichannelrx N=256 M=512 cp=64 taper=16 qam64 fec=none payload=1200B, all channels back-to-back",
+                N=256, M=512, cp=64, taper=16, payload=1200)
+B_ALG_PATH = 16.10          # 8 B in + 4 B channelizer out + 4 B sync in + 0.10 B payload, per wideband sample
+B_ALG = {"analyzer_kernel": 12.0, "sync_kernel": 4.10, "packet_decode_kernel": 0.20}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_period(reps_for_check=1):
+    """one steady-state frame period of the workload from the CPU oracle transmitter
+    -> (x[period] complex64, expected payload per channel, frame length in channel samples)"""
+    import refmc
+    w = WORKLOAD
+    L = refmc.ref_lib()
+    N, M, cp = w["N"], w["M"], w["cp"]
+    enc = w["payload"] + 4
+    nd = 356
+    nsym = 3 + 1 + -(-(-(-8 * enc // 6)) // nd) + 1
+    flen = nsym * (M + cp)
+    tx = refmc.McTx(L, N, M, cp, w["taper"])
+    x = tx.run(2 * flen, w["payload"], refmc.MOD_QAM64, refmc.FEC_NONE, refmc.FEC_NONE, seed=0xB2000000, gain=1.0 / N)
+    tx.close()
+    K = 2 * N
+    period = x[flen * K:2 * flen * K].copy()
+    expected = [L.frame_data(0xB2000000, c, 1, w["payload"]) for c in range(N)]
+    return period, expected, flen
+
+
+class Clocks(threading.Thread):
+    """sample SM clocks / throttle reasons while the timed region runs"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_reference(args, rank):
+    """the reference's own CPU implementation of the path: lib/multichannelrx.cc (unmodified)
+    over the oracle's restatement of liquid-dsp, one thread (the reference's DSP path has none)"""
+    if rank != 0:
+        return
+    import refmc
+    w = WORKLOAD
+    period, expected, flen = make_period()
+    L = refmc.ref_lib()
+    rx = refmc.McRx(L, w["N"], w["M"], w["cp"], w["taper"])
+    reps = 2                                         # bounded sample: 2 frame periods per step
+    x = np.tile(period, reps)
+    for _ in range(max(args.warmup, 1)):
+        rx.execute(x)
+        rx.frames()
+    t0 = time.perf_counter()
+    nfr = 0
+    for _ in range(args.steps):
+        rx.execute(x)
+        fr, _pl = rx.frames()
+        nfr += len(fr)
+    dt = time.perf_counter() - t0
+    rx.close()
+    val = args.steps * len(x) / dt / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (oracle transmitter, one frame period tiled)",
+            "config": {"workload": w["name"], "samples_per_step": len(x), "frames_decoded": nfr},
+            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": 1, "kind": "port",
+                             "sample": "%d wideband samples/step: reference lib/multichannelrx.cc compiled unmodified over the "
+                                       "oracle's C restatement of liquid-dsp (liquid-dsp itself is not installable here), gcc -O2" % len(x)},
+            "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+METRIC = "complex Msamples/s through multichannelrx (64ch OFDM) at 1/2/4/8 GPU vs CPU"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--reps", type=int, default=8, help="frame periods per step (8 -> 21.2 M samples, 170 MB > L2)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from b2 import pkg
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w = WORKLOAD
+    period, expected, flen = make_period()
+    n_step = len(period) * args.reps
+    # device-resident input (the "stubbed UHD source"), tiled on the device
+    d_period = torch.from_numpy(period.view(np.float32)).cuda()
+    d_x = d_period.repeat(args.reps).contiguous()
+    h_x = torch.from_numpy(np.tile(period, args.reps).view(np.float32)).pin_memory()
+    rx = pkg.MultichannelRx(w["N"], w["M"], w["cp"], w["taper"], device=local_rank, max_batch=n_step)
+    L = pkg.lib()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def check(recs, pl, nrep):
+        assert len(recs) >= w["N"] * (nrep - 1), "frames missing: %d" % len(recs)
+        assert int(recs["header_valid"].min()) == 1 and int(recs["payload_valid"].min()) == 1, "invalid frame"
+        for i in (0, len(recs) // 2, len(recs) - 1):
+            c = int(recs["channel"][i])
+            o = int(recs["payload_offset"][i])
+            assert np.array_equal(pl[o:o + w["payload"]], expected[c][1]), "payload mismatch on channel %d" % c
+
+    # ---- device-resident leg (value)
+    for _ in range(args.warmup):
+        rx.execute_device(d_x.data_ptr(), n_step)
+        recs, pl = rx.poll()
+    check(recs, pl, args.reps)
+    clk = Clocks(local_rank)
+    clk.start()
+    kt = np.zeros(4)
+    barrier()
+    t0 = time.perf_counter()
+    nfr = 0
+    for _ in range(args.steps):
+        rx.execute_device(d_x.data_ptr(), n_step)
+        kt += np.array(rx.last_timing())
+        recs, pl = rx.poll()
+        nfr += len(recs)
+    barrier()
+    dt = time.perf_counter() - t0
+    # ---- host leg (e2e): pinned host input -> C ABI -> records on the host
+    for _ in range(2):
+        L.b2_mcrx_execute(rx.h, C.c_void_p(h_x.data_ptr()), n_step)
+        recs, pl = rx.poll()
+    barrier()
+    t1 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        rc = L.b2_mcrx_execute(rx.h, C.c_void_p(h_x.data_ptr()), n_step)
+        assert rc == 0
+        recs, pl = rx.poll()
+        d2h += recs.nbytes + len(pl) + 32
+    barrier()
+    dt_e2e = time.perf_counter() - t1
+    clk.stop_flag = True
+    clk.join()
+    check(recs, pl, args.reps)
+
+    # max over ranks of the device-timed region
+    times = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dt, dt_e2e = float(times[0]), float(times[1])
+    total = n_step * args.steps * world
+    kt_avg = kt / args.steps                      # ms per launch: analyzer, sync, decode, whole call
+    names = ["analyzer_kernel", "sync_kernel", "packet_decode_kernel"]
+    dom = int(np.argmax(kt_avg[:3]))
+    peak, peak_src = peaks()
+    achieved = n_step * B_ALG[names[dom]] / (kt_avg[dom] * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": total / dt / 1e6, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (oracle transmitter, one frame period tiled on device)",
+            "config": {"workload": w["name"], "samples_per_step": n_step, "input_bytes_per_step": n_step * 8,
+                       "l2_policy": "input (%.0f MB/step) larger than L2" % (n_step * 8 / 1e6),
+                       "frames_per_step": nfr // args.steps, "parallelism": "independent receivers x%d" % world},
+            "e2e": {"value": total / dt_e2e / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": n_step * 8,
+                    "d2h_bytes_per_step": d2h // args.steps},
+            "gpu_launches": 3 * args.steps,
+            "kernels_ms_per_step": {"analyzer_kernel": kt_avg[0], "sync_kernel": kt_avg[1], "packet_decode_kernel": kt_avg[2], "call": kt_avg[3]},
+            "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "alg_bytes_per_sample": B_ALG[names[dom]],
+                         "path": {"alg_bytes_per_sample": B_ALG_PATH, "achieved": n_step * B_ALG_PATH / (kt_avg[3] * 1e-3) / 1e9,
+                                  "frac": n_step * B_ALG_PATH / (kt_avg[3] * 1e-3) / 1e9 / peak}},
+            "clocks": clk.summary()}
+    if rank == 0 and not args.no_cpu:
+        import refmc
+        Lr = refmc.ref_lib()
+        crx = refmc.McRx(Lr, w["N"], w["M"], w["cp"], w["taper"])
+        xs = np.tile(period, 2)
+        crx.execute(period)
+        tc = time.perf_counter()
+        ncpu = 0
+        while time.perf_counter() - tc < 10.0:
+            crx.execute(xs)
+            crx.frames()
+            ncpu += len(xs)
+        tcpu = time.perf_counter() - tc
+        crx.close()
+        line["cpu_baseline"] = {"value": ncpu / tcpu / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
+                                "sample": "%d wideband samples (same period, ~10 s): reference lib/multichannelrx.cc compiled "
+                                          "unmodified over the oracle's C restatement of liquid-dsp, gcc -O2, 1 thread" % ncpu}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    rx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -8,4 +8,5 @@ shared library is missing, importing `capi` raises.
 The directory name carries a hyphen (it mirrors the reference's name), so import it with
     importlib.import_module("liquid-usrp_b200")
 """
-from .capi import (B2Error, FRAME_DTYPE, MultichannelRx, OfdmSync, lib, lib_path)  # noqa: F401
+from .capi import (B2Error, FRAME_DTYPE, MsResamp, MultichannelRx, MultichannelTx, OfdmGen, OfdmSync,  # noqa: F401
+                   lib, lib_path)

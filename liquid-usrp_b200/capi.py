@@ -52,6 +52,26 @@ _PROTOS = {
     "b2_ofdmsync_execute_device": (C.c_int, [_vp, _vp, _sz, _sz]),
     "b2_ofdmsync_poll": (C.c_int, [_vp, _vp, _sz, C.POINTER(_sz), _vp, _sz, C.POINTER(_sz)]),
     "b2_ofdmsync_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float * 4)]),
+    "b2_mctx_create": (C.c_int, [C.c_uint, C.c_uint, C.c_uint, C.c_uint, _vp, C.c_int, C.POINTER(_vp)]),
+    "b2_mctx_destroy": (C.c_int, [_vp]),
+    "b2_mctx_reset": (C.c_int, [_vp]),
+    "b2_mctx_is_ready": (C.c_int, [_vp, C.c_uint, C.POINTER(C.c_int)]),
+    "b2_mctx_update": (C.c_int, [_vp, C.c_uint, _vp, _vp, C.c_uint, C.c_int, C.c_int, C.c_int]),
+    "b2_mctx_generate": (C.c_int, [_vp, _vp, _sz]),
+    "b2_mctx_generate_device": (C.c_int, [_vp, _vp, _sz]),
+    "b2_mctx_calls_to_boundary": (C.c_int, [_vp, C.POINTER(_sz)]),
+    "b2_mctx_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float * 4)]),
+    "b2_ofdmgen_create": (C.c_int, [C.c_uint, C.c_uint, C.c_uint, _vp, C.c_int, C.POINTER(_vp)]),
+    "b2_ofdmgen_destroy": (C.c_int, [_vp]),
+    "b2_ofdmgen_reset": (C.c_int, [_vp]),
+    "b2_ofdmgen_is_assembled": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "b2_ofdmgen_assemble": (C.c_int, [_vp, _vp, _vp, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint)]),
+    "b2_ofdmgen_write": (C.c_int, [_vp, _vp, C.c_uint, C.POINTER(C.c_int)]),
+    "b2_msresamp_create": (C.c_int, [C.c_float, C.c_float, C.c_int, C.POINTER(_vp)]),
+    "b2_msresamp_destroy": (C.c_int, [_vp]),
+    "b2_msresamp_reset": (C.c_int, [_vp]),
+    "b2_msresamp_execute": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
+    "b2_msresamp_execute_device": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
 }
 
 
@@ -65,10 +85,9 @@ def lib():
                               "(there is no CPU fallback)" % path)
         L = C.CDLL(path, mode=C.RTLD_GLOBAL)
         for name, (res, args) in _PROTOS.items():
-            if hasattr(L, name):
-                f = getattr(L, name)
-                f.restype = res
-                f.argtypes = args
+            f = getattr(L, name)            # AttributeError if the library lacks a declared symbol
+            f.restype = res
+            f.argtypes = args
         _LIB = L
     return _LIB
 
@@ -182,3 +201,112 @@ class OfdmSync(_FrameSource):
 
     def execute_device(self, dev_ptr, n, stride):
         _check(lib().b2_ofdmsync_execute_device(self.h, _ptr(dev_ptr), n, stride))
+
+
+class _Handle:
+    _destroy = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            getattr(lib(), self._destroy)(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultichannelTx(_Handle):
+    """b2_mctx_*: N-channel OFDM transmitter (multichanneltx, lib/multichanneltx.cc)"""
+    _destroy = "b2_mctx_destroy"
+
+    def __init__(self, num_channels, M, cp_len, taper_len, p=None, device=0):
+        self.N, self.M, self.cp, self.taper = num_channels, M, cp_len, taper_len
+        h = _vp()
+        pp = None if p is None else np.ascontiguousarray(p, np.uint8).ctypes.data
+        _check(lib().b2_mctx_create(num_channels, M, cp_len, taper_len, pp, device, C.byref(h)))
+        self.h = h
+
+    def reset(self):
+        _check(lib().b2_mctx_reset(self.h))
+
+    def is_ready(self, channel):
+        r = C.c_int(0)
+        _check(lib().b2_mctx_is_ready(self.h, channel, C.byref(r)))
+        return r.value
+
+    def update(self, channel, header, payload, mod, fec0, fec1):
+        header = np.ascontiguousarray(header, np.uint8)
+        payload = np.ascontiguousarray(payload, np.uint8)
+        _check(lib().b2_mctx_update(self.h, channel, header.ctypes.data, payload.ctypes.data, len(payload), mod, fec0, fec1))
+
+    def generate(self, n_calls):
+        out = np.zeros(n_calls * 2 * self.N, np.complex64)
+        _check(lib().b2_mctx_generate(self.h, out.ctypes.data, n_calls))
+        return out
+
+    def generate_device(self, dev_ptr, n_calls):
+        _check(lib().b2_mctx_generate_device(self.h, _ptr(dev_ptr), n_calls))
+
+    def calls_to_boundary(self):
+        n = _sz(0)
+        _check(lib().b2_mctx_calls_to_boundary(self.h, C.byref(n)))
+        return n.value
+
+    def last_timing(self):
+        ms = (C.c_float * 4)()
+        _check(lib().b2_mctx_last_timing(self.h, C.byref(ms)))
+        return [float(v) for v in ms]
+
+
+class OfdmGen(_Handle):
+    """b2_ofdmgen_*: one ofdmflexframegen (lib/ofdmtxrx.cc:79-84,314-328)"""
+    _destroy = "b2_ofdmgen_destroy"
+
+    def __init__(self, M, cp_len, taper_len, p=None, device=0):
+        self.M, self.cp, self.taper = M, cp_len, taper_len
+        h = _vp()
+        pp = None if p is None else np.ascontiguousarray(p, np.uint8).ctypes.data
+        _check(lib().b2_ofdmgen_create(M, cp_len, taper_len, pp, device, C.byref(h)))
+        self.h = h
+
+    def is_assembled(self):
+        r = C.c_int(0)
+        _check(lib().b2_ofdmgen_is_assembled(self.h, C.byref(r)))
+        return r.value
+
+    def assemble(self, header, payload, check, fec0, fec1, mod):
+        header = np.ascontiguousarray(header, np.uint8)
+        payload = np.ascontiguousarray(payload, np.uint8)
+        n = C.c_uint(0)
+        _check(lib().b2_ofdmgen_assemble(self.h, header.ctypes.data, payload.ctypes.data, len(payload), check, fec0, fec1, mod, C.byref(n)))
+        return n.value
+
+    def write(self, n_symbols):
+        out = np.zeros(n_symbols * (self.M + self.cp), np.complex64)
+        last = C.c_int(0)
+        _check(lib().b2_ofdmgen_write(self.h, out.ctypes.data, n_symbols, C.byref(last)))
+        return out, last.value
+
+
+class MsResamp(_Handle):
+    """b2_msresamp_*: msresamp_crcf (src/flexframe_rx.cc:179,240)"""
+    _destroy = "b2_msresamp_destroy"
+
+    def __init__(self, rate, As=60.0, device=0):
+        self.rate = rate
+        h = _vp()
+        _check(lib().b2_msresamp_create(rate, As, device, C.byref(h)))
+        self.h = h
+
+    def reset(self):
+        _check(lib().b2_msresamp_reset(self.h))
+
+    def execute(self, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        y = np.zeros(int(len(x) * float(self.rate) * 1.01) + 64, np.complex64)
+        ny = _sz(0)
+        _check(lib().b2_msresamp_execute(self.h, x.ctypes.data, len(x), y.ctypes.data, len(y), C.byref(ny)))
+        return y[:ny.value]

@@ -30,7 +30,7 @@ struct SyncCore {
     unsigned int streams = 0;
     size_t tmax = 0;                     // max samples per stream per launch
     // tables
-    DevBuf t_sctype, t_S0, t_S1, t_data, t_pilot, t_pilotx, t_active, t_seq, t_walk, t_B, t_perm, t_tw;
+    DevBuf t_sctype, t_S0, t_S1, t_data, t_pilot, t_pilotx, t_active, t_seq, t_walk, t_B, t_perm, t_tw, t_rank;
     // state
     DevBuf d_st, d_ring, d_G0, d_R, d_penc;
     size_t penc_cap = 0;
@@ -60,7 +60,8 @@ struct SyncCore {
     int init(unsigned int M, unsigned int cp, unsigned int taper, const unsigned char * p, unsigned int streams_,
              size_t tmax_, int device_, cudaStream_t st);
     void destroy();
-    int reset_state();
+    int reset_state();                   // fresh object: everything zero
+    int reset_streams();                 // ofdmflexframesync_reset on every stream
     // run sync + decode over in[s*stride + t], t < nsamples; appends results to `ready`
     int run(const cf * in, size_t in_stride, unsigned int nsamples, bool record_events);
     int collect();
@@ -95,7 +96,11 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     B2_TRY(t_sctype.upload(plan.p)); B2_TRY(t_S0.upload(plan.S0)); B2_TRY(t_S1.upload(plan.S1));
     B2_TRY(t_data.upload(plan.data_idx)); B2_TRY(t_pilot.upload(plan.pilot_idx)); B2_TRY(t_pilotx.upload(plan.pilot_x));
     B2_TRY(t_active.upload(plan.active_idx)); B2_TRY(t_seq.upload(plan.pilot_seq)); B2_TRY(t_walk.upload(walk));
-    B2_TRY(t_B.upload(B)); B2_TRY(t_perm.upload(fftM.perm)); B2_TRY(t_tw.upload(fftM.tw));
+    std::vector<uint16_t> sc_rank(M, 0xffff);
+    for (size_t d = 0; d < plan.data_idx.size(); d++) sc_rank[plan.data_idx[d]] = (uint16_t)d;
+    for (size_t n = 0; n < plan.pilot_idx.size(); n++) sc_rank[plan.pilot_idx[n]] = (uint16_t)(0x4000u | n);
+    if (plan.M_pilot + plan.M_data < 5) return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA path needs at least 5 active subcarriers");
+    B2_TRY(t_B.upload(B)); B2_TRY(t_perm.upload(fftM.perm)); B2_TRY(t_tw.upload(fftM.tw)); B2_TRY(t_rank.upload(sc_rank));
     // state
     const size_t W = M + cp;
     penc_cap = ((size_t)fec_enc_len(FEC_HAMMING128, fec_enc_len(FEC_CONV_V27, 65535 + 4)) + 64 + 15) & ~(size_t)15;
@@ -133,9 +138,10 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     sp.tb.sctype = t_sctype.as<uint8_t>(); sp.tb.S0 = t_S0.as<float>(); sp.tb.S1 = t_S1.as<float>();
     sp.tb.data_idx = t_data.as<uint16_t>(); sp.tb.pilot_idx = t_pilot.as<uint16_t>(); sp.tb.pilot_x = t_pilotx.as<float>();
     sp.tb.active_idx = t_active.as<uint16_t>(); sp.tb.pilot_seq = t_seq.as<uint8_t>(); sp.tb.hdr_walk = t_walk.as<uint16_t>();
-    sp.tb.B = t_B.as<cf>();
+    sp.tb.B = t_B.as<cf>(); sp.tb.sc_rank = t_rank.as<uint16_t>();
     sp.fft.n = fftM.n; sp.fft.npass = fftM.npass;
-    for (unsigned int i = 0; i < fftM.npass; i++) sp.fft.radix[i] = fftM.radix[i];
+    sp.fft.radices = 0;
+    for (unsigned int i = 0; i < fftM.npass; i++) sp.fft.radices |= fftM.radix[i] << (4 * i);
     sp.fft.perm = t_perm.as<uint16_t>(); sp.fft.tw = t_tw.as<cf>();
     sync_smem = sync_smem_bytes(sp);
     if (sync_smem > 227 * 1024) return b2_fail(B2_ERR_UNSUPPORTED, "M=%u needs %zu bytes of shared memory per stream", M, sync_smem);
@@ -167,6 +173,13 @@ int SyncCore::reset_state()
     B2_CUDA(cudaMemsetAsync(d_ring.p, 0, d_ring.bytes, stream));
     B2_CUDA(cudaMemsetAsync(d_G0.p, 0, d_G0.bytes, stream));
     B2_CUDA(cudaMemsetAsync(d_R.p, 0, d_R.bytes, stream));
+    B2_CUDA(cudaStreamSynchronize(stream));
+    return B2_OK;
+}
+
+int SyncCore::reset_streams()
+{
+    B2_CUDA(sync_reset_launch(d_st.as<SyncState>(), streams, stream));
     B2_CUDA(cudaStreamSynchronize(stream));
     return B2_OK;
 }
@@ -355,7 +368,7 @@ extern "C" int b2_mcrx_reset(b2_mcrx * q)
     B2_CUDA(cudaSetDevice(q->device));
     B2_CUDA(cudaMemsetAsync(q->d_stage.p, 0, sizeof(cf) * (q->hist_len + q->K), q->stream));
     q->carry = 0;
-    return q->core.reset_state();
+    return q->core.reset_streams();
 }
 
 static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device)
@@ -382,7 +395,8 @@ static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device)
         ap.theta0 = q->nco_theta - (uint32_t)(q->hist_len + q->carry) * q->nco_dtheta;
         ap.out = q->d_chan.as<cf>(); ap.out_stride = q->tcap; ap.out_col0 = 0;
         ap.fft.n = K; ap.fft.npass = q->fftK.npass;
-        for (unsigned int i = 0; i < q->fftK.npass; i++) ap.fft.radix[i] = q->fftK.radix[i];
+        ap.fft.radices = 0;
+        for (unsigned int i = 0; i < q->fftK.npass; i++) ap.fft.radices |= q->fftK.radix[i] << (4 * i);
         ap.fft.perm = q->t_perm.as<uint16_t>(); ap.fft.tw = q->t_tw.as<cf>();
         B2_CUDA(analyzer_launch(ap, q->an_grid, q->an_smem, q->stream));
     }
@@ -550,7 +564,7 @@ extern "C" int b2_ofdmsync_reset(b2_ofdmsync * q)
 {
     if (!q) return b2_fail(B2_ERR_ARG, "null handle");
     B2_CUDA(cudaSetDevice(q->device));
-    return q->core.reset_state();
+    return q->core.reset_streams();
 }
 static int ofdmsync_run(b2_ofdmsync * q, const cf * in, size_t stride, size_t n)
 {

@@ -190,3 +190,161 @@ cudaError_t analyzer_launch(const AnalyzerParams & p, int grid, size_t smem_byte
 }
 
 } // namespace b2
+
+// ================================================================== synthesis channelizer
+// synth_kernel replaces, per call of multichanneltx::GenerateSamples (lib/multichanneltx.cc:192-227),
+//     X[i] = fgbuffer[i][fgbuffer_index]  (i < N; X[N..2N) stay 0)    :205-210
+//     firpfbch_crcf_synthesizer_execute(channelizer, X, buffer)      :213
+//     nco_crcf_mix_up + nco_crcf_step per output sample              :219-222
+// Math (liquid firpfbch.c, synthesizer):  V_t = IFFT_K(X_t) (backward, unnormalised),
+//     y_t[i] = sum_{n=0}^{P-1} h[i + n*K] * V_{t-n}[i],   out[t*K + i] = y_t[i] * e^{+j theta}
+// A CTA owns a contiguous range of blocks; it keeps the last P-1+TB IFFT outputs in a shared
+// memory ring (the P-1 rows before its range are recomputed from the input, or come from the
+// persistent history for the first blocks of a call), slides a P-deep register window down each
+// column like the analyzer, and writes whole rows of K wideband samples.
+namespace b2 {
+
+constexpr int SY_THREADS = 256;
+constexpr int SY_P = 26;            // taps per branch of the transmit bank (m = 13, lib/multichanneltx.cc:85)
+
+struct SynSmem { unsigned int RR; size_t off_colw, off_roww, off_ring, total; };
+__host__ __device__ static inline SynSmem syn_layout(unsigned int K, unsigned int TB)
+{
+    SynSmem s;
+    s.RR = SY_P - 1 + TB;
+    size_t o = 0;
+    s.off_colw = o; o += (size_t)K * sizeof(cf);
+    s.off_roww = o; o += (size_t)(TB + 1) * sizeof(cf);
+    o = (o + 15) & ~(size_t)15;
+    s.off_ring = o; o += (size_t)s.RR * K * sizeof(cf);
+    s.total = o;
+    return s;
+}
+size_t synth_smem_bytes(const SynthParams & p) { return syn_layout(p.K, p.TB).total; }
+
+template <int JB>
+__global__ void __launch_bounds__(SY_THREADS, 1) synth_kernel(const SynthParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const unsigned int tid = threadIdx.x;
+    const unsigned int K = p.K, N = p.N, TB = p.TB;
+    const SynSmem L = syn_layout(K, TB);
+    cf * colw = (cf *)(smem + L.off_colw);
+    cf * roww = (cf *)(smem + L.off_roww);
+    cf * ring = (cf *)(smem + L.off_ring);
+    const unsigned int RR = L.RR;
+
+    unsigned int tiles_total = (p.nblocks + TB - 1) / TB;
+    unsigned int tiles_per = (tiles_total + gridDim.x - 1) / gridDim.x;
+    unsigned int b_begin = blockIdx.x * tiles_per * TB;
+    if (b_begin >= p.nblocks) return;
+    unsigned int b_end = min(p.nblocks, b_begin + tiles_per * TB);
+    unsigned int ntiles = (b_end - b_begin + TB - 1) / TB;
+
+    for (unsigned int r = tid; r < K; r += SY_THREADS) colw[r] = nco_cexp_pi(r * p.dtheta);
+
+    // V row of block t (t may be negative: history) -> ring slot (t - (b_begin - (P-1))) % RR.
+    // rows with t < 0 come from vhist[P-1+t]; others are IFFTs of the gathered channel samples.
+    auto fill_rows = [&](int t_lo, int t_hi) {
+        const int org = (int)b_begin - (SY_P - 1);
+        // history rows (t < 0) are copied, the others gathered in FFT-permuted order; the gather
+        // runs with time fastest so each channel contributes one contiguous run
+        const int h_hi = min(t_hi, 0);
+        for (int t = t_lo; t < h_hi; t++) {
+            cf * row = ring + (size_t)((unsigned int)(t - org) % RR) * K;
+            const cf * src = p.vhist + (size_t)(SY_P - 1 + t) * K;
+            for (unsigned int i = tid; i < K; i += SY_THREADS) row[i] = src[i];
+        }
+        const int g_lo = max(t_lo, 0);
+        if (g_lo < t_hi) {
+            const unsigned int nr = (unsigned int)(t_hi - g_lo);
+            for (unsigned int e = tid; e < nr * (K - N); e += SY_THREADS) {
+                unsigned int tq = e / (K - N), i = N + (e - tq * (K - N));
+                ring[(size_t)((unsigned int)(g_lo + (int)tq - org) % RR) * K + p.fft.perm[i]] = make_float2(0.f, 0.f);
+            }
+            for (unsigned int e = tid; e < nr * N; e += SY_THREADS) {
+                unsigned int i = e / nr, tq = e - i * nr;
+                cf v = p.in[(size_t)i * p.in_stride + p.in_off + (unsigned int)(g_lo + (int)tq)];
+                ring[(size_t)((unsigned int)(g_lo + (int)tq - org) % RR) * K + p.fft.perm[i]] = v;
+            }
+        }
+        __syncthreads();
+        for (int t = g_lo; t < t_hi;) {              // IFFT the rows, one contiguous run of ring slots at a time
+            unsigned int slot = (unsigned int)(t - org) % RR;
+            unsigned int run = min((unsigned int)(t_hi - t), RR - slot);
+            fft_inplace<+1, 0>(ring + (size_t)slot * K, K, run, p.fft, tid, SY_THREADS);
+            t += (int)run;
+        }
+    };
+
+    // halo: the P-1 rows before the range
+    fill_rows((int)b_begin - (SY_P - 1), (int)b_begin);
+
+    const unsigned int groups = TB / JB;
+    for (unsigned int tt = 0; tt < ntiles; tt++) {
+        const unsigned int tb0 = b_begin + tt * TB;
+        const unsigned int nb = min(TB, b_end - tb0);
+        fill_rows((int)tb0, (int)(tb0 + nb));
+        for (unsigned int g = tid; g < nb; g += SY_THREADS) roww[g] = nco_cexp_pi(p.theta0 + (tb0 + g) * K * p.dtheta);
+        __syncthreads();
+        for (unsigned int it = tid; it < groups * K; it += SY_THREADS) {
+            const unsigned int jb = it >> p.lgK, r = it & (K - 1);
+            if (jb * JB >= nb) continue;
+            float h[SY_P];
+#pragma unroll
+            for (int n = 0; n < SY_P; n++) h[n] = __ldg(p.taps + (size_t)n * K + r);
+            cf v[JB + SY_P - 1];
+            // v[q] = V_{tb0 + jb*JB - (P-1) + q}[r]
+            const unsigned int rel0 = tt * TB + jb * JB;                   // ring-relative row of v[0]
+#pragma unroll
+            for (int q = 0; q < JB + SY_P - 1; q++) v[q] = ring[(size_t)((rel0 + q) % RR) * K + r];
+            const cf cw = colw[r];
+#pragma unroll
+            for (int bl = 0; bl < JB; bl++) {
+                if (jb * JB + bl >= nb) break;
+                float ar = 0.f, ai = 0.f;
+#pragma unroll
+                for (int n = SY_P - 1; n >= 0; n--) {                      // oldest first, as dotprod_crcf
+                    ar = fmaf(h[n], v[bl + SY_P - 1 - n].x, ar);
+                    ai = fmaf(h[n], v[bl + SY_P - 1 - n].y, ai);
+                }
+                cf w = cmul(roww[jb * JB + bl], cw);
+                p.out[(size_t)(tb0 + jb * JB + bl) * K + r] = mix_up(make_float2(ar, ai), w);
+            }
+        }
+        __syncthreads();
+    }
+    // the CTA that owns the last blocks leaves the new history (last P-1 IFFT rows of the call)
+    if (b_end == p.nblocks) {
+        for (int q = 0; q < SY_P - 1; q++) {
+            int t = (int)p.nblocks - (SY_P - 1) + q;
+            cf * dst = p.vhist_out + (size_t)q * K;
+            if (t < (int)b_begin - (SY_P - 1)) {
+                // call shorter than the history: older rows shift down from the previous history
+                const cf * src = p.vhist + (size_t)(SY_P - 1 + t) * K;
+                for (unsigned int i = tid; i < K; i += SY_THREADS) dst[i] = src[i];
+            } else {
+                unsigned int slot = (unsigned int)(t - ((int)b_begin - (SY_P - 1))) % RR;
+                const cf * src = ring + (size_t)slot * K;
+                for (unsigned int i = tid; i < K; i += SY_THREADS) dst[i] = src[i];
+            }
+        }
+    }
+}
+
+cudaError_t synth_configure(size_t smem_bytes)
+{
+    cudaError_t e = cudaFuncSetAttribute(synth_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(synth_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+}
+
+cudaError_t synth_launch(const SynthParams & p, int grid, size_t smem_bytes, cudaStream_t st)
+{
+    if (p.nblocks == 0) return cudaSuccess;
+    if (p.TB % 8 == 0) synth_kernel<8><<<grid, SY_THREADS, smem_bytes, st>>>(p);
+    else synth_kernel<2><<<grid, SY_THREADS, smem_bytes, st>>>(p);
+    return cudaGetLastError();
+}
+
+} // namespace b2

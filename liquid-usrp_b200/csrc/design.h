@@ -7,6 +7,7 @@
 // Plain C++ (no CUDA); evaluated in float with the same formulas liquid uses so that the tables
 // agree with a liquid-dsp build to the last bit where libm agrees.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -256,6 +257,69 @@ static inline int fft_plan(FftPlan & f, unsigned int n)
         f.tw[2 * k + 1] = (float)sin(a);
     }
     return 0;
+}
+
+// ---------------------------------------------------------------- transmit-side tables
+// unnormalised radix-2 transform in float (host, construction time only)
+static inline void host_fft(std::vector<float> & re, std::vector<float> & im, int dir)
+{
+    const unsigned int n = (unsigned int)re.size();
+    unsigned int lg = ceil_log2(n);
+    for (unsigned int i = 0; i < n; i++) {
+        unsigned int r = 0;
+        for (unsigned int b = 0; b < lg; b++) if (i & (1u << b)) r |= 1u << (lg - 1 - b);
+        if (r > i) { std::swap(re[i], re[r]); std::swap(im[i], im[r]); }
+    }
+    for (unsigned int half = 1; half < n; half <<= 1) {
+        unsigned int stride = n / (2 * half);
+        for (unsigned int k = 0; k < n; k += 2 * half) {
+            for (unsigned int j = 0; j < half; j++) {
+                double a = (double)dir * 2.0 * M_PI * (double)(j * stride) / (double)n;
+                float wr = (float)cos(a), wi = (float)sin(a);
+                float br = re[k + j + half], bi = im[k + j + half];
+                float tr = br * wr - bi * wi, ti = br * wi + bi * wr;
+                float ar = re[k + j], ai = im[k + j];
+                re[k + j] = ar + tr; im[k + j] = ai + ti;
+                re[k + j + half] = ar - tr; im[k + j + half] = ai - ti;
+            }
+        }
+    }
+}
+// time-domain training symbols s0, s1 (IFFT of S0/S1 scaled by 1/sqrt(M_S)), interleaved re,im
+static inline void ofdm_training_time(const OfdmPlan & o, std::vector<float> & s0, std::vector<float> & s1)
+{
+    for (int which = 0; which < 2; which++) {
+        const std::vector<float> & S = which ? o.S1 : o.S0;
+        std::vector<float> re(S), im(o.M, 0.0f);
+        host_fft(re, im, +1);
+        float g = 1.0f / sqrtf((float)(which ? o.M_S1 : o.M_S0));
+        std::vector<float> & out = which ? s1 : s0;
+        out.resize(2 * (size_t)o.M);
+        for (unsigned int i = 0; i < o.M; i++) { out[2 * i] = re[i] * g; out[2 * i + 1] = im[i] * g; }
+    }
+}
+// raised-sine^2 taper (ofdmframegen)
+static inline std::vector<float> ofdm_taper(unsigned int taper)
+{
+    std::vector<float> w(taper ? taper : 1, 0.0f);
+    for (unsigned int i = 0; i < taper; i++) {
+        float t = ((float)i + 0.5f) / (float)taper;
+        float g = sinf(M_PI_2 * t);
+        w[i] = g * g;
+    }
+    return w;
+}
+// msresamp_crcf arbitrary stage: prototype (sum = npfb) and Q32 phase step
+static inline std::vector<float> resamp_prototype(float rate, float As, unsigned int m, unsigned int npfb)
+{
+    unsigned int hlen = 2 * m * npfb + 1;
+    float fc = 0.515f * (rate < 1.0f ? rate : 1.0f);
+    if (fc > 0.49f) fc = 0.49f;
+    std::vector<float> h = firdes_kaiser(hlen, fc / (float)npfb, fabsf(As));
+    double sum = 0.0;
+    for (float v : h) sum += (double)v;
+    for (float & v : h) v = (float)((double)v * (double)npfb / sum);
+    return h;
 }
 
 // ---------------------------------------------------------------- byte interleaver index walk

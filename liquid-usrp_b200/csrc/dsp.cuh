@@ -92,7 +92,7 @@ template <int PAD> __device__ __forceinline__ unsigned int phys(unsigned int i) 
 
 struct FftDev {
     unsigned int n, npass;
-    unsigned int radix[12];
+    unsigned int radices;      // radix of pass t in bits [4t, 4t+4)
     const uint16_t * perm;     // input permutation (device or shared)
     const cf * tw;             // forward twiddles e^{-j 2 pi k / n}
 };
@@ -138,7 +138,7 @@ __device__ __forceinline__ void fft_inplace(cf * buf, unsigned int ld, unsigned 
 {
     unsigned int L = 1;
     for (unsigned int t = 0; t < f.npass; t++) {
-        unsigned int R = f.radix[t];
+        unsigned int R = (f.radices >> (4 * t)) & 15u;
         L *= R;
         if (R == 8) fft_pass<8, DIR, PAD>(buf, ld, nfft, f.n, L, f.tw, tid, nthreads);
         else if (R == 4) fft_pass<4, DIR, PAD>(buf, ld, nfft, f.n, L, f.tw, tid, nthreads);
@@ -205,6 +205,15 @@ __device__ __forceinline__ void bulk_g2s(void * dst_smem, const void * src_gmem,
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// 8-byte asynchronous global -> shared copy (LDGSTS), completion via cp.async.wait_all
+__device__ __forceinline__ void cp_async8(void * dst_smem, const void * src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async()
 {

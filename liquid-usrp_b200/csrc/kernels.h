@@ -78,6 +78,8 @@ struct SyncTables {             // read-only, global memory
     const uint8_t * pilot_seq;  // [255]
     const uint16_t * hdr_walk;  // [4][18] header de-interleaver walks (n = 36)
     const cf * B;               // [M] e^{j 2 pi backoff i / M}
+    const uint16_t * sc_rank;   // [M] data: rank among data subcarriers (ascending index);
+                                //     pilot: 0x4000 | rank in fft-shifted visiting order; null: 0xffff
 };
 
 struct SyncParams {
@@ -108,6 +110,7 @@ size_t sync_smem_bytes(const SyncParams & p);
 cudaError_t sync_configure(size_t smem_bytes);
 cudaError_t sync_launch(const SyncParams & p, int threads, size_t smem_bytes, cudaStream_t st);
 void sync_state_init(SyncState & s, unsigned int M, unsigned int cp);
+cudaError_t sync_reset_launch(SyncState * st, unsigned int streams, cudaStream_t stream);
 
 // ------------------------------------------------------------------ packet decode
 // de-interleave + FEC decode + CRC of every completed frame (liquid packetizer_decode, called
@@ -121,5 +124,85 @@ struct PacketParams {
     uint8_t * decoded;               // same size as arena; payload bytes end up at payload_offset
 };
 cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t st);
+
+} // namespace b2
+
+namespace b2 {
+
+// ------------------------------------------------------------------ packet encode (transmit)
+struct EncodeJob {
+    uint8_t  header[8];
+    uint32_t payload_len, mod, bps, check, fec0, fec1;
+    uint32_t slot;              // output slot (= channel)
+    uint64_t payload_offset;    // into EncodeParams::payloads
+};
+struct EncodeParams {
+    const EncodeJob * jobs; unsigned int nframes;
+    const uint8_t * payloads;
+    uint8_t * header_mod;       // [slots][288] one BPSK bit per byte
+    uint8_t * payload_mod;      // [slots][mod_stride] one symbol per byte
+    size_t mod_stride;
+    uint8_t * work0, * work1;   // [slots][work_stride] scratch
+    size_t work_stride;
+};
+cudaError_t packet_encode_launch(const EncodeParams & p, cudaStream_t st);
+
+// ------------------------------------------------------------------ OFDM frame generator
+// ofdmflexframegen_write per channel per symbol period (lib/multichanneltx.cc:230-242,
+// lib/ofdmtxrx.cc:328): one CTA per channel walks the symbol periods of this call.
+struct GenDesc {                // per channel, per call (host is the source of truth)
+    uint32_t first_symbol;      // index of the first symbol to generate (0 = S0a)
+    uint32_t n_periods;         // leading periods of this call that carry the frame (rest: zeros)
+    uint32_t n_hdr, n_pay;      // header / payload OFDM symbols of the frame
+    uint32_t mod, bps, payload_mod_len;
+    uint32_t fresh;             // 1: frame starts in this call (clear the taper postfix)
+};
+struct FramegenParams {
+    unsigned int M, cp, taper, M_pilot, M_data;
+    float g_data;
+    float qam_alpha[9];
+    unsigned int nchan, nper;
+    const GenDesc * desc;
+    cf * postfix;               // [nchan][taper] persistent
+    const uint8_t * header_mod; const uint8_t * payload_mod; size_t mod_stride;
+    const cf * s0, * s1;        // [M] time-domain training symbols
+    const float * taper_w;      // [taper]
+    const uint16_t * sc_rank; const uint8_t * pilot_seq;
+    cf * out; size_t out_stride, out_off;   // out[c*out_stride + out_off + period*(M+cp) + i]
+    FftDev fft;
+};
+size_t framegen_smem_bytes(const FramegenParams & p);
+cudaError_t framegen_launch(const FramegenParams & p, cudaStream_t st);
+
+// ------------------------------------------------------------------ synthesis channelizer
+// firpfbch_crcf synthesizer + NCO mix-up (lib/multichanneltx.cc:205-222)
+struct SynthParams {
+    const cf * in; size_t in_stride, in_off;    // in[c*in_stride + in_off + t], c < N
+    unsigned int K, lgK, N, P, TB;
+    unsigned int nblocks;
+    const float * taps;         // [P][K]
+    cf * vhist;                 // [P-1][K] IFFT outputs of the last P-1 blocks (persistent)
+    cf * vhist_out;             // where this launch leaves the new history (ping-pong with vhist)
+    uint32_t theta0, dtheta;    // NCO phase of output sample 0
+    cf * out;                   // [nblocks*K] wideband
+    FftDev fft;
+};
+size_t synth_smem_bytes(const SynthParams & p);
+cudaError_t synth_configure(size_t smem_bytes);
+cudaError_t synth_launch(const SynthParams & p, int grid, size_t smem_bytes, cudaStream_t st);
+
+// ------------------------------------------------------------------ arbitrary resampler
+// msresamp_crcf (arbitrary stage, rate in [0.5, 2]); output k is a closed-form function of k:
+// t_k = tau0 + k*step (Q32), input index t_k >> 32 (relative to x[0] = first new sample)
+struct ResampParams {
+    const cf * x;               // [hist + nx] : hist = 2m-1 previous samples, then the new ones
+    unsigned int hist, nx;
+    const float * h;            // prototype taps [2*m*npfb + 1]
+    unsigned int npfb_bits, m2; // log2(npfb), 2m
+    unsigned long long tau0, step;
+    unsigned long long ny;
+    cf * y;
+};
+cudaError_t resamp_launch(const ResampParams & p, cudaStream_t st);
 
 } // namespace b2

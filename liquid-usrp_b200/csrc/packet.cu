@@ -322,6 +322,174 @@ __global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketP
     }
 }
 
+// ================================================================== packet ENCODE (transmit side)
+// liquid packetizer_encode + the ofdmflexframegen header/payload symbol mapping, as reached from
+// ofdmflexframegen_assemble (lib/multichanneltx.cc:188, lib/ofdmtxrx.cc:320,380):
+//   payload: msg || CRC-32 -> fec0 -> interleave -> fec1 -> interleave -> bps-bit symbols
+//   header : 8 user + 6 internal bytes || CRC-32 -> Golay(24,12) -> interleave -> scramble -> 288 bits
+__device__ void interleave(uint8_t * x, unsigned int n, unsigned int * scratch, unsigned int tid)
+{
+    if (n < 2) return;
+    unsigned int Mi = 1 + (unsigned int)floorf(sqrtf((float)n));
+    unsigned int Ni = n / Mi;
+    while (n >= Mi * Ni) Ni++;
+    deinterleave_pass(x, n, Mi, Ni, 0xff, scratch, tid);
+    deinterleave_pass(x, n, Mi, Ni + 2, 0x0f, scratch, tid);
+    deinterleave_pass(x, n, Mi, Ni + 4, 0x55, scratch, tid);
+    deinterleave_pass(x, n, Mi, Ni + 8, 0x33, scratch, tid);
+}
+
+__device__ __forceinline__ unsigned int hamming128_encode(unsigned int s)
+{
+    unsigned int c = ((s & 0x80) << 2) | ((s & 0x70) << 1) | (s & 0x0f);
+    c |= (__popc(c & 0x2aa) & 1) << 11;
+    c |= (__popc(c & 0x266) & 1) << 10;
+    c |= (__popc(c & 0x0e1) & 1) << 8;
+    c |= (__popc(c & 0x00f) & 1) << 4;
+    return c;
+}
+__device__ __forceinline__ unsigned int golay2412_encode(unsigned int s)
+{
+    s &= 0xfff;
+    return (golay_mul_P(s) << 12) | s;
+}
+
+__device__ void fec_encode_block(unsigned int scheme, const uint8_t * dec, uint8_t * enc, unsigned int n, unsigned int tid)
+{
+    if (scheme == 6) {                                  // Hamming(12,8): 2 bytes -> 3 bytes
+        unsigned int pairs = n / 2;
+        for (unsigned int k = tid; k < pairs; k += PK_THREADS) {
+            unsigned int m0 = hamming128_encode(dec[2 * k]), m1 = hamming128_encode(dec[2 * k + 1]);
+            enc[3 * k] = (m0 >> 4) & 0xff;
+            enc[3 * k + 1] = ((m0 << 4) & 0xf0) | ((m1 >> 8) & 0x0f);
+            enc[3 * k + 2] = m1 & 0xff;
+        }
+        if ((n & 1) && tid == 0) {
+            unsigned int m0 = hamming128_encode(dec[n - 1]);
+            enc[3 * pairs] = (m0 & 0x0ff0) >> 4;
+            enc[3 * pairs + 1] = (m0 & 0x000f) << 4;
+        }
+    } else if (scheme == 7) {                           // Golay(24,12): 3 bytes -> 6 bytes
+        unsigned int groups = n / 3, r = n % 3;
+        for (unsigned int k = tid; k < groups; k += PK_THREADS) {
+            unsigned int s0 = ((unsigned int)dec[3 * k] << 4) | (dec[3 * k + 1] >> 4);
+            unsigned int s1 = (((unsigned int)dec[3 * k + 1] & 0x0f) << 8) | dec[3 * k + 2];
+            unsigned int v0 = golay2412_encode(s0), v1 = golay2412_encode(s1);
+            uint8_t * e = enc + 6 * k;
+            e[0] = (v0 >> 16) & 0xff; e[1] = (v0 >> 8) & 0xff; e[2] = v0 & 0xff;
+            e[3] = (v1 >> 16) & 0xff; e[4] = (v1 >> 8) & 0xff; e[5] = v1 & 0xff;
+        }
+        if (tid < r) {
+            unsigned int v0 = golay2412_encode(dec[3 * groups + tid]);
+            uint8_t * e = enc + 6 * groups + 3 * tid;
+            e[0] = (v0 >> 16) & 0xff; e[1] = (v0 >> 8) & 0xff; e[2] = v0 & 0xff;
+        }
+    } else if (scheme == 11) {                          // conv r1/2 K=7: output byte j <- input bits 4j .. 4j+3
+        unsigned int nbits = 8 * n + 6, nout = (2 * nbits + 7) / 8;
+        for (unsigned int j = tid; j < nout; j += PK_THREADS) {
+            unsigned int v = 0;
+            for (unsigned int q = 0; q < 4; q++) {
+                unsigned int t = 4 * j + q;
+                unsigned int o = 0;
+                if (t < nbits) {
+                    // shift register after input bit t: bits t-6 .. t (bit t in the LSB)
+                    unsigned int sr = 0;
+                    for (int b = 6; b >= 0; b--) {
+                        int ti = (int)t - b;
+                        unsigned int bit = (ti >= 0 && (unsigned int)ti < 8 * n) ? (dec[ti >> 3] >> (7 - (ti & 7))) & 1u : 0u;
+                        sr = (sr << 1) | bit;
+                    }
+                    o = ((__popc(sr & 0x6d) & 1) << 1) | (__popc(sr & 0x4f) & 1);
+                }
+                v = (v << 2) | o;
+            }
+            enc[j] = (uint8_t)v;
+        }
+    } else {
+        for (unsigned int i = tid; i < n; i += PK_THREADS) enc[i] = dec[i];
+    }
+}
+
+__global__ void __launch_bounds__(PK_THREADS) packet_encode_kernel(const EncodeParams p)
+{
+    __shared__ unsigned int scratch[PK_THREADS / 32];
+    __shared__ uint8_t hbuf[2][40];
+    const unsigned int tid = threadIdx.x;
+    for (unsigned int fi = blockIdx.x; fi < p.nframes; fi += gridDim.x) {
+        const EncodeJob job = p.jobs[fi];
+        // ---- header: 14 bytes + CRC -> Golay -> interleave -> scramble -> 288 bits
+        if (tid < 8) hbuf[0][tid] = job.header[tid];
+        if (tid == 8) {
+            hbuf[0][8] = 105;                                       // protocol id (104 + packetizer version)
+            hbuf[0][9] = (job.payload_len >> 8) & 0xff;
+            hbuf[0][10] = job.payload_len & 0xff;
+            hbuf[0][11] = (uint8_t)job.mod;
+            hbuf[0][12] = (uint8_t)(((job.check & 7) << 5) | (job.fec0 & 0x1f));
+            hbuf[0][13] = (uint8_t)(job.fec1 & 0x1f);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t c = crc32_warp(hbuf[0], 14, tid);
+            if (tid == 0) { hbuf[0][14] = c >> 24; hbuf[0][15] = (c >> 16) & 0xff; hbuf[0][16] = (c >> 8) & 0xff; hbuf[0][17] = c & 0xff; }
+        }
+        __syncthreads();
+        fec_encode_block(7, hbuf[0], hbuf[1], 18, tid);
+        __syncthreads();
+        interleave(hbuf[1], 36, scratch, tid);
+        __syncthreads();
+        {
+            const uint8_t mask[4] = {0xb4, 0x6a, 0x8b, 0x45};
+            uint8_t * hm = p.header_mod + (size_t)job.slot * 288;
+            for (unsigned int i = tid; i < 288; i += PK_THREADS) {
+                unsigned int byte = hbuf[1][i >> 3] ^ mask[(i >> 3) & 3];
+                hm[i] = (byte >> (7 - (i & 7))) & 1u;
+            }
+        }
+        // ---- payload
+        const unsigned int plen = job.payload_len, crc_len = (job.check == 6) ? 4u : 0u;
+        const unsigned int n0 = plen + crc_len;
+        const unsigned int e0 = pk_fec_enc_len(job.fec0, n0), e1 = pk_fec_enc_len(job.fec1, e0);
+        uint8_t * A = p.work0 + (size_t)job.slot * p.work_stride;
+        uint8_t * B = p.work1 + (size_t)job.slot * p.work_stride;
+        const uint8_t * msg = p.payloads + job.payload_offset;
+        for (unsigned int i = tid; i < plen; i += PK_THREADS) A[i] = msg[i];
+        __syncthreads();
+        if (crc_len && tid < 32) {
+            uint32_t c = crc32_warp(A, plen, tid);
+            if (tid == 0) { A[plen] = c >> 24; A[plen + 1] = (c >> 16) & 0xff; A[plen + 2] = (c >> 8) & 0xff; A[plen + 3] = c & 0xff; }
+        }
+        __syncthreads();
+        fec_encode_block(job.fec0, A, B, n0, tid);
+        __syncthreads();
+        if (job.fec0 != 1) interleave(B, e0, scratch, tid);
+        __syncthreads();
+        fec_encode_block(job.fec1, B, A, e0, tid);
+        __syncthreads();
+        if (job.fec1 != 1) interleave(A, e1, scratch, tid);
+        __syncthreads();
+        // repack e1 bytes into bps-bit symbols, MSB first, zero padded
+        const unsigned int bps = job.bps, nsym = (8 * e1 + bps - 1) / bps;
+        uint8_t * pm = p.payload_mod + (size_t)job.slot * p.mod_stride;
+        for (unsigned int s = tid; s < nsym; s += PK_THREADS) {
+            unsigned int v = 0;
+            for (unsigned int b = 0; b < bps; b++) {
+                unsigned int bit = s * bps + b;
+                unsigned int bv = (bit < 8 * e1) ? (A[bit >> 3] >> (7 - (bit & 7))) & 1u : 0u;
+                v = (v << 1) | bv;
+            }
+            pm[s] = (uint8_t)v;
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t packet_encode_launch(const EncodeParams & p, cudaStream_t st)
+{
+    if (p.nframes == 0) return cudaSuccess;
+    packet_encode_kernel<<<p.nframes < 1024 ? p.nframes : 1024, PK_THREADS, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
 static uint2 * g_vit_ws[16] = {nullptr};
 static size_t g_vit_ws_stride[16] = {0};
 static int g_vit_ws_grid[16] = {0};

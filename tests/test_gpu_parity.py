@@ -1,0 +1,238 @@
+"""Parity of the CUDA receive path (through the C ABI, include/b200_ofdm.h) against the CPU
+oracle -- the reference's lib/multichanneltx.cc / lib/multichannelrx.cc compiled over oracle/.
+
+Bars (BASELINE.json north_star): decoded payload bytes and frame detect/complete sample indices
+bit-exact; equalised symbols within 1e-5 relative (max |X_gpu - X_ref| / max |X_ref| per OFDM
+symbol); frame stats (evm/rssi in dB, cfo) to 1e-3."""
+import numpy as np
+import pytest
+
+from refmc import (McRx, McTx, ref_lib, payload_of, FEC_NONE, FEC_HAMMING128, FEC_GOLAY2412, FEC_CONV_V27,
+                   MOD_QPSK, MOD_QAM16, MOD_QAM64, MOD_QAM256)
+
+pytestmark = pytest.mark.gpu
+SEED = 0xB2000000
+EXACT = ("channel", "header_valid", "payload_valid", "payload_len", "header", "mod_scheme", "mod_bps",
+         "check", "fec0", "fec1", "detect_index", "complete_index")
+
+CASES = {
+    # name: N, M, cp, taper, mod, fec0, fec1, payload_len, frames, noise_std
+    "c1_loopback_1ch": (1, 64, 16, 4, MOD_QPSK, FEC_NONE, FEC_NONE, 200, 3, 0.0),
+    "c2_8ch_h128": (8, 64, 16, 4, MOD_QPSK, FEC_NONE, FEC_HAMMING128, 150, 3, 0.0),
+    "c3_16ch_qam16_v27": (16, 256, 32, 8, MOD_QAM16, FEC_CONV_V27, FEC_NONE, 300, 2, 0.0),
+    "c4_shape_qam256": (2, 512, 64, 16, MOD_QAM256, FEC_NONE, FEC_NONE, 1200, 2, 0.0),
+    "c5_shape_32ch_qam64": (32, 512, 64, 16, MOD_QAM64, FEC_NONE, FEC_NONE, 1200, 2, 0.0),
+    "golay_outer_h128": (4, 128, 16, 4, MOD_QAM16, FEC_GOLAY2412, FEC_HAMMING128, 97, 2, 0.0),
+    "noisy_30dB": (8, 64, 16, 4, MOD_QPSK, FEC_NONE, FEC_HAMMING128, 150, 3, 0.03),
+    "noisy_v27": (4, 256, 32, 8, MOD_QAM16, FEC_CONV_V27, FEC_NONE, 200, 2, 0.05),
+}
+
+
+def make_input(case, seed=1):
+    N, M, cp, taper, mod, fec0, fec1, plen, nframes, noise = case
+    import orc
+    from test_oracle_loopback import frame_symbols
+    bps = {MOD_QPSK: 2, MOD_QAM16: 4, MOD_QAM64: 6, MOD_QAM256: 8}[mod]
+    nsym = frame_symbols(M, bps, orc.lib().orc_packetizer_enc_len(plen, 6, fec0, fec1))
+    ncalls = (nsym * nframes + 3) * (M + cp) + 7
+    tx = McTx(ref_lib(), N, M, cp, taper)
+    x = tx.run(ncalls, plen, mod, fec0, fec1, seed=SEED, max_frames=nframes, gain=1.0 / N)
+    tx.close()
+    if noise:
+        rng = np.random.default_rng(seed)
+        s = noise * np.sqrt(np.mean(np.abs(x) ** 2))
+        x = (x + s * (rng.standard_normal(len(x)) + 1j * rng.standard_normal(len(x))) / np.sqrt(2)).astype(np.complex64)
+    return x
+
+
+def run_oracle(case, x, tap=False):
+    N, M, cp, taper = case[:4]
+    rx = McRx(ref_lib(), N, M, cp, taper)
+    if tap:
+        rx.tap_symbols(True)
+    rx.execute(x)
+    sym = rx.symbols() if tap else None
+    fr, pl = rx.frames()
+    rx.close()
+    return fr, pl, sym
+
+
+def run_gpu(case, x, chunks=None, tap=False, max_batch=0):
+    from b2 import pkg
+    N, M, cp, taper = case[:4]
+    g = pkg.MultichannelRx(N, M, cp, taper, max_batch=max_batch)
+    if tap:
+        g.tap_symbols(True, 1 << 15)
+    frs, pls = [], []
+    if chunks is None:
+        chunks = [len(x)]
+    i = 0
+    for c in chunks:
+        g.execute(x[i:i + c])
+        i += c
+    assert i == len(x)
+    fr, pl = g.poll()
+    sym = g.read_symbols() if tap else None
+    g.close()
+    return fr, pl, sym
+
+
+def assert_frames_equal(fo, po, fg, pg):
+    assert len(fg) == len(fo), (len(fg), len(fo))
+    for name in EXACT:
+        assert np.array_equal(fo[name], fg[name]), name
+    assert np.array_equal(po, pg)
+    assert np.array_equal(fo["payload_offset"], fg["payload_offset"])
+    np.testing.assert_allclose(fg["evm"], fo["evm"], atol=2e-3)
+    np.testing.assert_allclose(fg["rssi"], fo["rssi"], atol=1e-3)
+    np.testing.assert_allclose(fg["cfo"], fo["cfo"], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_frames_bit_exact_and_symbols_within_tolerance(name):
+    case = CASES[name]
+    x = make_input(case)
+    fo, po, so = run_oracle(case, x, tap=True)
+    fg, pg, sg = run_gpu(case, x, tap=True)
+    assert len(fo) == case[0] * case[8]
+    assert int(fo["payload_valid"].sum()) == len(fo)
+    assert_frames_equal(fo, po, fg, pg)
+    # equalised symbols, matched by (channel, sample index)
+    cho, io, Xo = so
+    chg, ig, Xg = sg
+    assert len(cho) == len(chg) and len(cho) > 0
+    oo = np.lexsort((io, cho))
+    og = np.lexsort((ig, chg))
+    assert np.array_equal(cho[oo], chg[og]) and np.array_equal(io[oo], ig[og])
+    err = np.abs(Xg[og] - Xo[oo]).max(axis=1) / np.abs(Xo[oo]).max(axis=1)
+    tol = 1e-5 if case[9] == 0.0 else 2e-5
+    assert err.max() < tol, err.max()
+
+
+def test_chunking_invariance_on_device():
+    case = CASES["c2_8ch_h128"]
+    x = make_input(case)
+    fo, po, _ = run_oracle(case, x)
+    rng = np.random.default_rng(5)
+    for pattern in ("odd", "tiny", "blocks", "small_batch"):
+        if pattern == "odd":
+            chunks, left = [], len(x)
+            while left:
+                c = int(min(left, rng.integers(1, 5000)))
+                chunks.append(c)
+                left -= c
+            fg, pg, _ = run_gpu(case, x, chunks)
+        elif pattern == "tiny":
+            chunks = [1] * 40 + [3] * 11 + [len(x) - 73]
+            fg, pg, _ = run_gpu(case, x, chunks)
+        elif pattern == "blocks":
+            chunks = [16 * 100] * (len(x) // 1600) + ([len(x) % 1600] if len(x) % 1600 else [])
+            fg, pg, _ = run_gpu(case, x, chunks)
+        else:
+            fg, pg, _ = run_gpu(case, x, None, max_batch=4096)       # internal splitting of one call
+        assert_frames_equal(fo, po, fg, pg)
+
+
+def test_reset_mid_stream_matches_oracle():
+    case = CASES["c2_8ch_h128"]
+    N, M, cp, taper = case[:4]
+    x = make_input(case)
+    cut = len(x) // 3 + 5
+    from b2 import pkg
+    rx = McRx(ref_lib(), N, M, cp, taper)
+    rx.execute(x[:cut]); rx.reset(); rx.execute(x[cut:])
+    fo, po = rx.frames()
+    rx.close()
+    g = pkg.MultichannelRx(N, M, cp, taper)
+    g.execute(x[:cut]); g.reset(); g.execute(x[cut:])
+    fg, pg = g.poll()
+    g.close()
+    assert_frames_equal(fo, po, fg, pg)
+
+
+def test_idle_channels_corruption_and_noise_only():
+    N, M, cp, taper = 4, 64, 16, 4
+    case = (N, M, cp, taper)
+    tx = McTx(ref_lib(), N, M, cp, taper)
+    x = tx.run(80 * 60, 50, MOD_QPSK, FEC_NONE, FEC_NONE, seed=SEED, channel_mask=0b0101, max_frames=2, gain=0.25)
+    tx.close()
+    rng = np.random.default_rng(11)
+    x = x + (1e-3 * (rng.standard_normal(len(x)) + 1j * rng.standard_normal(len(x)))).astype(np.complex64)
+    # wipe part of one payload so the CRC fails on some frames
+    x[17000:17400] = 0
+    fo, po, _ = run_oracle(case, x)
+    fg, pg, _ = run_gpu(case, x)
+    assert sorted(set(fo["channel"].tolist())) == [0, 2]
+    assert int((fo["payload_valid"] == 0).sum()) >= 1
+    assert_frames_equal(fo, po, fg, pg)
+    # all-zero and noise-only input: no frames, no NaN trouble
+    z = np.zeros(80 * 40 * 8, np.complex64)
+    fg, pg, _ = run_gpu(case, z)
+    assert len(fg) == 0
+    n = (0.1 * (rng.standard_normal(len(z)) + 1j * rng.standard_normal(len(z)))).astype(np.complex64)
+    fo, po, _ = run_oracle(case, n)
+    fg, pg, _ = run_gpu(case, n)
+    assert_frames_equal(fo, po, fg, pg)
+
+
+def test_channelizer_output_matches_oracle():
+    import orc
+    from b2 import pkg
+    for N in (1, 8, 64):
+        K = 2 * N
+        rng = np.random.default_rng(N)
+        T = 700
+        x = (rng.standard_normal(T * K) + 1j * rng.standard_normal(T * K)).astype(np.complex64)
+        L = orc.lib()
+        q = L.firpfbch_crcf_create_kaiser(0, K, 7, 60.0)
+        off = np.float32(-0.5 * (N - 1) / N * np.pi)       # lib/multichannelrx.cc:98 (double product -> float)
+        u = L.orc_nco_constrain(off)
+        n = np.arange(T * K, dtype=np.uint64)
+        th = ((n * np.uint64(u)) & np.uint64(0xffffffff)).astype(np.uint32).astype(np.int32)
+        t = (th.astype(np.float64) * (np.pi / 2147483648.0)).astype(np.float32)
+        xm = (x * (np.cos(t.astype(np.float64)) - 1j * np.sin(t.astype(np.float64)))).astype(np.complex64)
+        ref = np.zeros((T, K), np.complex64)
+        y = np.zeros(K, np.complex64)
+        for b in range(T):
+            xi = np.ascontiguousarray(xm[b * K:(b + 1) * K])
+            L.firpfbch_crcf_analyzer_execute(q, xi.ctypes.data, y.ctypes.data)
+            ref[b] = y
+        L.firpfbch_crcf_destroy(q)
+        g = pkg.MultichannelRx(N, 64, 16, 4)
+        g.execute(x)
+        cz = g.read_channelizer()
+        g.close()
+        assert cz.shape == (N, T)
+        err = np.abs(cz - ref[:, :N].T).max() / np.abs(ref).max()
+        assert err < 2e-6, (N, err)
+
+
+def test_batched_single_link_sync_matches_multichannel_oracle_streams():
+    """b2_ofdmsync_*: each stream is an independent ofdmflexframesync; feed it the oracle
+    channelizer's per-channel streams and compare with the oracle's frames"""
+    from b2 import pkg
+    case = CASES["c2_8ch_h128"]
+    N, M, cp, taper = case[:4]
+    x = make_input(case)
+    fo, po, _ = run_oracle(case, x)
+    g = pkg.MultichannelRx(N, M, cp, taper)
+    g.execute(x)
+    g.poll()
+    cz = g.read_channelizer()
+    g.close()
+    s = pkg.OfdmSync(M, cp, taper, streams=N)
+    s.execute(cz)
+    fg, pg = s.poll()
+    s.close()
+    assert_frames_equal(fo, po, fg, pg)
+
+
+def test_error_codes_match_reference_throws():
+    from b2 import pkg
+    for args in ((0, 64, 16, 4), (2, 6, 2, 0), (2, 64, 0, 0), (2, 64, 4, 8)):
+        with pytest.raises(pkg.B2Error) as e:
+            pkg.MultichannelRx(*args)
+        assert e.value.code == -1
+    with pytest.raises(pkg.B2Error) as e:
+        pkg.MultichannelRx(3, 64, 16, 4)          # legal for liquid, outside the CUDA path
+    assert e.value.code == -2
