@@ -35,6 +35,9 @@ extern "C" {
 const char * b2_last_error(void);           /* thread-local text of the last failure             */
 const char * b2_version(void);
 int  b2_device_count(void);                 /* number of visible CUDA devices (0 = none)          */
+/* page-locked host memory for staging buffers handed to the *_execute / *_generate calls */
+void * b2_pinned_alloc(size_t bytes);
+void   b2_pinned_free(void * p);
 
 /* One decoded frame.  Mirrors the arguments of liquid's framesync_callback
  * (src/multichannel_rx.cc:37-43) plus the sample-index side channel the north star asks for. */

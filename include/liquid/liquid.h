@@ -212,6 +212,10 @@ float ofdmflexframesync_get_cfo(ofdmflexframesync _q);
 void ofdmflexframesync_debug_enable(ofdmflexframesync _q);
 void ofdmflexframesync_debug_disable(ofdmflexframesync _q);
 void ofdmflexframesync_debug_print(ofdmflexframesync _q, const char * _filename);
+/* extension of the B200 implementation (not in liquid-dsp): samples given to
+ * ofdmflexframesync_execute() are processed in batches; this runs whatever is pending and
+ * delivers the callbacks now.  reset/destroy flush implicitly. */
+void ofdmflexframesync_flush(ofdmflexframesync _q);
 
 /* ------------------------------------------------------------ ofdmframe.common */
 void ofdmframe_init_default_sctype(unsigned int _M, unsigned char * _p);

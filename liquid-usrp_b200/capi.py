@@ -34,6 +34,8 @@ _PROTOS = {
     "b2_last_error": (C.c_char_p, []),
     "b2_version": (C.c_char_p, []),
     "b2_device_count": (C.c_int, []),
+    "b2_pinned_alloc": (_vp, [_sz]),
+    "b2_pinned_free": (None, [_vp]),
     "b2_mcrx_create": (C.c_int, [C.c_uint, C.c_uint, C.c_uint, C.c_uint, _vp, C.c_int, _sz, C.POINTER(_vp)]),
     "b2_mcrx_destroy": (C.c_int, [_vp]),
     "b2_mcrx_reset": (C.c_int, [_vp]),
@@ -83,7 +85,7 @@ def lib():
         if not os.path.exists(path):
             raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(there is no CPU fallback)" % path)
-        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        L = C.CDLL(path, mode=C.RTLD_LOCAL)
         for name, (res, args) in _PROTOS.items():
             f = getattr(L, name)            # AttributeError if the library lacks a declared symbol
             f.restype = res

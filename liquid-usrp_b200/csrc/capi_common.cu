@@ -22,3 +22,14 @@ extern "C" int b2_device_count(void)
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
+
+extern "C" void * b2_pinned_alloc(size_t bytes)
+{
+    void * p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void b2_pinned_free(void * p)
+{
+    if (p) cudaFreeHost(p);
+}

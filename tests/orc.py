@@ -26,7 +26,7 @@ def lib():
     global _L
     if _L is not None:
         return _L
-    L = C.CDLL(os.path.join(ROOT, "oracle", "liborc.so"), mode=C.RTLD_GLOBAL)
+    L = C.CDLL(os.path.join(ROOT, "oracle", "liborc.so"), mode=C.RTLD_LOCAL)
     L.orc_crc32.restype = C.c_uint32
     L.orc_crc32.argtypes = [C.c_void_p, C.c_uint]
     for f in ("orc_hamming128_encode_symbol", "orc_hamming128_decode_symbol",

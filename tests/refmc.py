@@ -40,7 +40,7 @@ def _fptr(a):
 
 class McLib:
     def __init__(self, path):
-        self.lib = L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        self.lib = L = C.CDLL(path, mode=C.RTLD_LOCAL)
         L.mcshim_rx_create.restype = C.c_void_p
         L.mcshim_rx_create.argtypes = [C.c_uint] * 4
         L.mcshim_rx_destroy.argtypes = [C.c_void_p]
@@ -170,6 +170,6 @@ def ref_lib():
     """the reference's lib/*.cc over the oracle (oracle/_ref/libref_mc.so)"""
     global _ref
     if _ref is None:
-        C.CDLL(os.path.join(ROOT, "oracle", "liborc.so"), mode=C.RTLD_GLOBAL)
+        C.CDLL(os.path.join(ROOT, "oracle", "liborc.so"), mode=C.RTLD_LOCAL)
         _ref = McLib(os.path.join(ROOT, "oracle", "_ref", "libref_mc.so"))
     return _ref
