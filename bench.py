@@ -17,8 +17,16 @@ silence and the NCO phase is periodic in the period length.
   roofline  dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM peak
   cpu_baseline   the reference's lib/multichannelrx.cc over the oracle, on this box's host CPU
 
-Multi-GPU (--gpus N under torchrun): weak scaling, every rank channelizes and synchronises its own
-wideband stream (independent receivers; no data-path collective), rank 0 gathers the counts.
+Multi-GPU (--gpus N under torchrun), weak scaling in both modes:
+  --mode replicas (default)  every rank runs a complete 256-channel receiver on its own wideband
+                             stream (the natural partition of the path: independent receivers, no
+                             data-path collective; rank 0 only reduces the timings)
+  --mode sharded             ONE wideband stream, N x longer: stage 1 time-sharded, NCCL all-to-all
+                             of the channelizer output, stage 2 channel-sharded (256/N channels per
+                             rank over the whole time axis), frames gathered to rank 0
+                             (liquid-usrp_b200/sharded.py).  Stage 2 is a serial
+                             recurrence per channel, so this mode trades throughput for a single
+                             coherent stream; DESIGN.md discusses it.
 """
 import argparse
 import ctypes as C
@@ -135,6 +143,68 @@ def run_reference(args, rank):
 METRIC = "complex Msamples/s through multichannelrx (64ch OFDM) at 1/2/4/8 GPU vs CPU"
 
 
+def run_sharded(args, rank, local_rank, world, period, expected):
+    """one wideband stream over `world` GPUs: time-sharded channelizer, all-to-all, channel-sharded
+    synchronisers (liquid-usrp_b200/sharded.py)"""
+    import importlib
+    import torch
+    import torch.distributed as dist
+    sh = importlib.import_module("liquid-usrp_b200.sharded")
+    w = WORKLOAD
+    K = 2 * w["N"]
+    t_local = (len(period) // K) * args.reps
+    rxs = sh.ShardedMultichannelRx(w["N"], w["M"], w["cp"], w["taper"], t_local * world, rank, world, device=local_rank)
+    # the stream is periodic in `period`, every shard starts on a period boundary: halo = end of a period
+    tile = np.concatenate([period[-sh.HALO_BLOCKS * K:], np.tile(period, args.reps)])
+    d_x = torch.from_numpy(tile.view(np.float32)).cuda().view(-1, 2)
+    d_x = torch.view_as_complex(d_x)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        rxs.execute_device(d_x)
+        recs, pl = rxs.poll()
+    clk = Clocks(local_rank)
+    clk.start()
+    barrier()
+    t0 = time.perf_counter()
+    nfr = 0
+    for _ in range(args.steps):
+        rxs.execute_device(d_x)
+        recs, pl = rxs.poll()
+        allr, allp = sh.gather_frames(recs, pl, world, rank, torch.device("cuda", local_rank))
+        if rank == 0:
+            nfr += sum(len(r) for r in allr)
+    barrier()
+    dt = time.perf_counter() - t0
+    clk.stop_flag = True
+    clk.join()
+    assert len(recs) >= (w["N"] // world) * (args.reps * world - 1)
+    assert int(recs["payload_valid"].min()) == 1
+    c = int(recs["channel"][0]); o = int(recs["payload_offset"][0])
+    assert np.array_equal(pl[o:o + w["payload"]], expected[c][1])
+    times = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dt = float(times[0])
+    n_step = t_local * world * K
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "value": n_step * args.steps / dt / 1e6, "unit": "Msamples/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic (oracle transmitter, one frame period tiled on device)",
+                          "config": {"workload": w["name"], "samples_per_step": n_step, "frames_per_step": nfr // args.steps,
+                                     "parallelism": "one stream: time-sharded channelizer -> NCCL all-to-all -> %d channels/rank" % (w["N"] // world)},
+                          "gpu_launches": args.steps * (1 + 2 * world) * world, "clocks": clk.summary()}), flush=True)
+    rxs.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,6 +213,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--reps", type=int, default=8, help="frame periods per step (8 -> 21.2 M samples, 170 MB > L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -162,6 +233,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w = WORKLOAD
     period, expected, flen = make_period()
+    if args.mode == "sharded":
+        run_sharded(args, rank, local_rank, world, period, expected)
+        return
     n_step = len(period) * args.reps
     # device-resident input (the "stubbed UHD source"), tiled on the device
     d_period = torch.from_numpy(period.view(np.float32)).cuda()
@@ -195,10 +269,15 @@ def main():
     barrier()
     t0 = time.perf_counter()
     nfr = 0
+    t_exec = t_poll = 0.0
     for _ in range(args.steps):
+        ta = time.perf_counter()
         rx.execute_device(d_x.data_ptr(), n_step)
+        tb = time.perf_counter()
         kt += np.array(rx.last_timing())
-        recs, pl = rx.poll()
+        recs, pl = rx.poll_view()
+        t_poll += time.perf_counter() - tb
+        t_exec += tb - ta
         nfr += len(recs)
     barrier()
     dt = time.perf_counter() - t0
@@ -241,6 +320,7 @@ def main():
                     "d2h_bytes_per_step": d2h // args.steps},
             "gpu_launches": 3 * args.steps,
             "kernels_ms_per_step": {"analyzer_kernel": kt_avg[0], "sync_kernel": kt_avg[1], "packet_decode_kernel": kt_avg[2], "call": kt_avg[3]},
+            "host_ms_per_step": {"execute_call": 1e3 * t_exec / args.steps, "poll_call": 1e3 * t_poll / args.steps},
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "alg_bytes_per_sample": B_ALG[names[dom]],

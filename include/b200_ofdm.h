@@ -80,6 +80,10 @@ int b2_mcrx_execute_device(b2_mcrx * q, const float * x_dev, size_t n);
  * (ascending completion block, then channel).  Pass recs = NULL to get the counts only. */
 int b2_mcrx_poll(b2_mcrx * q, b2_frame_rec * recs, size_t recs_cap, size_t * n_recs,
                  uint8_t * payloads, size_t payloads_cap, size_t * n_payload_bytes);
+/* zero-copy variant: pointers into the handle's own buffers, valid until the next execute, poll
+ * or poll_view on this handle */
+int b2_mcrx_poll_view(b2_mcrx * q, const b2_frame_rec ** recs, size_t * n_recs,
+                      const uint8_t ** payloads, size_t * n_payload_bytes);
 /* debug tap: record every equalised OFDM symbol X[0..M) handed to the header/payload layer */
 int b2_mcrx_tap_symbols(b2_mcrx * q, int enable, size_t max_symbols);
 int b2_mcrx_read_symbols(b2_mcrx * q, uint32_t * channel, uint64_t * index, float * X, size_t cap, size_t * n);
@@ -90,6 +94,17 @@ int b2_mcrx_last_timing(b2_mcrx * q, float ms[4]);
 int b2_mcrx_read_channelizer(b2_mcrx * q, float * out, size_t cap_samples, size_t * n_blocks);
 /* the CUDA stream the kernels of this handle are launched on (cudaStream_t) */
 void * b2_mcrx_stream(b2_mcrx * q);
+/* Stage 1 alone, stateless, for a time shard of the wideband stream (multi-GPU):
+ * x_dev points at the first of (P-1) = 13 halo blocks that precede the shard (zeros at the very
+ * start of a stream), followed by n_blocks blocks of 2N samples; sample_offset is the absolute
+ * index of x_dev[0] in the stream (the NCO phase is exact in it).  Writes out_dev[c*out_stride + b],
+ * c < N, b < n_blocks, on the handle's stream, asynchronously. */
+int b2_mcrx_channelize_device(b2_mcrx * q, const float * x_dev, size_t n_blocks, int64_t sample_offset,
+                              float * out_dev, size_t out_stride);
+/* Stage 2 alone on channelizer output already in device memory: in_dev[c*in_stride + t], c < N,
+ * t < n (the handle's per-channel synchroniser state carries over, so a time-ordered sequence of
+ * calls equals one call); frames are queued for b2_mcrx_poll. */
+int b2_mcrx_sync_device(b2_mcrx * q, const float * in_dev, size_t n, size_t in_stride);
 
 /* ------------------------------------------------------------------ multichanneltx
  * replaces: multichanneltx::multichanneltx        lib/multichanneltx.cc:41-100
@@ -149,6 +164,8 @@ int b2_ofdmsync_execute(b2_ofdmsync * q, const float * x_host, size_t n);
 int b2_ofdmsync_execute_device(b2_ofdmsync * q, const float * x_dev, size_t n, size_t stride);
 int b2_ofdmsync_poll(b2_ofdmsync * q, b2_frame_rec * recs, size_t recs_cap, size_t * n_recs,
                      uint8_t * payloads, size_t payloads_cap, size_t * n_payload_bytes);
+int b2_ofdmsync_poll_view(b2_ofdmsync * q, const b2_frame_rec ** recs, size_t * n_recs,
+                          const uint8_t ** payloads, size_t * n_payload_bytes);
 int b2_ofdmsync_last_timing(b2_ofdmsync * q, float ms[4]);
 
 /* ------------------------------------------------------------------ msresamp_crcf

@@ -42,17 +42,21 @@ _PROTOS = {
     "b2_mcrx_execute": (C.c_int, [_vp, _vp, _sz]),
     "b2_mcrx_execute_device": (C.c_int, [_vp, _vp, _sz]),
     "b2_mcrx_poll": (C.c_int, [_vp, _vp, _sz, C.POINTER(_sz), _vp, _sz, C.POINTER(_sz)]),
+    "b2_mcrx_poll_view": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), C.POINTER(_sz)]),
     "b2_mcrx_tap_symbols": (C.c_int, [_vp, C.c_int, _sz]),
     "b2_mcrx_read_symbols": (C.c_int, [_vp, _vp, _vp, _vp, _sz, C.POINTER(_sz)]),
     "b2_mcrx_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float * 4)]),
     "b2_mcrx_read_channelizer": (C.c_int, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "b2_mcrx_stream": (_vp, [_vp]),
+    "b2_mcrx_channelize_device": (C.c_int, [_vp, _vp, _sz, C.c_int64, _vp, _sz]),
+    "b2_mcrx_sync_device": (C.c_int, [_vp, _vp, _sz, _sz]),
     "b2_ofdmsync_create": (C.c_int, [C.c_uint, C.c_uint, C.c_uint, _vp, C.c_uint, C.c_int, _sz, C.POINTER(_vp)]),
     "b2_ofdmsync_destroy": (C.c_int, [_vp]),
     "b2_ofdmsync_reset": (C.c_int, [_vp]),
     "b2_ofdmsync_execute": (C.c_int, [_vp, _vp, _sz]),
     "b2_ofdmsync_execute_device": (C.c_int, [_vp, _vp, _sz, _sz]),
     "b2_ofdmsync_poll": (C.c_int, [_vp, _vp, _sz, C.POINTER(_sz), _vp, _sz, C.POINTER(_sz)]),
+    "b2_ofdmsync_poll_view": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), C.POINTER(_sz)]),
     "b2_ofdmsync_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float * 4)]),
     "b2_mctx_create": (C.c_int, [C.c_uint, C.c_uint, C.c_uint, C.c_uint, _vp, C.c_int, C.POINTER(_vp)]),
     "b2_mctx_destroy": (C.c_int, [_vp]),
@@ -116,11 +120,22 @@ class _FrameSource:
         """-> (records as a FRAME_DTYPE array, payload bytes); clears the queue"""
         n, nb = _sz(0), _sz(0)
         _check(self._fn("poll")(self.h, None, 0, C.byref(n), None, 0, C.byref(nb)))
-        recs = np.zeros(n.value, FRAME_DTYPE)
-        pl = np.zeros(max(nb.value, 1), np.uint8)
+        recs = np.empty(n.value, FRAME_DTYPE)
+        pl = np.empty(max(nb.value, 1), np.uint8)
         if n.value:
             _check(self._fn("poll")(self.h, recs.ctypes.data, n.value, C.byref(n), pl.ctypes.data, len(pl), C.byref(nb)))
         return recs, pl[:nb.value]
+
+    def poll_view(self):
+        """zero-copy poll: arrays alias the library's buffers and are valid only until the next
+        execute / poll on this handle"""
+        pr, pp, n, nb = _vp(), _vp(), _sz(0), _sz(0)
+        _check(self._fn("poll_view")(self.h, C.byref(pr), C.byref(n), C.byref(pp), C.byref(nb)))
+        if n.value == 0:
+            return np.zeros(0, FRAME_DTYPE), np.zeros(0, np.uint8)
+        recs = np.frombuffer((C.c_char * (n.value * FRAME_DTYPE.itemsize)).from_address(pr.value), dtype=FRAME_DTYPE)
+        pl = np.frombuffer((C.c_char * max(nb.value, 1)).from_address(pp.value), dtype=np.uint8)[:nb.value] if nb.value else np.zeros(0, np.uint8)
+        return recs, pl
 
     def last_timing(self):
         ms = (C.c_float * 4)()
@@ -183,6 +198,12 @@ class MultichannelRx(_FrameSource):
 
     def stream(self):
         return lib().b2_mcrx_stream(self.h)
+
+    def channelize_device(self, x_ptr, n_blocks, sample_offset, out_ptr, out_stride):
+        _check(lib().b2_mcrx_channelize_device(self.h, _ptr(x_ptr), n_blocks, sample_offset, _ptr(out_ptr), out_stride))
+
+    def sync_device(self, in_ptr, n, in_stride):
+        _check(lib().b2_mcrx_sync_device(self.h, _ptr(in_ptr), n, in_stride))
 
 
 class OfdmSync(_FrameSource):

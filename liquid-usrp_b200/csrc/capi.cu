@@ -49,6 +49,8 @@ struct SyncCore {
     // results waiting for poll()
     std::vector<FrameRec> ready;
     std::vector<uint8_t> ready_payloads;
+    std::vector<FrameRec> view_recs;     // handed out by poll_view(), alive until the next poll/execute
+    std::vector<uint8_t> view_payloads;
     // kernel config
     int sync_threads = 128;
     size_t sync_smem = 0;
@@ -66,6 +68,7 @@ struct SyncCore {
     int run(const cf * in, size_t in_stride, unsigned int nsamples, bool record_events);
     int collect();
     int poll(b2_frame_rec * recs, size_t recs_cap, size_t * n_recs, uint8_t * payloads, size_t payloads_cap, size_t * n_payload_bytes);
+    int poll_view(const b2_frame_rec ** recs, size_t * n_recs, const uint8_t ** payloads, size_t * n_payload_bytes);
     int set_tap(int enable, size_t max_symbols);
 };
 
@@ -177,6 +180,18 @@ int SyncCore::reset_state()
     return B2_OK;
 }
 
+int SyncCore::poll_view(const b2_frame_rec ** recs, size_t * n_recs, const uint8_t ** payloads, size_t * n_payload_bytes)
+{
+    view_recs.clear(); view_payloads.clear();
+    view_recs.swap(ready);
+    view_payloads.swap(ready_payloads);
+    if (recs) *recs = (const b2_frame_rec *)view_recs.data();
+    if (n_recs) *n_recs = view_recs.size();
+    if (payloads) *payloads = view_payloads.data();
+    if (n_payload_bytes) *n_payload_bytes = view_payloads.size();
+    return B2_OK;
+}
+
 int SyncCore::reset_streams()
 {
     B2_CUDA(sync_reset_launch(d_st.as<SyncState>(), streams, stream));
@@ -244,12 +259,17 @@ int SyncCore::collect()
             if (h_recs[a].complete_index != h_recs[b].complete_index) return h_recs[a].complete_index < h_recs[b].complete_index;
             return h_recs[a].channel < h_recs[b].channel;
         });
+        size_t total = 0;
+        for (unsigned int i = 0; i < nrec; i++) if (h_recs[i].header_valid) total += h_recs[i].payload_len;
+        size_t o = ready_payloads.size();
+        ready_payloads.resize(o + total);
+        ready.reserve(ready.size() + nrec);
         for (unsigned int i = 0; i < nrec; i++) {
             FrameRec r = h_recs[order[i]];
-            size_t o = ready_payloads.size();
-            if (r.header_valid && r.payload_len)
-                ready_payloads.insert(ready_payloads.end(), h_payload + r.payload_offset, h_payload + r.payload_offset + r.payload_len);
+            const size_t len = (r.header_valid ? r.payload_len : 0);
+            if (len) memcpy(ready_payloads.data() + o, h_payload + r.payload_offset, len);
             r.payload_offset = o;
+            o += len;
             ready.push_back(r);
         }
     }
@@ -467,6 +487,13 @@ extern "C" int b2_mcrx_poll(b2_mcrx * q, b2_frame_rec * recs, size_t recs_cap, s
     return q->core.poll(recs, recs_cap, n_recs, payloads, payloads_cap, n_payload_bytes);
 }
 
+extern "C" int b2_mcrx_poll_view(b2_mcrx * q, const b2_frame_rec ** recs, size_t * n_recs,
+                                 const uint8_t ** payloads, size_t * n_payload_bytes)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    return q->core.poll_view(recs, n_recs, payloads, n_payload_bytes);
+}
+
 extern "C" int b2_mcrx_tap_symbols(b2_mcrx * q, int enable, size_t max_symbols)
 {
     if (!q) return b2_fail(B2_ERR_ARG, "null handle");
@@ -515,6 +542,48 @@ extern "C" int b2_mcrx_read_channelizer(b2_mcrx * q, float * out, size_t cap_sam
 }
 
 extern "C" void * b2_mcrx_stream(b2_mcrx * q) { return q ? (void *)q->stream : nullptr; }
+
+extern "C" int b2_mcrx_channelize_device(b2_mcrx * q, const float * x_dev, size_t n_blocks, int64_t sample_offset,
+                                         float * out_dev, size_t out_stride)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    if (n_blocks == 0) return B2_OK;
+    if (!x_dev || !out_dev) return b2_fail(B2_ERR_ARG, "null pointer");
+    if (((uintptr_t)x_dev) & 15) return b2_fail(B2_ERR_ARG, "input must be 16-byte aligned");
+    if (n_blocks > 0x7fffffffu) return b2_fail(B2_ERR_ARG, "too many blocks in one call");
+    B2_CUDA(cudaSetDevice(q->device));
+    AnalyzerParams ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.seg0 = (const cf *)x_dev; ap.rows0 = 0xffffffffu; ap.seg1 = (const cf *)x_dev;
+    ap.K = q->K; ap.lgK = q->lgK; ap.N = q->N; ap.P = q->P; ap.TB = q->TB;
+    ap.nblocks = (unsigned int)n_blocks;
+    ap.taps = q->t_taps.as<float>();
+    ap.dtheta = q->nco_dtheta;
+    ap.theta0 = (uint32_t)((uint64_t)sample_offset) * q->nco_dtheta;
+    ap.out = (cf *)out_dev; ap.out_stride = out_stride; ap.out_col0 = 0;
+    ap.fft.n = q->K; ap.fft.npass = q->fftK.npass; ap.fft.radices = 0;
+    for (unsigned int i = 0; i < q->fftK.npass; i++) ap.fft.radices |= q->fftK.radix[i] << (4 * i);
+    ap.fft.perm = q->t_perm.as<uint16_t>(); ap.fft.tw = q->t_tw.as<cf>();
+    B2_CUDA(analyzer_launch(ap, q->an_grid, q->an_smem, q->stream));
+    return B2_OK;
+}
+
+extern "C" int b2_mcrx_sync_device(b2_mcrx * q, const float * in_dev, size_t n, size_t in_stride)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    if (n == 0) return B2_OK;
+    if (!in_dev) return b2_fail(B2_ERR_ARG, "null pointer");
+    B2_CUDA(cudaSetDevice(q->device));
+    size_t done = 0;
+    while (done < n) {
+        size_t c = std::min(n - done, q->core.tmax);
+        B2_CUDA(cudaEventRecord(q->core.ev[0], q->stream));
+        int rc = q->core.run((const cf *)in_dev + done, in_stride, (unsigned int)c, true);
+        if (rc) return rc;
+        done += c;
+    }
+    return B2_OK;
+}
 
 // ================================================================== batched single-link synchroniser
 struct b2_ofdmsync_s {
@@ -616,6 +685,12 @@ extern "C" int b2_ofdmsync_poll(b2_ofdmsync * q, b2_frame_rec * recs, size_t rec
 {
     if (!q) return b2_fail(B2_ERR_ARG, "null handle");
     return q->core.poll(recs, recs_cap, n_recs, payloads, payloads_cap, n_payload_bytes);
+}
+extern "C" int b2_ofdmsync_poll_view(b2_ofdmsync * q, const b2_frame_rec ** recs, size_t * n_recs,
+                                     const uint8_t ** payloads, size_t * n_payload_bytes)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    return q->core.poll_view(recs, n_recs, payloads, n_payload_bytes);
 }
 extern "C" int b2_ofdmsync_last_timing(b2_ofdmsync * q, float ms[4])
 {

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -243,8 +244,16 @@ static inline int fft_plan(FftPlan & f, unsigned int n)
     unsigned int lg = ceil_log2(n);
     f.n = n; f.npass = 0;
     unsigned int rem = lg;
+    // experiment knob: B2_FFT_MAX_RADIX=4 builds the plan from radix-4 (and one radix-2) passes
+    if (const char * e = getenv("B2_FFT_MAX_RADIX")) {
+        if (atoi(e) == 4) {
+            if (rem & 1) { f.radix[f.npass++] = 2; rem -= 1; }
+            while (rem >= 2) { f.radix[f.npass++] = 4; rem -= 2; }
+        }
+    }
     // small radices first (cheap passes on short strides), radix-8 for the rest
-    if (rem % 3 == 1 && rem >= 4) { f.radix[f.npass++] = 4; f.radix[f.npass++] = 4; rem -= 4; }
+    if (rem == 0) { }
+    else if (rem % 3 == 1 && rem >= 4) { f.radix[f.npass++] = 4; f.radix[f.npass++] = 4; rem -= 4; }
     else if (rem % 3 == 1) { f.radix[f.npass++] = 2; rem -= 1; }
     else if (rem % 3 == 2) { f.radix[f.npass++] = 4; rem -= 2; }
     while (rem >= 3) { f.radix[f.npass++] = 8; rem -= 3; }

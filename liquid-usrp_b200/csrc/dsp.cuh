@@ -31,6 +31,15 @@ __device__ __forceinline__ cf nco_cexp_pi(uint32_t theta)
     sincospif((float)((double)(int32_t)theta * (1.0 / 2147483648.0)), &s, &c);
     return make_float2(c, s);
 }
+// fast variant for the per-sample mixers: float phase in (-pi, pi], SFU sine/cosine
+// (absolute error ~4e-7 on this range, one order below the 1e-5 budget on equalised symbols)
+__device__ __forceinline__ cf nco_cexp_fast(uint32_t theta)
+{
+    float t = (float)(int32_t)theta * (3.14159265358979323846f / 2147483648.0f);
+    float s, c;
+    __sincosf(t, &s, &c);
+    return make_float2(c, s);
+}
 __device__ __forceinline__ cf mix_down(cf x, cf w) { return make_float2(x.x * w.x + x.y * w.y, x.y * w.x - x.x * w.y); } // x*conj(w)
 __device__ __forceinline__ cf mix_up(cf x, cf w) { return cmul(x, w); }
 
@@ -88,7 +97,7 @@ template <int DIR> __device__ __forceinline__ void dft8(cf * v)
 
 // skewed shared-memory index (one pad element per 32) used where the access stride is a
 // multiple of the bank count (channelizer FFT rows)
-template <int PAD> __device__ __forceinline__ unsigned int phys(unsigned int i) { return PAD ? i + (i >> 5) : i; }
+template <int PAD> __device__ __forceinline__ unsigned int phys(unsigned int i) { return PAD == 2 ? i + (i >> 3) : (PAD ? i + (i >> 5) : i); }
 
 struct FftDev {
     unsigned int n, npass;
@@ -97,27 +106,31 @@ struct FftDev {
     const cf * tw;             // forward twiddles e^{-j 2 pi k / n}
 };
 
-// one radix-R pass over `nfft` transforms of length n laid out back to back in `buf` (row
-// stride `ld` elements); L = sub-transform length after this pass
+// one radix-R pass over `nfft` transforms of length n = 2^lgn laid out back to back in `buf` (row
+// stride `ld` elements); 2^lgL = sub-transform length after this pass.  All sizes are powers of
+// two, so the butterfly index splits with shifts and masks only.
 template <int R, int DIR, int PAD>
-__device__ __forceinline__ void fft_pass(cf * buf, unsigned int ld, unsigned int nfft, unsigned int n, unsigned int L,
+__device__ __forceinline__ void fft_pass(cf * buf, unsigned int ld, unsigned int nfft, unsigned int lgn, unsigned int lgL,
                                          const cf * __restrict__ tw, unsigned int tid, unsigned int nthreads)
 {
-    const unsigned int s = L / R;                 // stride between butterfly inputs
-    const unsigned int per = n / R;               // butterflies per transform
-    const unsigned int tstep = n / L;             // twiddle index step: w_L^j = tw[j * n/L]
-    for (unsigned int w = tid; w < per * nfft; w += nthreads) {
-        unsigned int f = w / per, b = w - f * per;
-        unsigned int blk = b / s, j = b - blk * s;
+    constexpr unsigned int lgR = (R == 8) ? 3 : ((R == 4) ? 2 : 1);
+    const unsigned int lgs = lgL - lgR;           // log2 of the stride between butterfly inputs
+    const unsigned int lgper = lgn - lgR;         // log2 of the butterflies per transform
+    const unsigned int s = 1u << lgs;
+    const unsigned int tshift = lgn - lgL;        // twiddle index step: w_L^j = tw[j << tshift]
+    const unsigned int total = nfft << lgper;
+    for (unsigned int w = tid; w < total; w += nthreads) {
+        const unsigned int f = w >> lgper, b = w & ((1u << lgper) - 1u);
+        const unsigned int blk = b >> lgs, j = b & (s - 1u);
         cf * x = buf + (size_t)f * ld;
-        const unsigned int i0 = blk * L + j;
+        const unsigned int i0 = (blk << lgL) + j;
         cf v[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) v[r] = x[phys<PAD>(i0 + r * s)];
-        if (s > 1) {
+        for (int r = 0; r < R; r++) v[r] = x[phys<PAD>(i0 + (r << lgs))];
+        if (lgs > 0) {
 #pragma unroll
             for (int r = 1; r < R; r++) {
-                cf t = tw[(j * r * tstep) & (n - 1)];
+                cf t = tw[(j * r) << tshift];
                 if (DIR > 0) t.y = -t.y;
                 v[r] = cmul(v[r], t);
             }
@@ -126,7 +139,7 @@ __device__ __forceinline__ void fft_pass(cf * buf, unsigned int ld, unsigned int
         else if (R == 4) dft4<DIR>(v);
         else dft8<DIR>(v);
 #pragma unroll
-        for (int r = 0; r < R; r++) x[phys<PAD>(i0 + r * s)] = v[r];
+        for (int r = 0; r < R; r++) x[phys<PAD>(i0 + (r << lgs))] = v[r];
     }
 }
 
@@ -136,13 +149,44 @@ template <int DIR, int PAD>
 __device__ __forceinline__ void fft_inplace(cf * buf, unsigned int ld, unsigned int nfft, const FftDev & f,
                                             unsigned int tid, unsigned int nthreads)
 {
-    unsigned int L = 1;
+    const unsigned int lgn = 31u - (unsigned int)__clz((int)f.n);
+    unsigned int lgL = 0;
     for (unsigned int t = 0; t < f.npass; t++) {
         unsigned int R = (f.radices >> (4 * t)) & 15u;
-        L *= R;
-        if (R == 8) fft_pass<8, DIR, PAD>(buf, ld, nfft, f.n, L, f.tw, tid, nthreads);
-        else if (R == 4) fft_pass<4, DIR, PAD>(buf, ld, nfft, f.n, L, f.tw, tid, nthreads);
-        else fft_pass<2, DIR, PAD>(buf, ld, nfft, f.n, L, f.tw, tid, nthreads);
+        if (R == 8) { lgL += 3; fft_pass<8, DIR, PAD>(buf, ld, nfft, lgn, lgL, f.tw, tid, nthreads); }
+        else if (R == 4) { lgL += 2; fft_pass<4, DIR, PAD>(buf, ld, nfft, lgn, lgL, f.tw, tid, nthreads); }
+        else { lgL += 1; fft_pass<2, DIR, PAD>(buf, ld, nfft, lgn, lgL, f.tw, tid, nthreads); }
+        __syncthreads();
+    }
+}
+
+// the same pass plan as design.h fft_plan() (radix-4 passes first when log2 n is not a multiple
+// of 3, radix-8 for the rest), with every size known at compile time
+__host__ __device__ constexpr unsigned int fft_static_radices(unsigned int n)
+{
+    unsigned int lg = 0;
+    while ((1u << lg) < n) lg++;
+    unsigned int r = 0, np = 0, rem = lg;
+    if (rem % 3 == 1 && rem >= 4) { r |= 4u << (4 * np++); r |= 4u << (4 * np++); rem -= 4; }
+    else if (rem % 3 == 1) { r |= 2u << (4 * np++); rem -= 1; }
+    else if (rem % 3 == 2) { r |= 4u << (4 * np++); rem -= 2; }
+    while (rem >= 3) { r |= 8u << (4 * np++); rem -= 3; }
+    return r;
+}
+template <unsigned int N, int DIR, int PAD>
+__device__ __forceinline__ void fft_static(cf * buf, const cf * __restrict__ tw, unsigned int tid, unsigned int nthreads)
+{
+    constexpr unsigned int radices = fft_static_radices(N);
+    constexpr unsigned int lgn = (N <= 2) ? 1 : (N <= 4) ? 2 : (N <= 8) ? 3 : (N <= 16) ? 4 : (N <= 32) ? 5 : (N <= 64) ? 6 : (N <= 128) ? 7 :
+                                 (N <= 256) ? 8 : (N <= 512) ? 9 : (N <= 1024) ? 10 : (N <= 2048) ? 11 : 12;
+    unsigned int lgL = 0;
+#pragma unroll
+    for (unsigned int t = 0; t < 6; t++) {
+        const unsigned int R = (radices >> (4 * t)) & 15u;
+        if (R == 0) break;
+        if (R == 8) { lgL += 3; fft_pass<8, DIR, PAD>(buf, N, 1, lgn, lgL, tw, tid, nthreads); }
+        else if (R == 4) { lgL += 2; fft_pass<4, DIR, PAD>(buf, N, 1, lgn, lgL, tw, tid, nthreads); }
+        else { lgL += 1; fft_pass<2, DIR, PAD>(buf, N, 1, lgn, lgL, tw, tid, nthreads); }
         __syncthreads();
     }
 }

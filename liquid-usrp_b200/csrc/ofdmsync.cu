@@ -25,6 +25,7 @@
 namespace b2 {
 
 #define PI_F 3.14159274101257324219f
+#define PX(i) ((i) + ((i) >> 3))          // skewed index into the FFT buffer (one pad per 8: radix-8 strides)
 
 void sync_state_init(SyncState & s, unsigned int M, unsigned int cp)
 {
@@ -42,7 +43,7 @@ void sync_state_init(SyncState & s, unsigned int M, unsigned int cp)
 struct SyLayout {
     unsigned int SZ;            // staging ring size (power of two)
     unsigned int PF;            // prefetch distance (samples)
-    size_t off_st, off_red, off_dsum, off_ring, off_X, off_G0, off_T, off_R, off_tw, off_perm, off_rank, off_sym, off_yph, off_stg, total;
+    size_t off_st, off_red, off_dsum, off_ring, off_X, off_G0, off_T, off_R, off_tw, off_perm, off_rank, off_sym, off_yph, off_stg, off_ref, off_px, off_pseq, total;
 };
 __host__ __device__ static inline SyLayout sy_layout(unsigned int M, unsigned int cp, unsigned int Na)
 {
@@ -55,7 +56,7 @@ __host__ __device__ static inline SyLayout sy_layout(unsigned int M, unsigned in
     L.off_red = o;  o += 128 * sizeof(float);
     L.off_dsum = o; o += (8 * 19 + 40) * sizeof(double);
     L.off_ring = o; o += (size_t)(M + cp) * sizeof(cf);
-    L.off_X = o;    o += (size_t)M * sizeof(cf);
+    L.off_X = o;    o += (size_t)(M + (M >> 3) + 2) * sizeof(cf);      // skewed: one pad element per 8
     L.off_G0 = o;   o += (size_t)M * sizeof(cf);
     L.off_T = o;    o += (size_t)M * sizeof(cf);
     L.off_R = o;    o += (size_t)M * sizeof(cf);
@@ -66,6 +67,9 @@ __host__ __device__ static inline SyLayout sy_layout(unsigned int M, unsigned in
     L.off_yph = o;  o += (size_t)(Na + 4) * sizeof(float) * 3;
     o = (o + 15) & ~(size_t)15;
     L.off_stg = o;  o += (size_t)L.SZ * sizeof(cf);
+    L.off_ref = o;  o += (size_t)2 * M * sizeof(float);            // S0 | S1 training signs
+    L.off_px = o;   o += (size_t)(Na + 4) * sizeof(float);         // pilot abscissae (at most Na pilots)
+    L.off_pseq = o; o += 256;                                      // one period of the pilot LFSR
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
@@ -138,10 +142,12 @@ __device__ __forceinline__ void warp_unwrap(float * y, const float * __restrict_
             float d = raw - prev;
             k = (d > PI_F) ? -1 : ((d < -PI_F) ? 1 : 0);
         }
+        if (__any_sync(0xffffffffu, k != 0)) {      // rare: most symbols need no unwrapping at all
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, k, o);
-            if (lane >= (unsigned int)o) k += t;
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, k, o);
+                if (lane >= (unsigned int)o) k += t;
+            }
         }
         k += carry;
         carry = __shfl_sync(0xffffffffu, k, 31);
@@ -176,11 +182,13 @@ __device__ __forceinline__ void solve5(const double * __restrict__ S, const doub
                 for (int i = 0; i < 6; i++) { double t = A[c][i]; A[c][i] = A[r][i]; A[r][i] = t; }
             }
         }
+        const double inv = 1.0 / A[c][c];          // one reciprocal per pivot (double division is slow)
+        A[c][c] = inv;
 #pragma unroll
         for (int r = c + 1; r < 5; r++) {
-            double f = A[r][c] / A[c][c];
+            double f = A[r][c] * inv;
 #pragma unroll
-            for (int i = c; i < 6; i++) A[r][i] -= f * A[c][i];
+            for (int i = c + 1; i < 6; i++) A[r][i] -= f * A[c][i];
         }
     }
     double p[5];
@@ -189,7 +197,7 @@ __device__ __forceinline__ void solve5(const double * __restrict__ S, const doub
         double s = A[r][5];
 #pragma unroll
         for (int c = r + 1; c < 5; c++) s -= A[r][c] * p[c];
-        p[r] = s / A[r][r];
+        p[r] = s * A[r][r];                        // diagonal holds the reciprocal pivot
     }
 #pragma unroll
     for (int i = 0; i < 5; i++) coef[i] = p[i];
@@ -209,12 +217,29 @@ __device__ __forceinline__ uint32_t crc32_nibble(const uint8_t * m, unsigned int
     return ~key;
 }
 
+// optional phase profile (build with -DB2_SYNC_PROF): cycles spent by CTA 0 between barriers
+#ifdef B2_SYNC_PROF
+__device__ unsigned long long g_sync_prof[16];
+#define PH(k) do { if (blockIdx.x == 0 && tid == 0) { long long _t = clock64(); atomicAdd(&g_sync_prof[k], (unsigned long long)(_t - t_last)); t_last = _t; } } while (0)
+extern "C" int b2_debug_sync_prof(unsigned long long * out, int reset)
+{
+    if (out) cudaMemcpyFromSymbol(out, g_sync_prof, sizeof(g_sync_prof));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_sync_prof, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define PH(k) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------ the kernel
+// MT / NT: number of subcarriers / threads known at compile time (0 = take them from the
+// launch), so the per-subcarrier loops unroll and the FFT passes are fixed
+template <unsigned int MT, unsigned int NT>
 __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const unsigned int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = (nt + 31) >> 5;
-    const unsigned int M = p.M, cp = p.cp, W = M + cp, M2 = p.M2;
+    const unsigned int tid = threadIdx.x, nt = NT ? NT : blockDim.x, lane = tid & 31, wid = tid >> 5, nw = (nt + 31) >> 5;
+    const unsigned int M = MT ? MT : p.M, cp = p.cp, W = M + cp, M2 = M / 2;
     const unsigned int sidx = blockIdx.x;
     const unsigned int Na = p.M_pilot + p.M_data;
     const SyLayout L = sy_layout(M, cp, Na);
@@ -232,6 +257,9 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
     uint8_t * sym = (uint8_t *)(smem + L.off_sym);
     float * yph = (float *)(smem + L.off_yph);         // [0..Na): y / y_arg, [Na..2Na): y_abs, [2Na..3Na): x_freq
     cf * stg = (cf *)(smem + L.off_stg);
+    float * refS = (float *)(smem + L.off_ref);
+    float * pilot_x = (float *)(smem + L.off_px);
+    uint8_t * pilot_seq = (uint8_t *)(smem + L.off_pseq);
     const unsigned int SZM = L.SZ - 1, PF = L.PF;
 
     const cf * in = p.in + (size_t)sidx * p.in_stride;
@@ -255,13 +283,20 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
         for (unsigned int i = tid; i < M; i += nt) {
             G0[i] = g0[i]; R[i] = gR[i];
             tw[i] = p.fft.tw[i];
-            perm[i] = p.fft.perm[i];
+            perm[i] = (uint16_t)phys<2>(p.fft.perm[i]);         // FFT buffer positions are skewed (bank conflicts)
             rank[i] = p.tb.sc_rank[i];
+            refS[i] = p.tb.S0[i];
+            refS[M + i] = p.tb.S1[i];
         }
+        for (unsigned int i = tid; i < p.M_pilot; i += nt) pilot_x[i] = p.tb.pilot_x[i];
+        for (unsigned int i = tid; i < 255; i += nt) pilot_seq[i] = p.tb.pilot_seq[i];
     }
     FftDev fft = p.fft;
     fft.tw = tw; fft.perm = perm;
     unsigned int pos = 0;
+#ifdef B2_SYNC_PROF
+    long long t_last = clock64();
+#endif
 
     // block-wide sum of up to 4 floats per thread; result in red[100..103] after the call
     auto block_sum4 = [&](float a, float b, float c, float d) {
@@ -293,8 +328,10 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
     };
 
     while (true) {
+        PH(6);
         cp_async_wait_all();
         __syncthreads();                     // staged samples + state of the previous event visible
+        PH(0);
         // ---- advance to the next event (or to the end of this launch's samples)
         const int state = S->state;
         const int timer = S->timer;
@@ -309,10 +346,11 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
         const bool fire = (adv == need);
         const unsigned int off = (state == ST_RX) ? cp - p.backoff : cp;    // FFT window offset in the sample window
         const bool fused = fire && (adv >= W - off);                        // FFT window made of new samples only
+        const bool mixing = (state != ST_SEEK) && ((th | dth) != 0u);     // e^{-j0} = 1 exactly
         float en = 0.f;
         for (unsigned int j = tid; j < adv; j += nt) {
             cf x = stg[(pos + j) & SZM];
-            if (state != ST_SEEK) x = mix_down(x, nco_cexp(th + j * dth));
+            if (mixing) x = mix_down(x, nco_cexp_fast(th + j * dth));
             if (j + W >= adv) {
                 unsigned int k = head + j;
                 while (k >= W) k -= W;
@@ -330,6 +368,7 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
         unsigned int head2 = head + adv;
         while (head2 >= W) head2 -= W;
         __syncthreads();
+        PH(1);
         if (tid == 0) {
             S->ring_head = head2;
             if (state != ST_SEEK) S->nco_theta = th + adv * dth;
@@ -350,22 +389,25 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
             }
             __syncthreads();
         }
-        fft_inplace<-1, 0>(X, M, 1, fft, tid, nt);
+        PH(8);
+        if (MT) fft_static<MT, -1, 2>(X, tw, tid, nt);
+        else fft_inplace<-1, 2>(X, M, 1, fft, tid, nt);
+        PH(2);
 
         if (state != ST_RX) {
             // ---- preamble events.  G[i] = X[i]*ref[i]*gain on the training subcarriers
             const bool long_seq = (state == ST_S1);
-            const float * __restrict__ ref = long_seq ? p.tb.S1 : p.tb.S0;
+            const float * __restrict__ ref = long_seq ? refS + M : refS;
             const unsigned int step = long_seq ? 1u : 2u;
             const float gain = sqrtf((float)(long_seq ? p.M_S1 : p.M_S0)) / (float)M;
             float mr = 0.f, mi = 0.f, cr = 0.f, ci = 0.f;
             for (unsigned int i = tid; i < M; i += nt) {
                 float r = ref[i];
-                cf g = make_float2(X[i].x * r * gain, X[i].y * r * gain);
+                cf g = make_float2(X[PX(i)].x * r * gain, X[PX(i)].y * r * gain);
                 if ((i & (step - 1)) == 0) {
                     unsigned int i2 = (i + step) & (M - 1);
                     float r2 = ref[i2];
-                    cf g2 = make_float2(X[i2].x * r2 * gain, X[i2].y * r2 * gain);
+                    cf g2 = make_float2(X[PX(i2)].x * r2 * gain, X[PX(i2)].y * r2 * gain);
                     cf t = cmulc(g2, g);
                     mr += t.x; mi += t.y;
                 }
@@ -497,26 +539,28 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
                     }
                 }
             }
+            PH(7);
             continue;                        // loop top synchronises
         }
 
         // ---- ST_RX: one OFDM symbol.  Equalise (each thread owns subcarriers tid, tid+nt, ...)
         const unsigned int ppos = S->pilot_pos;
         for (unsigned int i = tid; i < M; i += nt) {
-            cf xe = cmul(X[i], R[i]);
-            X[i] = xe;
+            cf xe = cmul(X[PX(i)], R[i]);
+            X[PX(i)] = xe;
             unsigned int rk = rank[i];
             if ((rk & 0xC000u) == 0x4000u) {
                 unsigned int n = rk & 0x3fffu;
                 unsigned int q = (ppos + n) % 255u;
-                float pil = p.tb.pilot_seq[q] ? 1.0f : -1.0f;
+                float pil = pilot_seq[q] ? 1.0f : -1.0f;
                 yph[n] = atan2f(xe.y * pil, xe.x * pil);
             }
         }
         __syncthreads();
+        PH(3);
         if (wid == 0) {
             float sy, sxy;
-            warp_unwrap(yph, p.tb.pilot_x, p.M_pilot, false, lane, sy, sxy);
+            warp_unwrap(yph, pilot_x, p.M_pilot, false, lane, sy, sxy);
             sy = warp_sum(sy);
             sxy = warp_sum(sxy);
             if (lane == 0) {
@@ -541,6 +585,7 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
             }
         }
         __syncthreads();
+        PH(4);
 
         // ---- derotate own subcarriers, demap the data ones
         const int fstate = S->fstate;
@@ -553,13 +598,13 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
             const float alpha = p.qam_alpha[bps];
             for (unsigned int i = tid; i < M; i += nt) {
                 unsigned int rk = rank[i];
-                if (rk == 0xffffu) { X[i] = make_float2(0.f, 0.f); continue; }
+                if (rk == 0xffffu) { X[PX(i)] = make_float2(0.f, 0.f); continue; }
                 float fx = (i > M2) ? (float)i - (float)M : (float)i;
                 float thv = __fadd_rn(p0, __fmul_rn(p1, fx));
                 float sn, cs;
-                sincosf(thv, &sn, &cs);
-                cf x = cmul(X[i], make_float2(cs, -sn));
-                X[i] = x;
+                __sincosf(thv, &sn, &cs);
+                cf x = cmul(X[PX(i)], make_float2(cs, -sn));
+                X[PX(i)] = x;
                 if (rk < take) {
                     if (fstate == FS_HEADER) {
                         unsigned int b = x.x > 0 ? 0u : 1u;
@@ -574,6 +619,7 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
         }
         if (fstate == FS_HEADER) block_sum4(ev, 0.f, 0.f, 0.f);      // two barriers inside
         else __syncthreads();
+        PH(5);
 
         // ---- debug tap of the equalised symbol
         if (p.tap_cap) {
@@ -581,7 +627,7 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
             __syncthreads();
             unsigned int slot = __float_as_uint(red[113]);
             if (slot < p.tap_cap) {
-                for (unsigned int i = tid; i < M; i += nt) p.tap_X[(size_t)slot * M + i] = X[i];
+                for (unsigned int i = tid; i < M; i += nt) p.tap_X[(size_t)slot * M + i] = X[PX(i)];
                 if (tid == 0) { p.tap_chan[slot] = sidx; p.tap_index[slot] = S->sample_index - 1; }
             }
         }
@@ -779,16 +825,44 @@ cudaError_t sync_reset_launch(SyncState * st, unsigned int streams, cudaStream_t
     return cudaGetLastError();
 }
 
-cudaError_t sync_configure(size_t smem_bytes)
+template <unsigned int MT, unsigned int NT>
+static cudaError_t sync_launch_t(const SyncParams & p, int threads, size_t smem_bytes, cudaStream_t st)
 {
-    return cudaFuncSetAttribute(sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    static size_t configured = 0;
+    if (smem_bytes > configured) {
+        cudaError_t e = cudaFuncSetAttribute(sync_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        configured = smem_bytes;
+    }
+    sync_kernel<MT, NT><<<p.streams, threads, smem_bytes, st>>>(p);
+    return cudaGetLastError();
 }
+
+cudaError_t sync_configure(size_t smem_bytes) { (void)smem_bytes; return cudaSuccess; }
 
 cudaError_t sync_launch(const SyncParams & p, int threads, size_t smem_bytes, cudaStream_t st)
 {
     if (p.nsamples == 0 || p.streams == 0) return cudaSuccess;
-    sync_kernel<<<p.streams, threads, smem_bytes, st>>>(p);
-    return cudaGetLastError();
+    // the fixed-size instances assume the default pass plan of design.h fft_plan()
+    const bool std_plan = p.fft.radices == fft_static_radices(p.M);
+    if (std_plan && threads == 256) {
+        switch (p.M) {
+        case 64:   return sync_launch_t<64, 256>(p, threads, smem_bytes, st);
+        case 128:  return sync_launch_t<128, 256>(p, threads, smem_bytes, st);
+        case 256:  return sync_launch_t<256, 256>(p, threads, smem_bytes, st);
+        case 512:  return sync_launch_t<512, 256>(p, threads, smem_bytes, st);
+        case 1024: return sync_launch_t<1024, 256>(p, threads, smem_bytes, st);
+        default: break;
+        }
+    } else if (std_plan && threads == 128) {
+        switch (p.M) {
+        case 64:   return sync_launch_t<64, 128>(p, threads, smem_bytes, st);
+        case 128:  return sync_launch_t<128, 128>(p, threads, smem_bytes, st);
+        case 256:  return sync_launch_t<256, 128>(p, threads, smem_bytes, st);
+        default: break;
+        }
+    }
+    return sync_launch_t<0, 0>(p, threads, smem_bytes, st);
 }
 
 } // namespace b2

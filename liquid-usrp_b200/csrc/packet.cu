@@ -18,6 +18,8 @@
 namespace b2 {
 
 constexpr int PK_THREADS = 256;
+constexpr unsigned int PKF_MAX = 4096;              // longest packet the uncoded fast path stages (bytes)
+constexpr int PKF_WARPS = 8;
 constexpr unsigned int PK_TB_STEPS = 2048;          // traceback staging chunk (steps)
 
 __device__ __forceinline__ unsigned int pk_fec_enc_len(unsigned int scheme, unsigned int n)
@@ -271,6 +273,7 @@ __global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketP
         FrameRec * rec = p.recs + ri;
         if (!rec->header_valid) continue;
         const unsigned int plen = rec->payload_len, check = rec->check, fec0 = rec->fec0, fec1 = rec->fec1;
+        if (fec0 == 1 && fec1 == 1 && plen + 4 <= PKF_MAX) continue;      // done by packet_plain_kernel
         const unsigned long long off = rec->payload_offset;
         const unsigned int crc_len = (check == 6) ? 4u : 0u;
         const unsigned int n0 = plen + crc_len;
@@ -490,6 +493,63 @@ cudaError_t packet_encode_launch(const EncodeParams & p, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// ================================================================== uncoded frames: one WARP per frame
+// fec0 = fec1 = none (BASELINE configs 1, 4, 5): the packet is the payload followed by its CRC.
+// Each warp copies its frame through shared memory and checks the CRC with a 256-entry table:
+// lane 0 takes the first n - 31*per bytes, lanes 1..31 take `per` bytes each, and the partial
+// registers are merged in a 5-level tree with x^(8*per*2^l) mod P products.
+
+
+
+__global__ void __launch_bounds__(PKF_WARPS * 32) packet_plain_kernel(const PacketParams p)
+{
+    __shared__ uint32_t table[256];
+    __shared__ __align__(16) uint8_t stage[PKF_WARPS][PKF_MAX];
+    const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    {
+        uint32_t c = tid;
+#pragma unroll
+        for (int j = 0; j < 8; j++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+        table[tid] = c;                          // blockDim.x == 256
+    }
+    __syncthreads();
+    const unsigned int nrec = p.counters[0];
+    for (unsigned int ri = p.first_rec + blockIdx.x * PKF_WARPS + wid; ri < nrec; ri += gridDim.x * PKF_WARPS) {
+        FrameRec * rec = p.recs + ri;
+        if (!rec->header_valid || rec->fec0 != 1 || rec->fec1 != 1) continue;
+        const unsigned int plen = rec->payload_len, crc_len = (rec->check == 6) ? 4u : 0u, n0 = plen + crc_len;
+        if (n0 > PKF_MAX) continue;              // left to the general kernel
+        const unsigned long long off = rec->payload_offset;
+        const uint32_t * src = (const uint32_t *)(p.arena + off);       // offsets are 16-byte aligned
+        uint32_t * dst = (uint32_t *)(p.decoded + off);
+        uint32_t * st = (uint32_t *)stage[wid];
+        for (unsigned int i = lane; i < (n0 + 3) / 4; i += 32) { uint32_t v = src[i]; st[i] = v; dst[i] = v; }
+        __syncwarp();
+        int valid = 1;
+        if (crc_len) {
+            const uint8_t * m = stage[wid];
+            const unsigned int per = plen / 32, first = plen - 31 * per;
+            const unsigned int lo = lane ? first + (lane - 1) * per : 0, hi = lane ? lo + per : first;
+            uint32_t key = lane ? 0u : ~0u;
+            for (unsigned int i = lo; i < hi; i++) key = (key >> 8) ^ table[(key ^ m[i]) & 0xffu];
+            // tree merge; the right operand of every merge spans a multiple of `per` bytes
+            uint32_t xp = crc_x8n(per);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t right = __shfl_down_sync(0xffffffffu, key, o);
+                if ((lane & (2 * o - 1)) == 0) key = crc_multmodp(xp, key) ^ right;
+                xp = crc_multmodp(xp, xp);
+            }
+            if (lane == 0) {
+                uint32_t want = ((uint32_t)m[plen] << 24) | ((uint32_t)m[plen + 1] << 16) | ((uint32_t)m[plen + 2] << 8) | m[plen + 3];
+                valid = (~key == want);
+            }
+        }
+        if (lane == 0) rec->payload_valid = valid;
+        __syncwarp();
+    }
+}
+
 static uint2 * g_vit_ws[16] = {nullptr};
 static size_t g_vit_ws_stride[16] = {0};
 static int g_vit_ws_grid[16] = {0};
@@ -508,6 +568,7 @@ cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t 
         g_vit_ws_stride[dev] = steps;
         g_vit_ws_grid[dev] = grid;
     }
+    packet_plain_kernel<<<grid, PKF_WARPS * 32, 0, st>>>(p);
     packet_decode_kernel<<<grid, PK_THREADS, 0, st>>>(p, g_vit_ws[dev], g_vit_ws_stride[dev]);
     return cudaGetLastError();
 }

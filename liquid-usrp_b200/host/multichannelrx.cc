@@ -126,11 +126,12 @@ void multichannelrx::Flush()
 // replay the user callbacks: ascending completion block, then channel (lib/multichannelrx.cc:193-194)
 void multichannelrx::Deliver()
 {
+    // zero-copy view of the frames completed so far; pointers stay valid during the callbacks
+    // because nothing below touches the handle
     size_t n = 0, nb = 0;
-    if (b2_mcrx_poll(rx, NULL, 0, &n, NULL, 0, &nb) != B2_OK || n == 0) return;
-    std::vector<b2_frame_rec> recs(n);
-    std::vector<uint8_t> payloads(nb ? nb : 1);
-    if (b2_mcrx_poll(rx, recs.data(), n, &n, payloads.data(), payloads.size(), &nb) != B2_OK) {
+    const b2_frame_rec * recs = NULL;
+    const uint8_t * payloads = NULL;
+    if (b2_mcrx_poll_view(rx, &recs, &n, &payloads, &nb) != B2_OK) {
         fprintf(stderr, "error: multichannelrx::Execute(), %s\n", b2_last_error());
         throw 0;
     }
@@ -144,7 +145,7 @@ void multichannelrx::Deliver()
         stats.check = r.check; stats.fec0 = r.fec0; stats.fec1 = r.fec1;
         unsigned char header[8];
         memcpy(header, r.header, 8);
-        unsigned char * payload = (r.header_valid && r.payload_len) ? payloads.data() + r.payload_offset : NULL;
+        unsigned char * payload = (r.header_valid && r.payload_len) ? (unsigned char *)payloads + r.payload_offset : NULL;
         tls_detect_index = r.detect_index;
         tls_complete_index = r.complete_index;
         callback[r.channel](header, r.header_valid, payload, r.payload_len, r.payload_valid, stats, userdata[r.channel]);

@@ -236,3 +236,40 @@ def test_error_codes_match_reference_throws():
     with pytest.raises(pkg.B2Error) as e:
         pkg.MultichannelRx(3, 64, 16, 4)          # legal for liquid, outside the CUDA path
     assert e.value.code == -2
+
+
+def test_stagewise_and_sharded_world1_equal_monolithic():
+    """b2_mcrx_channelize_device + b2_mcrx_sync_device, and the ShardedMultichannelRx plumbing with
+    a single rank, reproduce b2_mcrx_execute"""
+    import importlib
+    import torch
+    from b2 import pkg
+    sh = importlib.import_module("liquid-usrp_b200.sharded")
+    case = CASES["c2_8ch_h128"]
+    N, M, cp, taper = case[:4]
+    K = 2 * N
+    x = make_input(case)
+    x = x[:(len(x) // (2 * K)) * 2 * K]
+    fo, po, _ = run_oracle(case, x)
+    T = len(x) // K
+    H = sh.HALO_BLOCKS
+    # two calls of T/2 blocks each through the sharded front end
+    rxs = sh.ShardedMultichannelRx(N, M, cp, taper, T // 2, 0, 1, device=0)
+    pad = np.concatenate([np.zeros(H * K, np.complex64), x])
+    for call in range(2):
+        seg = pad[call * (T // 2) * K:(call * (T // 2) + H + T // 2) * K]
+        d = torch.from_numpy(seg.copy()).cuda()
+        rxs.execute_device(d)
+    fg, pg = rxs.poll()
+    rxs.close()
+    assert_frames_equal(fo, po, fg, pg)
+    # stage-wise calls on one handle
+    g = pkg.MultichannelRx(N, M, cp, taper)
+    d = torch.from_numpy(pad.copy()).cuda()
+    out = torch.empty((N, T), dtype=torch.complex64, device="cuda")
+    g.channelize_device(d.data_ptr(), T, -H * K, out.data_ptr(), T)
+    torch.cuda.synchronize()
+    g.sync_device(out.data_ptr(), T, T)
+    fg, pg = g.poll()
+    g.close()
+    assert_frames_equal(fo, po, fg, pg)
