@@ -30,7 +30,7 @@ struct SyncCore {
     unsigned int streams = 0;
     size_t tmax = 0;                     // max samples per stream per launch
     // tables
-    DevBuf t_sctype, t_S0, t_S1, t_data, t_pilot, t_pilotx, t_active, t_seq, t_walk, t_B, t_perm, t_tw, t_rank;
+    DevBuf t_sctype, t_S0, t_S1, t_data, t_pilot, t_pilotx, t_active, t_seq, t_walk, t_B, t_perm, t_tw, t_rank, t_P;
     // state
     DevBuf d_st, d_ring, d_G0, d_R, d_penc;
     size_t penc_cap = 0;
@@ -103,14 +103,18 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     for (size_t d = 0; d < plan.data_idx.size(); d++) sc_rank[plan.data_idx[d]] = (uint16_t)d;
     for (size_t n = 0; n < plan.pilot_idx.size(); n++) sc_rank[plan.pilot_idx[n]] = (uint16_t)(0x4000u | n);
     if (plan.M_pilot + plan.M_data < 5) return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA path needs at least 5 active subcarriers");
+    B2_TRY(t_P.upload(eqgain_fit_matrix(plan)));
     B2_TRY(t_B.upload(B)); B2_TRY(t_perm.upload(fftM.perm)); B2_TRY(t_tw.upload(fftM.tw)); B2_TRY(t_rank.upload(sc_rank));
     // state
     const size_t W = M + cp;
-    penc_cap = ((size_t)fec_enc_len(FEC_HAMMING128, fec_enc_len(FEC_CONV_V27, 65535 + 4)) + 64 + 15) & ~(size_t)15;
+    // in-progress payload of a stream: one byte per demapped symbol (ofdmsync8.cu; at most 8 symbols
+    // per encoded byte, BPSK) or the packed encoded bytes (ofdmsync.cu)
+    unsigned int max_payload = 65535;
     if (const char * e = getenv("B2_MAX_PAYLOAD")) {
         unsigned long v = strtoul(e, nullptr, 10);
-        if (v >= 1 && v <= 65535) penc_cap = ((size_t)fec_enc_len(FEC_HAMMING128, fec_enc_len(FEC_CONV_V27, (unsigned int)v + 4)) + 64 + 15) & ~(size_t)15;
+        if (v >= 1 && v <= 65535) max_payload = (unsigned int)v;
     }
+    penc_cap = (8 * (size_t)fec_enc_len(FEC_HAMMING128, fec_enc_len(FEC_CONV_V27, max_payload + 4)) + 64 + 15) & ~(size_t)15;
     B2_TRY(d_st.alloc(sizeof(SyncState) * streams)); B2_TRY(d_ring.alloc(sizeof(cf) * W * streams));
     B2_TRY(d_G0.alloc(sizeof(cf) * M * streams)); B2_TRY(d_R.alloc(sizeof(cf) * M * streams));
     B2_TRY(d_penc.alloc(penc_cap * streams));
@@ -141,7 +145,7 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     sp.tb.sctype = t_sctype.as<uint8_t>(); sp.tb.S0 = t_S0.as<float>(); sp.tb.S1 = t_S1.as<float>();
     sp.tb.data_idx = t_data.as<uint16_t>(); sp.tb.pilot_idx = t_pilot.as<uint16_t>(); sp.tb.pilot_x = t_pilotx.as<float>();
     sp.tb.active_idx = t_active.as<uint16_t>(); sp.tb.pilot_seq = t_seq.as<uint8_t>(); sp.tb.hdr_walk = t_walk.as<uint16_t>();
-    sp.tb.B = t_B.as<cf>(); sp.tb.sc_rank = t_rank.as<uint16_t>();
+    sp.tb.B = t_B.as<cf>(); sp.tb.sc_rank = t_rank.as<uint16_t>(); sp.tb.eqfit_P = t_P.as<double>();
     sp.fft.n = fftM.n; sp.fft.npass = fftM.npass;
     sp.fft.radices = 0;
     for (unsigned int i = 0; i < fftM.npass; i++) sp.fft.radices |= fftM.radix[i] << (4 * i);

@@ -268,6 +268,55 @@ static inline int fft_plan(FftPlan & f, unsigned int n)
     return 0;
 }
 
+// ---------------------------------------------------------------- S1 equaliser-gain fit
+// liquid's ofdmframesync_estimate_eqgain_poly fits order-4 polynomials to |G| and arg G over the
+// active subcarriers (abscissa = signed subcarrier index / M).  The abscissae are fixed by the
+// allocation, so the least-squares solution is a constant matrix applied to the ordinates:
+// coef = P y with P = (X^T X)^-1 X^T  (5 x Na, row major), computed here once in long double.
+static inline std::vector<double> eqgain_fit_matrix(const OfdmPlan & o)
+{
+    const size_t Na = o.active_idx.size();
+    std::vector<double> x(Na);
+    for (size_t n = 0; n < Na; n++) {
+        unsigned int k = o.active_idx[n];
+        float xf = (k > o.M2) ? (float)k - (float)o.M : (float)k;
+        x[n] = (double)(xf / (float)o.M);
+    }
+    long double A[5][10];
+    for (int r = 0; r < 5; r++)
+        for (int c = 0; c < 10; c++) A[r][c] = (c >= 5 && c - 5 == r) ? 1.0L : 0.0L;
+    for (size_t n = 0; n < Na; n++) {
+        long double pw[9], xp = 1.0L;
+        for (int r = 0; r < 9; r++) { pw[r] = xp; xp *= (long double)x[n]; }
+        for (int r = 0; r < 5; r++)
+            for (int c = 0; c < 5; c++) A[r][c] += pw[r + c];
+    }
+    for (int c = 0; c < 5; c++) {                       // Gauss-Jordan with partial pivoting
+        int piv = c;
+        for (int r = c + 1; r < 5; r++) if (fabsl(A[r][c]) > fabsl(A[piv][c])) piv = r;
+        if (piv != c) for (int i = 0; i < 10; i++) std::swap(A[c][i], A[piv][i]);
+        long double d = A[c][c];
+        if (d == 0.0L) d = 1e-300L;
+        for (int i = 0; i < 10; i++) A[c][i] /= d;
+        for (int r = 0; r < 5; r++) {
+            if (r == c) continue;
+            long double f = A[r][c];
+            for (int i = 0; i < 10; i++) A[r][i] -= f * A[c][i];
+        }
+    }
+    std::vector<double> P(5 * Na);
+    for (size_t n = 0; n < Na; n++) {
+        long double pw[5], xp = 1.0L;
+        for (int r = 0; r < 5; r++) { pw[r] = xp; xp *= (long double)x[n]; }
+        for (int r = 0; r < 5; r++) {
+            long double a = 0.0L;
+            for (int c = 0; c < 5; c++) a += A[r][5 + c] * pw[c];
+            P[(size_t)r * Na + n] = (double)a;
+        }
+    }
+    return P;
+}
+
 // ---------------------------------------------------------------- transmit-side tables
 // unnormalised radix-2 transform in float (host, construction time only)
 static inline void host_fft(std::vector<float> & re, std::vector<float> & im, int dir)

@@ -64,8 +64,9 @@ struct FrameRec {               // same layout as b2_frame_rec (include/b200_ofd
 };
 
 struct FrameAux {               // device-only companion of FrameRec
-    uint32_t enc_len;           // encoded payload bytes in the arena
-    uint32_t pad;
+    uint32_t enc_len;           // encoded payload bytes
+    uint32_t sym_bps;           // 0: the arena holds the enc_len packed bytes; else it holds the
+                                // ceil(8*enc_len/sym_bps) demapped symbols, one per byte
 };
 
 struct SyncTables {             // read-only, global memory
@@ -78,6 +79,7 @@ struct SyncTables {             // read-only, global memory
     const uint8_t * pilot_seq;  // [255]
     const uint16_t * hdr_walk;  // [4][18] header de-interleaver walks (n = 36)
     const cf * B;               // [M] e^{j 2 pi backoff i / M}
+    const double * eqfit_P;     // [5][M_pilot+M_data] least-squares matrix of the S1 gain fit (design.h)
     const uint16_t * sc_rank;   // [M] data: rank among data subcarriers (ascending index);
                                 //     pilot: 0x4000 | rank in fft-shifted visiting order; null: 0xffff
 };
@@ -111,6 +113,9 @@ cudaError_t sync_configure(size_t smem_bytes);
 cudaError_t sync_launch(const SyncParams & p, int threads, size_t smem_bytes, cudaStream_t st);
 void sync_state_init(SyncState & s, unsigned int M, unsigned int cp);
 cudaError_t sync_reset_launch(SyncState * st, unsigned int streams, cudaStream_t stream);
+// register-resident fast path (ofdmsync8.cu), M/8 threads per stream; sync_launch() picks it
+bool sync8_supported(unsigned int M);
+cudaError_t sync8_launch(const SyncParams & p, cudaStream_t st);
 
 // ------------------------------------------------------------------ packet decode
 // de-interleave + FEC decode + CRC of every completed frame (liquid packetizer_decode, called

@@ -19,12 +19,13 @@
 // warp-parallel scan in warp 0; equalise / derotate / demap touch each subcarrier once.
 // The sample window, G0, R and all scalar state persist in global memory across launches, so
 // results do not depend on how the stream is chunked.
+#include <cstdlib>
 #include "kernels.h"
 #include "fec.cuh"
+#include "syncdev.cuh"
 
 namespace b2 {
 
-#define PI_F 3.14159274101257324219f
 #define PX(i) ((i) + ((i) >> 3))          // skewed index into the FFT buffer (one pad per 8: radix-8 strides)
 
 void sync_state_init(SyncState & s, unsigned int M, unsigned int cp)
@@ -74,148 +75,6 @@ __host__ __device__ static inline SyLayout sy_layout(unsigned int M, unsigned in
     return L;
 }
 size_t sync_smem_bytes(const SyncParams & p) { return sy_layout(p.M, p.cp, p.M_pilot + p.M_data).total; }
-
-// hard demodulation of one symbol (liquid modem_demodulate for BPSK / QPSK / square QAM)
-__device__ __forceinline__ unsigned int demod_axis(float v, int m, float alpha)
-{
-    unsigned int s = 0;
-    for (int k = m - 1; k >= 0; k--) {
-        float ref = (float)(1u << k) * alpha;
-        s <<= 1;
-        if (v > 0) { s |= 1u; v -= ref; } else { v += ref; }
-    }
-    return s ^ (s >> 1);        // gray encode
-}
-__device__ __forceinline__ unsigned int demod_symbol(cf x, unsigned int scheme, unsigned int bps, float alpha)
-{
-    if (scheme == 39) return x.x > 0 ? 0u : 1u;                                   // BPSK
-    if (scheme == 40) return (x.x > 0 ? 0u : 1u) + (x.y > 0 ? 0u : 2u);           // QPSK
-    int m = (int)bps >> 1;
-    unsigned int si = demod_axis(x.x, m, alpha);
-    unsigned int sq = demod_axis(x.y, m, alpha);
-    return (si << m) + sq;
-}
-
-__device__ __forceinline__ unsigned int dev_fec_enc_len(unsigned int scheme, unsigned int n)
-{
-    switch (scheme) {
-    case 6:  return (n * 12 + 7) / 8;
-    case 7:  { unsigned int blocks = (n * 8 + 11) / 12; return (blocks * 24 + 7) / 8; }
-    case 11: return (2 * (8 * n + 6) + 7) / 8;
-    default: return n;
-    }
-}
-__device__ __forceinline__ bool dev_fec_ok(unsigned int s) { return s == 1 || s == 6 || s == 7 || s == 11; }
-__device__ __forceinline__ unsigned int dev_mod_bps(unsigned int s)
-{
-    switch (s) { case 39: return 1; case 40: case 25: return 2; case 27: return 4; case 29: return 6; case 31: return 8; default: return 0; }
-}
-__device__ __forceinline__ unsigned int div_bps(unsigned int x, unsigned int bps)
-{
-    switch (bps) {
-    case 1: return x;
-    case 2: return x >> 1;
-    case 4: return x >> 2;
-    case 8: return x >> 3;
-    default: return (x * 0xAAABu) >> 18;        // bps = 6, x < 2^15
-    }
-}
-
-// warp-parallel phase unwrap of y[0..n) (liquid: "while (y[i]-y[i-1] > pi) y[i] -= 2pi" ...),
-// in place when `store`, returning per-lane partial sums of y' and x*y' (x may be null).
-// The number of 2*pi steps of element i is the running sum of the steps implied by the RAW
-// neighbour differences; the value itself is then built by repeated float adds like liquid does.
-__device__ __forceinline__ void warp_unwrap(float * y, const float * __restrict__ x, unsigned int n, bool store,
-                                            unsigned int lane, float & sy, float & sxy)
-{
-    int carry = 0;
-    float last_raw = 0.f;
-    sy = 0.f; sxy = 0.f;
-    for (unsigned int base = 0; base < n; base += 32) {
-        const unsigned int i = base + lane;
-        const bool valid = i < n;
-        const float raw = valid ? y[i] : 0.f;
-        float prev = __shfl_up_sync(0xffffffffu, raw, 1);
-        if (lane == 0) prev = last_raw;
-        int k = 0;
-        if (valid && i > 0) {
-            float d = raw - prev;
-            k = (d > PI_F) ? -1 : ((d < -PI_F) ? 1 : 0);
-        }
-        if (__any_sync(0xffffffffu, k != 0)) {      // rare: most symbols need no unwrapping at all
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, k, o);
-                if (lane >= (unsigned int)o) k += t;
-            }
-        }
-        k += carry;
-        carry = __shfl_sync(0xffffffffu, k, 31);
-        last_raw = __shfl_sync(0xffffffffu, raw, 31);
-        float yy = raw;
-        for (int q = k; q > 0; q--) yy += 2 * PI_F;
-        for (int q = k; q < 0; q++) yy -= 2 * PI_F;
-        if (valid) {
-            if (store) y[i] = yy;
-            sy = __fadd_rn(sy, yy);
-            if (x) sxy = __fadd_rn(sxy, __fmul_rn(x[i], yy));
-        }
-    }
-}
-
-// solve the 5x5 normal equations sum_c S[r+c] p[c] = b[r] (Gaussian elimination, partial pivoting)
-__device__ __forceinline__ void solve5(const double * __restrict__ S, const double * __restrict__ b, double * __restrict__ coef)
-{
-    double A[5][6];
-#pragma unroll
-    for (int r = 0; r < 5; r++) {
-#pragma unroll
-        for (int c = 0; c < 5; c++) A[r][c] = S[r + c];
-        A[r][5] = b[r];
-    }
-#pragma unroll
-    for (int c = 0; c < 5; c++) {
-#pragma unroll
-        for (int r = c + 1; r < 5; r++) {
-            if (fabs(A[r][c]) > fabs(A[c][c])) {
-#pragma unroll
-                for (int i = 0; i < 6; i++) { double t = A[c][i]; A[c][i] = A[r][i]; A[r][i] = t; }
-            }
-        }
-        const double inv = 1.0 / A[c][c];          // one reciprocal per pivot (double division is slow)
-        A[c][c] = inv;
-#pragma unroll
-        for (int r = c + 1; r < 5; r++) {
-            double f = A[r][c] * inv;
-#pragma unroll
-            for (int i = c + 1; i < 6; i++) A[r][i] -= f * A[c][i];
-        }
-    }
-    double p[5];
-#pragma unroll
-    for (int r = 4; r >= 0; r--) {
-        double s = A[r][5];
-#pragma unroll
-        for (int c = r + 1; c < 5; c++) s -= A[r][c] * p[c];
-        p[r] = s * A[r][r];                        // diagonal holds the reciprocal pivot
-    }
-#pragma unroll
-    for (int i = 0; i < 5; i++) coef[i] = p[i];
-}
-
-// CRC-32 with a 16-entry nibble table (frame header: 14 bytes)
-__device__ __forceinline__ uint32_t crc32_nibble(const uint8_t * m, unsigned int n)
-{
-    const uint32_t T[16] = {0x00000000u, 0x1DB71064u, 0x3B6E20C8u, 0x26D930ACu, 0x76DC4190u, 0x6B6B51F4u, 0x4DB26158u, 0x5005713Cu,
-                            0xEDB88320u, 0xF00F9344u, 0xD6D6A3E8u, 0xCB61B38Cu, 0x9B64C2B0u, 0x86D3D2D4u, 0xA00AE278u, 0xBDBDF21Cu};
-    uint32_t key = ~0u;
-    for (unsigned int i = 0; i < n; i++) {
-        key ^= m[i];
-        key = (key >> 4) ^ T[key & 15u];
-        key = (key >> 4) ^ T[key & 15u];
-    }
-    return ~key;
-}
 
 // optional phase profile (build with -DB2_SYNC_PROF): cycles spent by CTA 0 between barriers
 #ifdef B2_SYNC_PROF
@@ -763,7 +622,7 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
                     r.complete_index = S->sample_index - 1;
                     r.payload_offset = offb;
                     p.recs[slot] = r;
-                    FrameAux a; a.enc_len = e2; a.pad = 0;
+                    FrameAux a; a.enc_len = e2; a.sym_bps = 0;
                     p.aux[slot] = a;
                     red[115] = 1.f;
                     dsum[30] = __longlong_as_double((long long)offb);
@@ -843,6 +702,8 @@ cudaError_t sync_configure(size_t smem_bytes) { (void)smem_bytes; return cudaSuc
 cudaError_t sync_launch(const SyncParams & p, int threads, size_t smem_bytes, cudaStream_t st)
 {
     if (p.nsamples == 0 || p.streams == 0) return cudaSuccess;
+    static const bool force_generic = getenv("B2_SYNC_GENERIC") != nullptr;
+    if (!force_generic && sync8_supported(p.M) && p.M_pilot + p.M_data >= 5) return sync8_launch(p, st);
     // the fixed-size instances assume the default pass plan of design.h fft_plan()
     const bool std_plan = p.fft.radices == fft_static_radices(p.M);
     if (std_plan && threads == 256) {

@@ -32,6 +32,28 @@ __device__ __forceinline__ unsigned int pk_fec_enc_len(unsigned int scheme, unsi
     }
 }
 
+// ------------------------------------------------------------------ symbols -> encoded bytes
+// ofdmsync8.cu leaves a payload as one demapped symbol per byte; liquid packs them MSB first into
+// the encoded message (liquid_repack_bytes in ofdmflexframesync's payload path).  Thread `tid` of
+// `nthreads` builds 32-bit words of the byte stream: word w = stream bits [32w, 32w+32).
+__device__ __forceinline__ void pack_symbols(const uint8_t * __restrict__ sym, unsigned int mod_len, unsigned int bps,
+                                             uint32_t * out0, uint32_t * out1, unsigned int nbytes,
+                                             unsigned int tid, unsigned int nthreads)
+{
+    const unsigned int nwords = (nbytes + 3) / 4;
+    for (unsigned int w = tid; w < nwords; w += nthreads) {
+        const unsigned int lo = 32 * w, hi = lo + 32;
+        const unsigned int d0 = lo / bps, d1 = (hi - 1) / bps;
+        unsigned long long acc = 0;
+        for (unsigned int d = d0; d <= d1; d++) acc = (acc << bps) | (d < mod_len ? (unsigned long long)sym[d] : 0ull);
+        const unsigned int top = (d1 + 1) * bps;
+        const uint32_t be = (uint32_t)(acc >> (top - hi));
+        const uint32_t le = __byte_perm(be, 0, 0x0123);           // first stream byte at the lowest address
+        out0[w] = le;
+        if (out1) out1[w] = le;
+    }
+}
+
 // ------------------------------------------------------------------ block-wide exclusive scan of small counts
 __device__ __forceinline__ unsigned int block_excl_scan(unsigned int v, unsigned int * scratch, unsigned int tid,
                                                         unsigned int * total)
@@ -284,6 +306,15 @@ __global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketP
         uint8_t * D = p.decoded + off;
         uint2 * ws = vit_ws + (size_t)blockIdx.x * vit_ws_stride;
         int ok = 1;
+        const unsigned int sym_bps = p.aux[ri].sym_bps;
+        if (sym_bps) {
+            // the arena holds demapped symbols: pack them, then work in place as before
+            const unsigned int mod_len = (8 * e1 + sym_bps - 1) / sym_bps;
+            pack_symbols(A, mod_len, sym_bps, (uint32_t *)D, nullptr, e1, tid, PK_THREADS);
+            __syncthreads();
+            for (unsigned int i = tid; i < (e1 + 3) / 4; i += PK_THREADS) ((uint32_t *)A)[i] = ((const uint32_t *)D)[i];
+            __syncthreads();
+        }
         // stage 1 (outer code)
         uint8_t * s1out = A;
         if (fec1 != 1) {
@@ -523,7 +554,9 @@ __global__ void __launch_bounds__(PKF_WARPS * 32) packet_plain_kernel(const Pack
         const uint32_t * src = (const uint32_t *)(p.arena + off);       // offsets are 16-byte aligned
         uint32_t * dst = (uint32_t *)(p.decoded + off);
         uint32_t * st = (uint32_t *)stage[wid];
-        for (unsigned int i = lane; i < (n0 + 3) / 4; i += 32) { uint32_t v = src[i]; st[i] = v; dst[i] = v; }
+        const unsigned int sym_bps = p.aux[ri].sym_bps;
+        if (sym_bps) pack_symbols(p.arena + off, (8 * n0 + sym_bps - 1) / sym_bps, sym_bps, st, dst, n0, lane, 32);
+        else for (unsigned int i = lane; i < (n0 + 3) / 4; i += 32) { uint32_t v = src[i]; st[i] = v; dst[i] = v; }
         __syncwarp();
         int valid = 1;
         if (crc_len) {

@@ -13,10 +13,10 @@ L = pkg.lib()
 for _ in range(3):
     rx.execute_device(x.data_ptr(), len(period) * reps); rx.poll()
 out = (C.c_ulonglong * 16)()
-L.b2_debug_sync_prof(out, 1)
+L.b2_debug_sync8_prof(out, 1)
 rx.execute_device(x.data_ptr(), len(period) * reps); rx.poll()
-L.b2_debug_sync_prof(out, 0)
-names = ["top wait", "push/mix", "gather+FFT", "eq+pilots", "fit", "derot+demap", "pack+rest", "preamble post", "pre-fft(upd+prefetch+gather)", "pass1", "pass2", "pass3"]
+L.b2_debug_sync8_prof(out, 0)
+names = ["top wait", "consume+pass1", "fft rest", "eq+pilots", "fit", "derot+demap", "pack+emit", "preamble post", "-", "-", "-", "-"]
 tot = sum(out[:12])
 print("timing", rx.last_timing())
 for i, n in enumerate(names):
