@@ -211,7 +211,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--reps", type=int, default=8, help="frame periods per step (8 -> 21.2 M samples, 170 MB > L2)")
+    ap.add_argument("--reps", type=int, default=91, help="frame periods per step (91 -> 2^28 wideband samples, the per-GPU share "
+                    "of BASELINE configs[4]'s 2^31; 2.1 GB of input per step, far larger than L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"])
     args = ap.parse_args()
@@ -266,6 +267,7 @@ def main():
     clk = Clocks(local_rank)
     clk.start()
     kt = np.zeros(4)
+    launches = 0
     barrier()
     t0 = time.perf_counter()
     nfr = 0
@@ -275,6 +277,7 @@ def main():
         rx.execute_device(d_x.data_ptr(), n_step)
         tb = time.perf_counter()
         kt += np.array(rx.last_timing())
+        launches += rx.last_launches()[0]
         recs, pl = rx.poll_view()
         t_poll += time.perf_counter() - tb
         t_exec += tb - ta
@@ -315,10 +318,11 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (oracle transmitter, one frame period tiled on device)",
             "config": {"workload": w["name"], "samples_per_step": n_step, "input_bytes_per_step": n_step * 8,
                        "l2_policy": "input (%.0f MB/step) larger than L2" % (n_step * 8 / 1e6),
-                       "frames_per_step": nfr // args.steps, "parallelism": "independent receivers x%d" % world},
+                       "frames_per_step": nfr // args.steps, "parallelism": "independent receivers x%d" % world,
+                       "pipeline_chunks_per_step": rx.last_launches()[1]},
             "e2e": {"value": total / dt_e2e / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": n_step * 8,
                     "d2h_bytes_per_step": d2h // args.steps},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": launches,
             "kernels_ms_per_step": {"analyzer_kernel": kt_avg[0], "sync_kernel": kt_avg[1], "packet_decode_kernel": kt_avg[2], "call": kt_avg[3]},
             "host_ms_per_step": {"execute_call": 1e3 * t_exec / args.steps, "poll_call": 1e3 * t_poll / args.steps},
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",

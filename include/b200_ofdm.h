@@ -87,9 +87,13 @@ int b2_mcrx_poll_view(b2_mcrx * q, const b2_frame_rec ** recs, size_t * n_recs,
 /* debug tap: record every equalised OFDM symbol X[0..M) handed to the header/payload layer */
 int b2_mcrx_tap_symbols(b2_mcrx * q, int enable, size_t max_symbols);
 int b2_mcrx_read_symbols(b2_mcrx * q, uint32_t * channel, uint64_t * index, float * X, size_t cap, size_t * n);
-/* device-side timing of the last execute call, milliseconds (CUDA events on the handle's
- * stream): [0] channelizer kernel, [1] sync kernel, [2] packet-decode kernel, [3] whole call */
+/* device-side timing of the last execute call, milliseconds (CUDA events on the streams the
+ * kernels are launched on; the stages of successive chunks overlap, so [0..2] are sums over the
+ * chunks of the call and may add up to more than [3]): [0] channelizer kernels, [1] sync kernels,
+ * [2] packet-decode kernels, [3] whole call */
 int b2_mcrx_last_timing(b2_mcrx * q, float ms[4]);
+/* number of kernels launched by the last execute call and number of pipeline chunks it used */
+int b2_mcrx_last_launches(b2_mcrx * q, unsigned int * kernels, unsigned int * chunks);
 /* raw access for tests: channelizer output of the last execute call, [num_channels][n_blocks] */
 int b2_mcrx_read_channelizer(b2_mcrx * q, float * out, size_t cap_samples, size_t * n_blocks);
 /* the CUDA stream the kernels of this handle are launched on (cudaStream_t) */

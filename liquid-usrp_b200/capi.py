@@ -46,6 +46,7 @@ _PROTOS = {
     "b2_mcrx_tap_symbols": (C.c_int, [_vp, C.c_int, _sz]),
     "b2_mcrx_read_symbols": (C.c_int, [_vp, _vp, _vp, _vp, _sz, C.POINTER(_sz)]),
     "b2_mcrx_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float * 4)]),
+    "b2_mcrx_last_launches": (C.c_int, [_vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "b2_mcrx_read_channelizer": (C.c_int, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "b2_mcrx_stream": (_vp, [_vp]),
     "b2_mcrx_channelize_device": (C.c_int, [_vp, _vp, _sz, C.c_int64, _vp, _sz]),
@@ -141,6 +142,12 @@ class _FrameSource:
         ms = (C.c_float * 4)()
         _check(self._fn("last_timing")(self.h, C.byref(ms)))
         return [float(v) for v in ms]
+
+    def last_launches(self):
+        """(kernels launched, pipeline chunks) of the last execute call (multichannelrx only)"""
+        k, c = C.c_uint(0), C.c_uint(0)
+        _check(lib().b2_mcrx_last_launches(self.h, C.byref(k), C.byref(c)))
+        return int(k.value), int(c.value)
 
     def reset(self):
         _check(self._fn("reset")(self.h))

@@ -15,6 +15,7 @@
 #include "design.h"
 #include "kernels.h"
 #include "capi_util.h"
+#include "smpart.h"
 
 using namespace b2;
 
@@ -47,10 +48,21 @@ struct SyncCore {
     FrameRec * h_recs = nullptr;         // pinned
     uint8_t * h_payload = nullptr;       // pinned
     // results waiting for poll()
+    // records in callback order.  payload_offset of record i points into ready_payloads for
+    // i < n_compacted, and straight into the pinned copy of the last batch's output (h_payload)
+    // for the rest: the payload bytes of a batch are not touched by the host unless it asks
     std::vector<FrameRec> ready;
     std::vector<uint8_t> ready_payloads;
+    size_t n_compacted = 0;
+    size_t pending_bytes = 0;            // payload bytes of the records beyond n_compacted
+    unsigned long long last_used = 0;    // bytes of h_payload the last batch filled
     std::vector<FrameRec> view_recs;     // handed out by poll_view(), alive until the next poll/execute
     std::vector<uint8_t> view_payloads;
+    RangeMark * h_range = nullptr;       // pinned copy of d_range
+    cudaStream_t xstream = nullptr;      // device -> host copies of finished chunks
+    std::vector<std::pair<unsigned long long, unsigned int>> order;
+    void compact_pending();
+    void process_chunk(unsigned int lo, unsigned int hi);
     // kernel config
     int sync_threads = 128;
     size_t sync_smem = 0;
@@ -58,14 +70,25 @@ struct SyncCore {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
     SyncParams sp;
+    // a batch = one collect(); its chunks run sync on `stream` and decode on `dstream`
+    cudaStream_t dstream = nullptr;
+    DevBuf d_range;                      // [chunks+1] record count after each chunk's synchroniser
+    unsigned int range_cap = 0, chunk = 0, launches = 0;
+    struct ChunkEv { cudaEvent_t s0, s1, d0, d1, x; };
+    std::vector<ChunkEv> cev;            // sync begin/end, decode begin/end of each chunk
+    bool timing = true;
 
     int init(unsigned int M, unsigned int cp, unsigned int taper, const unsigned char * p, unsigned int streams_,
-             size_t tmax_, int device_, cudaStream_t st);
+             size_t tmax_, int device_, cudaStream_t st, cudaStream_t decode_st = nullptr);
     void destroy();
     int reset_state();                   // fresh object: everything zero
     int reset_streams();                 // ofdmflexframesync_reset on every stream
     // run sync + decode over in[s*stride + t], t < nsamples; appends results to `ready`
     int run(const cf * in, size_t in_stride, unsigned int nsamples, bool record_events);
+    int begin_batch();
+    // `after`: event on another stream that must complete before the synchroniser may read `in`
+    int launch_chunk(const cf * in, size_t in_stride, unsigned int nsamples, cudaEvent_t after);
+    int end_batch();
     int collect();
     int poll(b2_frame_rec * recs, size_t recs_cap, size_t * n_recs, uint8_t * payloads, size_t payloads_cap, size_t * n_payload_bytes);
     int poll_view(const b2_frame_rec ** recs, size_t * n_recs, const uint8_t ** payloads, size_t * n_payload_bytes);
@@ -73,7 +96,7 @@ struct SyncCore {
 };
 
 int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const unsigned char * p, unsigned int streams_,
-                   size_t tmax_, int device_, cudaStream_t st)
+                   size_t tmax_, int device_, cudaStream_t st, cudaStream_t decode_st)
 {
     device = device_; stream = st; streams = streams_; tmax = tmax_;
     if (M < 8 || (M & 1) || cp < 1 || cp > M || taper > cp) return b2_fail(B2_ERR_ARG, "invalid OFDM configuration (M=%u cp=%u taper=%u)", M, cp, taper);
@@ -128,6 +151,14 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     B2_CUDA(cudaMallocHost(&h_recs, sizeof(FrameRec) * recs_cap));
     B2_CUDA(cudaMallocHost(&h_payload, arena_cap));
     for (int i = 0; i < 5; i++) B2_CUDA(cudaEventCreate(&ev[i]));
+    if (decode_st) dstream = decode_st;
+    else B2_CUDA(cudaStreamCreateWithFlags(&dstream, cudaStreamNonBlocking));
+    B2_CUDA(cudaStreamCreateWithFlags(&xstream, cudaStreamNonBlocking));
+    range_cap = 4096;
+    B2_TRY(d_range.alloc(sizeof(RangeMark) * (range_cap + 1)));
+    B2_CUDA(cudaMallocHost(&h_range, sizeof(RangeMark) * (range_cap + 1)));
+    memset(h_range, 0, sizeof(RangeMark) * (range_cap + 1));
+    timing = getenv("B2_NO_TIMING") == nullptr;
 
     memset(&sp, 0, sizeof(sp));
     sp.M = M; sp.cp = cp; sp.M2 = M / 2; sp.backoff = plan.backoff;
@@ -166,8 +197,13 @@ void SyncCore::destroy()
     if (h_counters) cudaFreeHost(h_counters);
     if (h_recs) cudaFreeHost(h_recs);
     if (h_payload) cudaFreeHost(h_payload);
-    h_counters = nullptr; h_recs = nullptr; h_payload = nullptr;
+    if (h_range) cudaFreeHost(h_range);
+    if (xstream) cudaStreamDestroy(xstream);
+    h_counters = nullptr; h_recs = nullptr; h_payload = nullptr; h_range = nullptr; xstream = nullptr;
     for (int i = 0; i < 5; i++) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+    for (auto & e : cev) { cudaEventDestroy(e.s0); cudaEventDestroy(e.s1); cudaEventDestroy(e.d0); cudaEventDestroy(e.d1); cudaEventDestroy(e.x); }
+    cev.clear();
+    if (dstream) { cudaStreamDestroy(dstream); dstream = nullptr; }
 }
 
 int SyncCore::reset_state()
@@ -184,15 +220,36 @@ int SyncCore::reset_state()
     return B2_OK;
 }
 
+// payloads of the records that still point into h_payload move into ready_payloads (needed
+// before the next batch overwrites h_payload, or when a caller wants one compact buffer)
+void SyncCore::compact_pending()
+{
+    if (n_compacted == ready.size()) return;
+    size_t o = ready_payloads.size();
+    ready_payloads.resize(o + pending_bytes);
+    for (size_t i = n_compacted; i < ready.size(); i++) {
+        FrameRec & r = ready[i];
+        const size_t len = r.header_valid ? r.payload_len : 0;
+        if (len) memcpy(ready_payloads.data() + o, h_payload + r.payload_offset, len);
+        r.payload_offset = o;
+        o += len;
+    }
+    n_compacted = ready.size();
+    pending_bytes = 0;
+}
+
 int SyncCore::poll_view(const b2_frame_rec ** recs, size_t * n_recs, const uint8_t ** payloads, size_t * n_payload_bytes)
 {
     view_recs.clear(); view_payloads.clear();
+    const bool zero_copy = (n_compacted == 0);           // everything waiting comes from the last batch
+    if (!zero_copy) compact_pending();
     view_recs.swap(ready);
-    view_payloads.swap(ready_payloads);
+    if (!zero_copy) view_payloads.swap(ready_payloads);
     if (recs) *recs = (const b2_frame_rec *)view_recs.data();
     if (n_recs) *n_recs = view_recs.size();
-    if (payloads) *payloads = view_payloads.data();
-    if (n_payload_bytes) *n_payload_bytes = view_payloads.size();
+    if (payloads) *payloads = zero_copy ? h_payload : view_payloads.data();
+    if (n_payload_bytes) *n_payload_bytes = zero_copy ? (view_recs.empty() ? 0 : (size_t)last_used) : view_payloads.size();
+    n_compacted = 0; pending_bytes = 0;
     return B2_OK;
 }
 
@@ -216,79 +273,151 @@ int SyncCore::set_tap(int enable, size_t max_symbols)
 
 int SyncCore::run(const cf * in, size_t in_stride, unsigned int nsamples, bool record_events)
 {
+    (void)record_events;
+    if (nsamples == 0) return B2_OK;
+    B2_TRY(begin_batch());
+    B2_TRY(launch_chunk(in, in_stride, nsamples, nullptr));
+    return end_batch();
+}
+
+int SyncCore::begin_batch()
+{
+    compact_pending();                       // h_payload is about to be overwritten
+    B2_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(unsigned int), stream));
+    B2_CUDA(cudaMemsetAsync(d_range.p, 0, sizeof(RangeMark), stream));
+    memset(&h_range[0], 0, sizeof(RangeMark));
+    chunk = 0; launches = 0;
+    return B2_OK;
+}
+
+int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsamples, cudaEvent_t after)
+{
     if (nsamples == 0) return B2_OK;
     if (nsamples > tmax) return b2_fail(B2_ERR_ARG, "internal: launch of %u samples exceeds tmax %zu", nsamples, tmax);
-    B2_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(unsigned int), stream));
+    if (chunk >= range_cap) return b2_fail(B2_ERR_ARG, "internal: too many chunks in one batch");
+    if (cev.size() <= chunk) {
+        ChunkEv e;
+        B2_CUDA(cudaEventCreate(&e.s0)); B2_CUDA(cudaEventCreate(&e.s1));
+        B2_CUDA(cudaEventCreate(&e.d0)); B2_CUDA(cudaEventCreate(&e.d1));
+        B2_CUDA(cudaEventCreateWithFlags(&e.x, cudaEventDisableTiming));
+        cev.push_back(e);
+    }
+    ChunkEv & e = cev[chunk];
+    if (after) B2_CUDA(cudaStreamWaitEvent(stream, after, 0));
     SyncParams q = sp;
     q.in = in; q.in_stride = in_stride; q.nsamples = nsamples;
     q.tap_cap = tap_cap;
     q.tap_X = d_tapX.as<cf>(); q.tap_chan = d_tapc.as<uint32_t>(); q.tap_index = d_tapi.as<unsigned long long>();
-    if (record_events) B2_CUDA(cudaEventRecord(ev[1], stream));
+    if (timing) B2_CUDA(cudaEventRecord(e.s0, stream));
     B2_CUDA(sync_launch(q, sync_threads, sync_smem, stream));
-    if (record_events) B2_CUDA(cudaEventRecord(ev[2], stream));
+    RangeMark * range = d_range.as<RangeMark>() + chunk;
+    B2_CUDA(record_mark_launch(d_counters.as<unsigned int>(), range + 1, stream));
+    B2_CUDA(cudaMemcpyAsync(h_range + chunk + 1, range + 1, sizeof(RangeMark), cudaMemcpyDeviceToHost, stream));
+    B2_CUDA(cudaEventRecord(e.s1, stream));
+    // decode of this chunk runs beside the synchroniser of the next one
+    B2_CUDA(cudaStreamWaitEvent(dstream, e.s1, 0));
     PacketParams pp;
-    pp.recs = d_recs.as<FrameRec>(); pp.aux = d_aux.as<FrameAux>(); pp.counters = d_counters.as<unsigned int>();
-    pp.first_rec = 0;
+    pp.recs = d_recs.as<FrameRec>(); pp.aux = d_aux.as<FrameAux>(); pp.range = range;
     pp.arena = d_arena.as<uint8_t>(); pp.scratch = d_scratch.as<uint8_t>(); pp.decoded = d_decoded.as<uint8_t>();
-    B2_CUDA(packet_decode_launch(pp, decode_grid, stream));
-    if (record_events) B2_CUDA(cudaEventRecord(ev[3], stream));
-    return collect();
+    if (timing) B2_CUDA(cudaEventRecord(e.d0, dstream));
+    B2_CUDA(packet_decode_launch(pp, decode_grid, dstream));
+    B2_CUDA(cudaEventRecord(e.d1, dstream));
+    chunk++; launches += 4;                  // synchroniser, record mark, two decode kernels
+    return B2_OK;
 }
 
+// records [lo, hi) of h_recs (one chunk: their completion indices all lie inside the chunk) go to
+// `ready` in the order the reference would have fired their callbacks: completion block, then
+// channel.  Payload bytes stay where the DMA put them.
+void SyncCore::process_chunk(unsigned int lo, unsigned int hi)
+{
+    order.clear();
+    for (unsigned int i = lo; i < hi; i++) order.push_back({(h_recs[i].complete_index << 16) | (h_recs[i].channel & 0xffffu), i});
+    std::sort(order.begin(), order.end());
+    for (auto & kv : order) {
+        const FrameRec & r = h_recs[kv.second];
+        ready.push_back(r);
+        if (r.header_valid) pending_bytes += r.payload_len;
+    }
+}
+
+int SyncCore::end_batch()
+{
+    if (chunk == 0) return B2_OK;
+    // chunk by chunk, as soon as its decode is done: records + decoded payloads -> pinned host memory on
+    // the copy stream, and the host orders chunk c-1 while chunk c is in flight
+    int rc = B2_OK;
+    ready.reserve(ready.size() + 1024);
+    for (unsigned int c = 0; c <= chunk; c++) {
+        if (c < chunk) {
+            B2_CUDA(cudaEventSynchronize(cev[c].d1));
+            const unsigned int lo = std::min(h_range[c].nrec, recs_cap), hi = std::min(h_range[c + 1].nrec, recs_cap);
+            const unsigned long long ulo = std::min(h_range[c].arena_used, arena_cap), uhi = std::min(h_range[c + 1].arena_used, arena_cap);
+            if (hi > lo) B2_CUDA(cudaMemcpyAsync(h_recs + lo, d_recs.as<FrameRec>() + lo, sizeof(FrameRec) * (hi - lo), cudaMemcpyDeviceToHost, xstream));
+            if (uhi > ulo) B2_CUDA(cudaMemcpyAsync(h_payload + ulo, d_decoded.as<uint8_t>() + ulo, uhi - ulo, cudaMemcpyDeviceToHost, xstream));
+            B2_CUDA(cudaEventRecord(cev[c].x, xstream));
+        }
+        if (c > 0) {
+            B2_CUDA(cudaEventSynchronize(cev[c - 1].x));
+            const unsigned int lo = std::min(h_range[c - 1].nrec, recs_cap), hi = std::min(h_range[c].nrec, recs_cap);
+            process_chunk(lo, hi);
+
+        }
+    }
+
+    last_used = std::min(h_range[chunk].arena_used, arena_cap);
+    rc = collect();
+    last_ms[1] = 0.f; last_ms[2] = 0.f;
+    if (timing) {
+        for (unsigned int i = 0; i < chunk; i++) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, cev[i].s0, cev[i].s1);
+            cudaEventElapsedTime(&b, cev[i].d0, cev[i].d1);
+            last_ms[1] += a; last_ms[2] += b;
+        }
+    }
+    return rc;
+}
+
+// end of a batch: overflow flag and the debug tap
 int SyncCore::collect()
 {
     B2_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     B2_CUDA(cudaStreamSynchronize(stream));
     if (h_counters[1]) return b2_fail(B2_ERR_OVERFLOW, "internal: frame output arena overflow");
-    const unsigned int nrec = h_counters[0];
-    const unsigned long long used = *(const unsigned long long *)(h_counters + 2);
     const unsigned int ntap = std::min(h_counters[4], tap_cap);
-    if (nrec) {
-        B2_CUDA(cudaMemcpyAsync(h_recs, d_recs.p, sizeof(FrameRec) * nrec, cudaMemcpyDeviceToHost, stream));
-        if (used) B2_CUDA(cudaMemcpyAsync(h_payload, d_decoded.p, used, cudaMemcpyDeviceToHost, stream));
-    }
     if (ntap) {
         size_t o = tap_chan.size();
         tap_chan.resize(o + ntap); tap_index.resize(o + ntap); tap_X.resize((o + ntap) * 2 * (size_t)plan.M);
         B2_CUDA(cudaMemcpyAsync(&tap_chan[o], d_tapc.p, sizeof(uint32_t) * ntap, cudaMemcpyDeviceToHost, stream));
         B2_CUDA(cudaMemcpyAsync(&tap_index[o], d_tapi.p, sizeof(uint64_t) * ntap, cudaMemcpyDeviceToHost, stream));
         B2_CUDA(cudaMemcpyAsync(&tap_X[o * 2 * (size_t)plan.M], d_tapX.p, sizeof(cf) * plan.M * ntap, cudaMemcpyDeviceToHost, stream));
-    }
-    if (nrec || ntap) B2_CUDA(cudaStreamSynchronize(stream));
-    if (nrec) {
-        // the reference fires callbacks in order of completion block, then channel
-        std::vector<unsigned int> order(nrec);
-        for (unsigned int i = 0; i < nrec; i++) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](unsigned int a, unsigned int b) {
-            if (h_recs[a].complete_index != h_recs[b].complete_index) return h_recs[a].complete_index < h_recs[b].complete_index;
-            return h_recs[a].channel < h_recs[b].channel;
-        });
-        size_t total = 0;
-        for (unsigned int i = 0; i < nrec; i++) if (h_recs[i].header_valid) total += h_recs[i].payload_len;
-        size_t o = ready_payloads.size();
-        ready_payloads.resize(o + total);
-        ready.reserve(ready.size() + nrec);
-        for (unsigned int i = 0; i < nrec; i++) {
-            FrameRec r = h_recs[order[i]];
-            const size_t len = (r.header_valid ? r.payload_len : 0);
-            if (len) memcpy(ready_payloads.data() + o, h_payload + r.payload_offset, len);
-            r.payload_offset = o;
-            o += len;
-            ready.push_back(r);
-        }
+        B2_CUDA(cudaStreamSynchronize(stream));
     }
     return B2_OK;
 }
 
 int SyncCore::poll(b2_frame_rec * recs, size_t cap, size_t * n_recs, uint8_t * payloads, size_t payloads_cap, size_t * n_payload_bytes)
 {
+    const size_t total = ready_payloads.size() + pending_bytes;
     if (n_recs) *n_recs = ready.size();
-    if (n_payload_bytes) *n_payload_bytes = ready_payloads.size();
+    if (n_payload_bytes) *n_payload_bytes = total;
     if (!recs) return B2_OK;
-    if (cap < ready.size() || (payloads_cap < ready_payloads.size())) return b2_fail(B2_ERR_OVERFLOW, "poll buffers too small");
-    if (!ready.empty()) memcpy(recs, ready.data(), ready.size() * sizeof(FrameRec));
-    if (payloads && !ready_payloads.empty()) memcpy(payloads, ready_payloads.data(), ready_payloads.size());
+    if (cap < ready.size() || (payloads_cap < total)) return b2_fail(B2_ERR_OVERFLOW, "poll buffers too small");
+    FrameRec * out = (FrameRec *)recs;
+    if (!ready.empty()) memcpy(out, ready.data(), ready.size() * sizeof(FrameRec));
+    if (payloads) {
+        if (!ready_payloads.empty()) memcpy(payloads, ready_payloads.data(), ready_payloads.size());
+        size_t o = ready_payloads.size();
+        for (size_t i = n_compacted; i < ready.size(); i++) {       // straight from the pinned batch output
+            const size_t len = out[i].header_valid ? out[i].payload_len : 0;
+            if (len) memcpy(payloads + o, h_payload + out[i].payload_offset, len);
+            out[i].payload_offset = o;
+            o += len;
+        }
+    }
     ready.clear(); ready_payloads.clear();
+    n_compacted = 0; pending_bytes = 0;
     return B2_OK;
 }
 
@@ -308,7 +437,16 @@ struct b2_mcrx_s {
     uint32_t nco_theta = 0, nco_dtheta = 0;      // phase of the next incoming sample
     size_t an_smem = 0;
     int an_grid = 148;
+    unsigned int an_sms = 148;           // SMs the channelizer may use
     unsigned int last_blocks = 0;
+    // pipeline: copies on cstream, channelizer on stream, synchronisers on sstream (core.stream),
+    // decode on core.dstream; chunk c of a call flows through all four while chunk c+1 follows
+    cudaStream_t cstream = nullptr, sstream = nullptr;
+    SmPartition part;                    // SMs split between the synchroniser chains and the throughput kernels
+    unsigned int chunk_blocks = 0;
+    struct AnEv { cudaEvent_t copied, a0, a1; };
+    std::vector<AnEv> aev;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     SyncCore core;
 };
 
@@ -340,7 +478,18 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
     q->max_batch = max_batch;
     int rc = B2_OK;
     do {
-        if (cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaStreamCreate failed"); break; }
+        // many channels: the synchroniser chains get their own SMs (smpart.cu); B2_SYNC_SMS sizes the set
+        cudaStream_t decode_stream = nullptr;
+        if (N >= 32 && sync8_supported(M) && K >= 64) {
+            unsigned int want = 64;
+            if (const char * e = getenv("B2_SYNC_SMS")) { long v = atol(e); if (v >= 8 && v <= 136) want = (unsigned int)v; }
+            if (sm_partition_create(q->part, device, want)) {
+                q->stream = q->part.big_stream[0];
+                q->sstream = q->part.small_stream;
+                decode_stream = q->part.big_stream[1];
+            }
+        }
+        if (!q->stream && cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaStreamCreate failed"); break; }
         // firpfbch_crcf_create_kaiser(LIQUID_ANALYZER, 2N, m=7, As=60): lib/multichannelrx.cc:89-91
         std::vector<float> h = firpfbch_prototype(K, 7, 60.0f);
         fft_plan(q->fftK, K);
@@ -362,9 +511,17 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
         if (analyzer_configure(q->an_smem) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (q->part.ok) sms = (int)q->part.big_sms;
         int per_sm = std::max(1, (int)((227 * 1024) / (q->an_smem + 1024)));
         q->an_grid = sms * std::min(per_sm, 2);
-        if ((rc = q->core.init(M, cp, taper, p, N, q->tcap, device, q->stream))) break;
+        q->an_sms = (unsigned int)sms;
+        if (cudaStreamCreateWithFlags(&q->cstream, cudaStreamNonBlocking) != cudaSuccess ||
+            (!q->sstream && cudaStreamCreateWithFlags(&q->sstream, cudaStreamNonBlocking) != cudaSuccess) ||
+            cudaEventCreate(&q->ev_begin) != cudaSuccess || cudaEventCreate(&q->ev_end) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaStreamCreate failed"); break; }
+        // chunk of the pipeline: long enough to amortise launches, short enough to overlap stages
+        q->chunk_blocks = std::max(64u, (1u << 22) / K);
+        if (const char * e = getenv("B2_CHUNK_BLOCKS")) { long v = atol(e); if (v >= 1) q->chunk_blocks = (unsigned int)v; }
+        if ((rc = q->core.init(M, cp, taper, p, N, q->tcap, device, q->sstream, decode_stream))) break;
         B2_CUDA(cudaMemsetAsync(q->d_stage.p, 0, q->d_stage.bytes, q->stream));
         B2_CUDA(cudaStreamSynchronize(q->stream));
     } while (0);
@@ -378,8 +535,15 @@ extern "C" int b2_mcrx_destroy(b2_mcrx * q)
     if (!q) return B2_OK;
     cudaSetDevice(q->device);
     if (q->stream) cudaStreamSynchronize(q->stream);
+    if (q->sstream) cudaStreamSynchronize(q->sstream);
+    if (q->cstream) cudaStreamSynchronize(q->cstream);
     q->core.destroy();
+    for (auto & e : q->aev) { cudaEventDestroy(e.copied); cudaEventDestroy(e.a0); cudaEventDestroy(e.a1); }
+    if (q->ev_begin) cudaEventDestroy(q->ev_begin);
+    if (q->ev_end) cudaEventDestroy(q->ev_end);
     if (q->stream) cudaStreamDestroy(q->stream);
+    if (q->sstream) cudaStreamDestroy(q->sstream);
+    if (q->cstream) cudaStreamDestroy(q->cstream);
     delete q;
     return B2_OK;
 }
@@ -391,6 +555,7 @@ extern "C" int b2_mcrx_reset(b2_mcrx * q)
     if (!q) return b2_fail(B2_ERR_ARG, "null handle");
     B2_CUDA(cudaSetDevice(q->device));
     B2_CUDA(cudaMemsetAsync(q->d_stage.p, 0, sizeof(cf) * (q->hist_len + q->K), q->stream));
+    B2_CUDA(cudaStreamSynchronize(q->stream));
     q->carry = 0;
     return q->core.reset_streams();
 }
@@ -403,26 +568,57 @@ static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device)
     const size_t total = q->carry + n;
     const size_t T = total / K, leftover = total % K;
     const bool direct = on_device && q->carry == 0 && T > 0 && (((uintptr_t)x) & 15) == 0;
-    if (!direct)
-        B2_CUDA(cudaMemcpyAsync(stage + front, x, sizeof(cf) * n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, q->stream));
-    B2_CUDA(cudaEventRecord(q->core.ev[0], q->stream));
-    if (T > 0) {
-        AnalyzerParams ap;
-        memset(&ap, 0, sizeof(ap));
-        ap.seg0 = stage;
-        ap.rows0 = direct ? q->P - 1 : 0xffffffffu;
-        ap.seg1 = direct ? (const cf *)x : stage;
-        ap.K = K; ap.lgK = q->lgK; ap.N = q->N; ap.P = q->P; ap.TB = q->TB;
-        ap.nblocks = (unsigned int)T;
-        ap.taps = q->t_taps.as<float>();
-        ap.dtheta = q->nco_dtheta;
-        ap.theta0 = q->nco_theta - (uint32_t)(q->hist_len + q->carry) * q->nco_dtheta;
-        ap.out = q->d_chan.as<cf>(); ap.out_stride = q->tcap; ap.out_col0 = 0;
-        ap.fft.n = K; ap.fft.npass = q->fftK.npass;
-        ap.fft.radices = 0;
-        for (unsigned int i = 0; i < q->fftK.npass; i++) ap.fft.radices |= q->fftK.radix[i] << (4 * i);
-        ap.fft.perm = q->t_perm.as<uint16_t>(); ap.fft.tw = q->t_tw.as<cf>();
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    B2_CUDA(cudaEventRecord(q->ev_begin, q->stream));
+    AnalyzerParams ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.seg0 = stage;
+    ap.rows0 = direct ? q->P - 1 : 0xffffffffu;
+    ap.seg1 = direct ? (const cf *)x : stage;
+    ap.K = K; ap.lgK = q->lgK; ap.N = q->N; ap.P = q->P; ap.TB = q->TB;
+    ap.sm_limit = q->an_sms;
+    ap.taps = q->t_taps.as<float>();
+    ap.dtheta = q->nco_dtheta;
+    ap.theta0 = q->nco_theta - (uint32_t)(q->hist_len + q->carry) * q->nco_dtheta;
+    ap.out = q->d_chan.as<cf>(); ap.out_stride = q->tcap;
+    ap.fft.n = K; ap.fft.npass = q->fftK.npass;
+    ap.fft.radices = 0;
+    for (unsigned int i = 0; i < q->fftK.npass; i++) ap.fft.radices |= q->fftK.radix[i] << (4 * i);
+    ap.fft.perm = q->t_perm.as<uint16_t>(); ap.fft.tw = q->t_tw.as<cf>();
+
+    size_t copied = 0;                                       // samples of x already on their way into the stage
+    unsigned int nchunks = 0;
+    if (T > 0) B2_TRY(q->core.begin_batch());
+    for (size_t b0 = 0; b0 < T; b0 += q->chunk_blocks, nchunks++) {
+        const size_t tc = std::min((size_t)q->chunk_blocks, T - b0);
+        const bool last = b0 + tc == T;
+        if (q->aev.size() <= nchunks) {
+            b2_mcrx_s::AnEv e;
+            B2_CUDA(cudaEventCreateWithFlags(&e.copied, cudaEventDisableTiming));
+            B2_CUDA(cudaEventCreate(&e.a0)); B2_CUDA(cudaEventCreate(&e.a1));
+            q->aev.push_back(e);
+        }
+        b2_mcrx_s::AnEv & e = q->aev[nchunks];
+        if (!direct) {
+            // samples this chunk's blocks need (the last chunk also brings the leftover)
+            const size_t upto = last ? n : (b0 + tc) * K - q->carry;
+            if (upto > copied) {
+                B2_CUDA(cudaMemcpyAsync(stage + front + copied, (const cf *)x + copied, sizeof(cf) * (upto - copied), kind, q->cstream));
+                copied = upto;
+            }
+            B2_CUDA(cudaEventRecord(e.copied, q->cstream));
+            B2_CUDA(cudaStreamWaitEvent(q->stream, e.copied, 0));
+        }
+        ap.block0 = (unsigned int)b0; ap.nblocks = (unsigned int)tc; ap.out_col0 = b0;
+        if (q->core.timing) B2_CUDA(cudaEventRecord(e.a0, q->stream));
         B2_CUDA(analyzer_launch(ap, q->an_grid, q->an_smem, q->stream));
+        B2_CUDA(cudaEventRecord(e.a1, q->stream));
+        q->core.launches++;
+        B2_TRY(q->core.launch_chunk(q->d_chan.as<cf>() + b0, q->tcap, (unsigned int)tc, e.a1));
+    }
+    if (T == 0 && n > 0) {
+        B2_CUDA(cudaMemcpyAsync(stage + front, x, sizeof(cf) * n, kind, q->cstream));
+        B2_CUDA(cudaStreamSynchronize(q->cstream));
     }
     q->last_blocks = (unsigned int)T;
     // keep the last (P-1)*K + leftover samples of the stream at the front of the stage
@@ -453,15 +649,26 @@ static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device)
         q->carry = leftover;
         q->nco_theta += (uint32_t)n * q->nco_dtheta;
     }
-    int rc = q->core.run(q->d_chan.as<cf>(), q->tcap, (unsigned int)T, true);
-    if (rc) return rc;
-    B2_CUDA(cudaEventRecord(q->core.ev[4], q->stream));
-    B2_CUDA(cudaEventSynchronize(q->core.ev[4]));
+    if (T > 0) B2_TRY(q->core.end_batch());
+    B2_CUDA(cudaStreamSynchronize(q->stream));
+    B2_CUDA(cudaEventRecord(q->ev_end, q->stream));
+    B2_CUDA(cudaEventSynchronize(q->ev_end));
     if (T > 0) {
-        cudaEventElapsedTime(&q->core.last_ms[0], q->core.ev[0], q->core.ev[1]);
-        cudaEventElapsedTime(&q->core.last_ms[1], q->core.ev[1], q->core.ev[2]);
-        cudaEventElapsedTime(&q->core.last_ms[2], q->core.ev[2], q->core.ev[3]);
-        cudaEventElapsedTime(&q->core.last_ms[3], q->core.ev[0], q->core.ev[4]);
+        q->core.last_ms[0] = 0.f;
+        if (q->core.timing)
+            for (unsigned int i = 0; i < nchunks; i++) { float a = 0.f; cudaEventElapsedTime(&a, q->aev[i].a0, q->aev[i].a1); q->core.last_ms[0] += a; }
+        cudaEventElapsedTime(&q->core.last_ms[3], q->ev_begin, q->ev_end);
+        if (q->core.timing && getenv("B2_DUMP_TIMELINE")) {
+            // per chunk: begin/end of the channelizer, synchroniser and decode kernels, ms since the call began
+            for (unsigned int i = 0; i < nchunks; i++) {
+                float t[6] = {0, 0, 0, 0, 0, 0};
+                cudaEventElapsedTime(&t[0], q->ev_begin, q->aev[i].a0); cudaEventElapsedTime(&t[1], q->ev_begin, q->aev[i].a1);
+                cudaEventElapsedTime(&t[2], q->ev_begin, q->core.cev[i].s0); cudaEventElapsedTime(&t[3], q->ev_begin, q->core.cev[i].s1);
+                cudaEventElapsedTime(&t[4], q->ev_begin, q->core.cev[i].d0); cudaEventElapsedTime(&t[5], q->ev_begin, q->core.cev[i].d1);
+                fprintf(stderr, "chunk %3u  channelizer %7.3f-%7.3f  sync %7.3f-%7.3f  decode %7.3f-%7.3f\n", i, t[0], t[1], t[2], t[3], t[4], t[5]);
+            }
+            fprintf(stderr, "call %7.3f ms\n", q->core.last_ms[3]);
+        }
     }
     return B2_OK;
 }
@@ -532,6 +739,14 @@ extern "C" int b2_mcrx_last_timing(b2_mcrx * q, float ms[4])
     return B2_OK;
 }
 
+extern "C" int b2_mcrx_last_launches(b2_mcrx * q, unsigned int * kernels, unsigned int * chunks)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    if (kernels) *kernels = q->core.launches;
+    if (chunks) *chunks = q->core.chunk;
+    return B2_OK;
+}
+
 extern "C" int b2_mcrx_read_channelizer(b2_mcrx * q, float * out, size_t cap_samples, size_t * n_blocks)
 {
     if (!q) return b2_fail(B2_ERR_ARG, "null handle");
@@ -560,6 +775,7 @@ extern "C" int b2_mcrx_channelize_device(b2_mcrx * q, const float * x_dev, size_
     memset(&ap, 0, sizeof(ap));
     ap.seg0 = (const cf *)x_dev; ap.rows0 = 0xffffffffu; ap.seg1 = (const cf *)x_dev;
     ap.K = q->K; ap.lgK = q->lgK; ap.N = q->N; ap.P = q->P; ap.TB = q->TB;
+    ap.sm_limit = q->an_sms;
     ap.nblocks = (unsigned int)n_blocks;
     ap.taps = q->t_taps.as<float>();
     ap.dtheta = q->nco_dtheta;
@@ -578,10 +794,10 @@ extern "C" int b2_mcrx_sync_device(b2_mcrx * q, const float * in_dev, size_t n, 
     if (n == 0) return B2_OK;
     if (!in_dev) return b2_fail(B2_ERR_ARG, "null pointer");
     B2_CUDA(cudaSetDevice(q->device));
+    B2_CUDA(cudaStreamSynchronize(q->stream));               // a preceding b2_mcrx_channelize_device
     size_t done = 0;
     while (done < n) {
         size_t c = std::min(n - done, q->core.tmax);
-        B2_CUDA(cudaEventRecord(q->core.ev[0], q->stream));
         int rc = q->core.run((const cf *)in_dev + done, in_stride, (unsigned int)c, true);
         if (rc) return rc;
         done += c;
@@ -647,8 +863,6 @@ static int ofdmsync_run(b2_ofdmsync * q, const cf * in, size_t stride, size_t n)
     B2_CUDA(cudaEventRecord(q->core.ev[4], q->stream));
     B2_CUDA(cudaEventSynchronize(q->core.ev[4]));
     q->core.last_ms[0] = 0.f;
-    cudaEventElapsedTime(&q->core.last_ms[1], q->core.ev[1], q->core.ev[2]);
-    cudaEventElapsedTime(&q->core.last_ms[2], q->core.ev[2], q->core.ev[3]);
     cudaEventElapsedTime(&q->core.last_ms[3], q->core.ev[0], q->core.ev[4]);
     return B2_OK;
 }

@@ -18,6 +18,7 @@
 // window down one column for JB consecutive blocks (each staged sample is read once per JB
 // outputs); the K-point FFTs run in place in shared memory; the N kept channels leave through a
 // transposed read so each channel's TB outputs are one contiguous run in HBM.
+#include <cstdlib>
 #include "kernels.h"
 
 namespace b2 {
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(AN_THREADS, 1) analyzer_kernel(const AnalyzerP
         while (lo < hi) {
             unsigned int slot = lo % RR;
             unsigned int run = min(hi - lo, RR - slot);
-            unsigned int g = b_begin + lo;
+            unsigned int g = p.block0 + b_begin + lo;
             const cf * src;
             if (g < p.rows0) { run = min(run, p.rows0 - g); src = p.seg0 + (size_t)g * K; }
             else src = p.seg1 + (size_t)(g - p.rows0) * K;
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(AN_THREADS, 1) analyzer_kernel(const AnalyzerP
 
         // row phasors of the arriving rows
         for (unsigned int g = new_lo + tid; g < new_hi; g += AN_THREADS)
-            roww[g % RR] = nco_cexp_pi(p.theta0 + (b_begin + g) * K * p.dtheta);
+            roww[g % RR] = nco_cexp_pi(p.theta0 + (p.block0 + b_begin + g) * K * p.dtheta);
         mbar_wait(&bar[t & 1], (t >> 1) & 1);
         __syncthreads();
 
@@ -184,6 +185,8 @@ cudaError_t analyzer_configure(size_t smem_bytes)
 cudaError_t analyzer_launch(const AnalyzerParams & p, int grid, size_t smem_bytes, cudaStream_t st)
 {
     if (p.nblocks == 0) return cudaSuccess;
+    static const bool force_generic = getenv("B2_ANALYZER_GENERIC") != nullptr;
+    if (!force_generic && analyzer8_supported(p)) return analyzer8_launch(p, st);
     if (p.TB % 8 == 0) analyzer_kernel<8><<<grid, AN_THREADS, smem_bytes, st>>>(p);
     else analyzer_kernel<4><<<grid, AN_THREADS, smem_bytes, st>>>(p);
     return cudaGetLastError();

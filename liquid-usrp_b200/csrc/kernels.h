@@ -15,6 +15,8 @@ struct AnalyzerParams {
     const cf * seg1;            // logical input rows [rows0, ...): seg1 + (row-rows0)*K
     unsigned int K, lgK, N, P;  // filterbank size (= 1<<lgK), channels kept, taps per branch
     unsigned int TB;            // blocks per tile (multiple of JB)
+    unsigned int sm_limit;      // SMs available to this launch (0 = the whole device)
+    unsigned int block0;        // first output block of this launch (chunk of a longer call)
     unsigned int nblocks;       // output blocks this launch; block b reads rows b .. b+P-1
     const float * taps;         // [P][K]: taps[n*K + i] = h[i + n*K]
     uint32_t theta0, dtheta;    // NCO phase of logical sample 0, phase step per sample
@@ -25,6 +27,9 @@ struct AnalyzerParams {
 size_t analyzer_smem_bytes(const AnalyzerParams & p);
 cudaError_t analyzer_configure(size_t smem_bytes);
 cudaError_t analyzer_launch(const AnalyzerParams & p, int grid, size_t smem_bytes, cudaStream_t st);
+// column-per-thread fast path (channelizer8.cu), K in {64,128,256,512}; analyzer_launch() picks it
+bool analyzer8_supported(const AnalyzerParams & p);
+cudaError_t analyzer8_launch(const AnalyzerParams & p, cudaStream_t st);
 
 // ------------------------------------------------------------------ per-stream OFDM synchroniser
 // One CTA walks one stream (channel) through the ofdmflexframesync state machine
@@ -120,15 +125,21 @@ cudaError_t sync8_launch(const SyncParams & p, cudaStream_t st);
 // ------------------------------------------------------------------ packet decode
 // de-interleave + FEC decode + CRC of every completed frame (liquid packetizer_decode, called
 // from inside ofdmflexframesync_execute in the reference)
+struct RangeMark {               // output counters after a chunk's synchroniser
+    unsigned int nrec, pad;
+    unsigned long long arena_used;
+};
 struct PacketParams {
     FrameRec * recs; const FrameAux * aux;
-    const unsigned int * counters;   // [0] = number of records
-    unsigned int first_rec;          // records before this index were decoded by earlier launches
+    const RangeMark * range;         // device: records [range[0].nrec, range[1].nrec) belong to this launch
     uint8_t * arena;                 // encoded payloads (decoded in place / via scratch)
     uint8_t * scratch;               // same size as arena
     uint8_t * decoded;               // same size as arena; payload bytes end up at payload_offset
 };
 cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t st);
+// mark_out = {counters[0], counters[2..3]} (records / arena bytes so far), one thread; runs between
+// the synchroniser of a chunk and its decode so that chunk c decodes records [mark[c], mark[c+1])
+cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_out, cudaStream_t st);
 
 } // namespace b2
 

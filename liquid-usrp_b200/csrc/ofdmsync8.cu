@@ -30,32 +30,31 @@ namespace b2 {
 
 struct S8Layout {
     unsigned int SZ;
-    size_t off_st, off_red, off_dsum, off_stg, off_hist, off_fa, off_fb, off_G0, off_G, off_tw, off_yph, off_yc, off_px,
-           off_ref, off_sym, off_pseq, total;
+    size_t off_st, off_red, off_dsum, off_stg, off_hist, off_fa, off_fb, off_G0, off_yc, off_px, off_ref, off_sym, off_pseq, total;
 };
+// ~31 KB for M = 512: two streams per SM leave room for the channelizer CTA of the next chunk.
+// Gs (training-symbol gains of the current event) aliases FFT buffer B and yph (phases handed to
+// warp 0) aliases FFT buffer A: both are only touched between the last FFT pass of an event and
+// the top barrier of the next one (which of the two is safe for Gs depends on the pass count).
 __host__ __device__ static inline S8Layout s8_layout(unsigned int M, unsigned int cp, unsigned int Na, unsigned int Mp)
 {
     S8Layout L;
     const unsigned int W = M + cp;
     L.SZ = 256;
-    while (L.SZ < 2 * W) L.SZ <<= 1;
+    while (L.SZ < W + M / 2 + 64) L.SZ <<= 1;
     size_t o = 0;
     L.off_st = o;   o += (sizeof(SyncState) + 15) & ~(size_t)15;
     L.off_red = o;  o += 160 * sizeof(float);
-    L.off_dsum = o; o += (16 * 19 + 40) * sizeof(double);
+    L.off_dsum = o; o += (16 * 10 + 32) * sizeof(double);
     L.off_stg = o;  o += (size_t)L.SZ * sizeof(cf);
     L.off_hist = o; o += (size_t)W * sizeof(cf);
-    L.off_fa = o;   o += (size_t)f8_buf_elems(M) * sizeof(cf);
-    L.off_fb = o;   o += (size_t)f8_buf_elems(M) * sizeof(cf);
+    L.off_fa = o;   o += (size_t)f8_buf_elems(M) * sizeof(cf);          // >= 2*(Na+4) floats
+    L.off_fb = o;   o += (size_t)f8_buf_elems(M) * sizeof(cf);          // >= M cf
     L.off_G0 = o;   o += (size_t)M * sizeof(cf);
-    L.off_G = o;    o += (size_t)M * sizeof(cf);
-    L.off_tw = o;   o += (size_t)M * sizeof(cf);
-    L.off_yph = o;  o += (size_t)(Na + 4) * sizeof(float) * 3;
-    o = (o + 7) & ~(size_t)7;
     L.off_yc = o;   o += (size_t)(Mp + 4) * sizeof(cf);
     L.off_px = o;   o += (size_t)(Mp + 4) * sizeof(float);
     L.off_ref = o;  o += (size_t)2 * M;                                 // S0 | S1 training signs, int8
-    L.off_sym = o;  o += ((size_t)M + 15) & ~(size_t)15;
+    L.off_sym = o;  o += 304;                                           // 288 header bits
     L.off_pseq = o; o += 256;
     L.total = (o + 15) & ~(size_t)15;
     return L;
@@ -123,7 +122,7 @@ extern "C" int b2_debug_sync8_prof(unsigned long long * out, int reset)
 #endif
 
 template <unsigned int M>
-__global__ void __launch_bounds__(M / 8) sync8_kernel(const SyncParams p)
+__global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncParams p)   // <= 128 registers: 8 streams of M = 512 per SM
 {
     constexpr unsigned int T = M / 8, NW = T / 32, M2 = M / 2;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -140,9 +139,11 @@ __global__ void __launch_bounds__(M / 8) sync8_kernel(const SyncParams p)
     cf * fa = (cf *)(smem + L.off_fa);
     cf * fb = (cf *)(smem + L.off_fb);
     cf * G0 = (cf *)(smem + L.off_G0);
-    cf * Gs = (cf *)(smem + L.off_G);
-    cf * tw = (cf *)(smem + L.off_tw);
-    float * yph = (float *)(smem + L.off_yph);          // [0..Na): y / y_arg, [Na..2Na): y_abs, [2Na..3Na): x_freq
+    // aliases (see s8_layout): Gs must be the buffer the LAST exchange of the FFT did not use (a thread
+    // leaving the last pass may not overwrite what a slower thread is still loading)
+    constexpr bool last_load_from_b = (M == 256 || M == 512);          // 3 passes: A, B; 4 passes: A, B, A
+    cf * Gs = last_load_from_b ? fa : fb;
+    float * yph = (float *)(last_load_from_b ? fb : fa);               // [0..Na) y / y_arg, [Na..2Na) y_abs
     cf * yc = (cf *)(smem + L.off_yc);                  // pilots of the current symbol, sign removed
     float * pilot_x = (float *)(smem + L.off_px);
     int8_t * refS = (int8_t *)(smem + L.off_ref);
@@ -192,16 +193,15 @@ __global__ void __launch_bounds__(M / 8) sync8_kernel(const SyncParams p)
             G0[i] = g0[i];
             Rr[s] = gR[i];
             rk[s] = p.tb.sc_rank[i];
-            tw[i] = p.fft.tw[i];
             refS[i] = (int8_t)p.tb.S0[i];
             refS[M + i] = (int8_t)p.tb.S1[i];
         }
         for (unsigned int i = t; i < Mp; i += T) pilot_x[i] = p.tb.pilot_x[i];
         for (unsigned int i = t; i < 255; i += T) pilot_seq[i] = p.tb.pilot_seq[i];
     }
-    __syncthreads();
     cf twr[f8_tw_count(M, 8) + 1];           // this thread's twiddles of the passes after the first
-    f8_tw_init<M, 8>(twr, t, tw);
+    f8_tw_init<M, 8>(twr, t, p.fft.tw);
+    const cf * tw = nullptr;                 // no table at run time
     float fxs[8];                            // signed subcarrier index of own subcarriers
     unsigned int pilot_mask = 0;
 #pragma unroll
@@ -723,12 +723,12 @@ __global__ void __launch_bounds__(M / 8) sync8_kernel(const SyncParams p)
                     FrameAux a; a.enc_len = e2; a.sym_bps = (emit == 2) ? S->bps_payload : 0u;
                     p.aux[slot] = a;
                     red[115] = 1.f;
-                    dsum[30] = __longlong_as_double((long long)offb);
+                    dsum[16 * 10 + 2] = __longlong_as_double((long long)offb);
                 }
             }
             __syncthreads();
             if (emit == 2 && red[115] > 0.f) {
-                const unsigned long long offb = (unsigned long long)__double_as_longlong(dsum[30]);
+                const unsigned long long offb = (unsigned long long)__double_as_longlong(dsum[16 * 10 + 2]);
                 const unsigned int m2 = S->payload_mod_len;
                 uint4 * dst = (uint4 *)(p.arena + offb);
                 const uint4 * src = (const uint4 *)penc;

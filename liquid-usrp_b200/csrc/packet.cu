@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketP
     __shared__ uint2 stage[PK_TB_STEPS];
     __shared__ int s_valid;
     const unsigned int tid = threadIdx.x;
-    const unsigned int nrec = p.counters[0];
-    for (unsigned int ri = p.first_rec + blockIdx.x; ri < nrec; ri += gridDim.x) {
+    const unsigned int nrec = p.range[1].nrec;
+    for (unsigned int ri = p.range[0].nrec + blockIdx.x; ri < nrec; ri += gridDim.x) {
         FrameRec * rec = p.recs + ri;
         if (!rec->header_valid) continue;
         const unsigned int plen = rec->payload_len, check = rec->check, fec0 = rec->fec0, fec1 = rec->fec1;
@@ -544,8 +544,8 @@ __global__ void __launch_bounds__(PKF_WARPS * 32) packet_plain_kernel(const Pack
         table[tid] = c;                          // blockDim.x == 256
     }
     __syncthreads();
-    const unsigned int nrec = p.counters[0];
-    for (unsigned int ri = p.first_rec + blockIdx.x * PKF_WARPS + wid; ri < nrec; ri += gridDim.x * PKF_WARPS) {
+    const unsigned int nrec = p.range[1].nrec;
+    for (unsigned int ri = p.range[0].nrec + blockIdx.x * PKF_WARPS + wid; ri < nrec; ri += gridDim.x * PKF_WARPS) {
         FrameRec * rec = p.recs + ri;
         if (!rec->header_valid || rec->fec0 != 1 || rec->fec1 != 1) continue;
         const unsigned int plen = rec->payload_len, crc_len = (rec->check == 6) ? 4u : 0u, n0 = plen + crc_len;
@@ -581,6 +581,19 @@ __global__ void __launch_bounds__(PKF_WARPS * 32) packet_plain_kernel(const Pack
         if (lane == 0) rec->payload_valid = valid;
         __syncwarp();
     }
+}
+
+__global__ void record_mark_kernel(const unsigned int * counters, RangeMark * mark_out)
+{
+    RangeMark m;
+    m.nrec = counters[0]; m.pad = 0;
+    m.arena_used = *(const unsigned long long *)(counters + 2);
+    *mark_out = m;
+}
+cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_out, cudaStream_t st)
+{
+    record_mark_kernel<<<1, 1, 0, st>>>(counters, mark_out);
+    return cudaGetLastError();
 }
 
 static uint2 * g_vit_ws[16] = {nullptr};

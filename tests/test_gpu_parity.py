@@ -178,7 +178,7 @@ def test_idle_channels_corruption_and_noise_only():
 def test_channelizer_output_matches_oracle():
     import orc
     from b2 import pkg
-    for N in (1, 8, 64):
+    for N in (1, 8, 32, 64, 128, 256):      # K = 64..512 take the column-per-thread kernel (channelizer8.cu)
         K = 2 * N
         rng = np.random.default_rng(N)
         T = 700
@@ -205,6 +205,24 @@ def test_channelizer_output_matches_oracle():
         assert cz.shape == (N, T)
         err = np.abs(cz - ref[:, :N].T).max() / np.abs(ref).max()
         assert err < 2e-6, (N, err)
+        # the same stream in ragged pieces (history + partial-block carry across calls), device input
+        import torch
+        g = pkg.MultichannelRx(N, 64, 16, 4)
+        cuts = [0, 3 * K + 5, 3 * K + 6, 200 * K, 300 * K, 300 * K + K // 2, T * K]     # [200K, 300K) takes the zero-copy path
+        got = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if (a % 2) == 0:
+                d = torch.from_numpy(x[a:b].view(np.float32).copy()).cuda()
+                g.execute_device(d.data_ptr(), b - a)
+            else:
+                g.execute(x[a:b])
+            cz2 = g.read_channelizer()
+            if cz2.size:
+                got.append(cz2)
+        g.close()
+        cz2 = np.concatenate(got, axis=1)
+        assert cz2.shape == (N, T)
+        assert np.array_equal(cz2, cz), N
 
 
 def test_batched_single_link_sync_matches_multichannel_oracle_streams():
