@@ -31,7 +31,7 @@ struct SyncCore {
     unsigned int streams = 0;
     size_t tmax = 0;                     // max samples per stream per launch
     // tables
-    DevBuf t_sctype, t_S0, t_S1, t_data, t_pilot, t_pilotx, t_active, t_seq, t_walk, t_B, t_perm, t_tw, t_rank, t_P;
+    DevBuf t_sctype, t_S0, t_S1, t_data, t_pilot, t_pilotx, t_active, t_seq, t_walk, t_B, t_perm, t_tw, t_rank, t_P, t_arank;
     // state
     DevBuf d_st, d_ring, d_G0, d_R, d_penc;
     size_t penc_cap = 0;
@@ -127,6 +127,9 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     for (size_t n = 0; n < plan.pilot_idx.size(); n++) sc_rank[plan.pilot_idx[n]] = (uint16_t)(0x4000u | n);
     if (plan.M_pilot + plan.M_data < 5) return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA path needs at least 5 active subcarriers");
     B2_TRY(t_P.upload(eqgain_fit_matrix(plan)));
+    std::vector<uint16_t> act_rank(M, 0xffff);
+    for (size_t n = 0; n < plan.active_idx.size(); n++) act_rank[plan.active_idx[n]] = (uint16_t)n;
+    B2_TRY(t_arank.upload(act_rank));
     B2_TRY(t_B.upload(B)); B2_TRY(t_perm.upload(fftM.perm)); B2_TRY(t_tw.upload(fftM.tw)); B2_TRY(t_rank.upload(sc_rank));
     // state
     const size_t W = M + cp;
@@ -176,7 +179,7 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     sp.tb.sctype = t_sctype.as<uint8_t>(); sp.tb.S0 = t_S0.as<float>(); sp.tb.S1 = t_S1.as<float>();
     sp.tb.data_idx = t_data.as<uint16_t>(); sp.tb.pilot_idx = t_pilot.as<uint16_t>(); sp.tb.pilot_x = t_pilotx.as<float>();
     sp.tb.active_idx = t_active.as<uint16_t>(); sp.tb.pilot_seq = t_seq.as<uint8_t>(); sp.tb.hdr_walk = t_walk.as<uint16_t>();
-    sp.tb.B = t_B.as<cf>(); sp.tb.sc_rank = t_rank.as<uint16_t>(); sp.tb.eqfit_P = t_P.as<double>();
+    sp.tb.B = t_B.as<cf>(); sp.tb.sc_rank = t_rank.as<uint16_t>(); sp.tb.eqfit_P = t_P.as<double>(); sp.tb.act_rank = t_arank.as<uint16_t>();
     sp.fft.n = fftM.n; sp.fft.npass = fftM.npass;
     sp.fft.radices = 0;
     for (unsigned int i = 0; i < fftM.npass; i++) sp.fft.radices |= fftM.radix[i] << (4 * i);
@@ -519,7 +522,7 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
             (!q->sstream && cudaStreamCreateWithFlags(&q->sstream, cudaStreamNonBlocking) != cudaSuccess) ||
             cudaEventCreate(&q->ev_begin) != cudaSuccess || cudaEventCreate(&q->ev_end) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaStreamCreate failed"); break; }
         // chunk of the pipeline: long enough to amortise launches, short enough to overlap stages
-        q->chunk_blocks = std::max(64u, (1u << 22) / K);
+        q->chunk_blocks = std::max(64u, (1u << 24) / K);
         if (const char * e = getenv("B2_CHUNK_BLOCKS")) { long v = atol(e); if (v >= 1) q->chunk_blocks = (unsigned int)v; }
         if ((rc = q->core.init(M, cp, taper, p, N, q->tcap, device, q->sstream, decode_stream))) break;
         B2_CUDA(cudaMemsetAsync(q->d_stage.p, 0, q->d_stage.bytes, q->stream));

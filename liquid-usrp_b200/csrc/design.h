@@ -272,7 +272,8 @@ static inline int fft_plan(FftPlan & f, unsigned int n)
 // liquid's ofdmframesync_estimate_eqgain_poly fits order-4 polynomials to |G| and arg G over the
 // active subcarriers (abscissa = signed subcarrier index / M).  The abscissae are fixed by the
 // allocation, so the least-squares solution is a constant matrix applied to the ordinates:
-// coef = P y with P = (X^T X)^-1 X^T  (5 x Na, row major), computed here once in long double.
+// coef = P y with P = (X^T X)^-1 X^T, computed here once in long double and returned as
+// P[n*5 + r] (one 40-byte row per active subcarrier, fft-shifted visiting order).
 static inline std::vector<double> eqgain_fit_matrix(const OfdmPlan & o)
 {
     const size_t Na = o.active_idx.size();
@@ -311,7 +312,7 @@ static inline std::vector<double> eqgain_fit_matrix(const OfdmPlan & o)
         for (int r = 0; r < 5; r++) {
             long double a = 0.0L;
             for (int c = 0; c < 5; c++) a += A[r][5 + c] * pw[c];
-            P[(size_t)r * Na + n] = (double)a;
+            P[n * 5 + (size_t)r] = (double)a;
         }
     }
     return P;

@@ -84,7 +84,8 @@ struct SyncTables {             // read-only, global memory
     const uint8_t * pilot_seq;  // [255]
     const uint16_t * hdr_walk;  // [4][18] header de-interleaver walks (n = 36)
     const cf * B;               // [M] e^{j 2 pi backoff i / M}
-    const double * eqfit_P;     // [5][M_pilot+M_data] least-squares matrix of the S1 gain fit (design.h)
+    const double * eqfit_P;     // [M_pilot+M_data][5] least-squares matrix of the S1 gain fit (design.h)
+    const uint16_t * act_rank;  // [M] position in the fft-shifted visiting order of the active subcarriers; null: 0xffff
     const uint16_t * sc_rank;   // [M] data: rank among data subcarriers (ascending index);
                                 //     pilot: 0x4000 | rank in fft-shifted visiting order; null: 0xffff
 };

@@ -89,6 +89,14 @@ __device__ __forceinline__ float atan2_fast(float y, float x)
     return copysignf(r, y);
 }
 
+// nco_constrain_dev for |theta| < 2 pi (the NCO trims): p - floor(p) is p or p + 1 there
+__device__ __forceinline__ uint32_t nco_constrain_small(float theta)
+{
+    const double p = (double)theta * 0.15915494309189535;
+    const double f = p < 0.0 ? p + 1.0 : p;
+    return (uint32_t)(__double2ull_rn(f * 4294967296.0) & 0xffffffffull);
+}
+
 // hard demapper with the constellation known at compile time (same decisions as demod_symbol)
 template <int MB> __device__ __forceinline__ unsigned int demod_axis_t(float v, float alpha)
 {
@@ -273,7 +281,25 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
         while (head2 >= W) head2 -= W;
 
         cf v[8];
-        if (fused) {
+        if (state == ST_RX && adv == W) {
+            // steady state of a frame: the whole window is replaced, so it is rewritten from slot 0
+            // (head2 = 0) and the FFT window starts `off` samples in
+#pragma unroll
+            for (unsigned int s = 0; s < 8; s++) {
+                const unsigned int j = off + t + s * T;
+                cf x = stg[(pos + j) & SZM];
+                if (mixing) x = mix_down(x, nco_cexp_fast(th + j * dth));
+                v[s] = x;
+                hist[j] = x;
+            }
+            for (unsigned int jj = t; jj < cp; jj += T) {
+                const unsigned int j = (jj < off) ? jj : jj + M;
+                cf x = stg[(pos + j) & SZM];
+                if (mixing) x = mix_down(x, nco_cexp_fast(th + j * dth));
+                hist[j] = x;
+            }
+            head2 = 0;
+        } else if (fused) {
             const unsigned int j0 = adv - (W - off);                        // first new sample inside the FFT window
 #pragma unroll
             for (unsigned int s = 0; s < 8; s++) {
@@ -428,33 +454,54 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
                     }
                 }
                 __syncthreads();
+                PH(11);
                 if (red[110] != 0.f) {
                     // G *= M/sqrt(Na) * B ; smooth |G| and arg G with an order-4 polynomial over the
                     // active subcarriers (liquid ofdmframesync_estimate_eqgain_poly); R = B / G.
-                    // coef = P y with the constant matrix P of design.h eqgain_fit_matrix().
+                    // coef = P y with the constant matrix P of design.h eqgain_fit_matrix(); every
+                    // thread works on its own 8 subcarriers, only the phase unwrap (sequential in the
+                    // fft-shifted visiting order) goes through shared memory.
                     const float gsc = (float)M / sqrtf((float)Na);
-                    for (unsigned int n = t; n < Na; n += T) {
-                        unsigned int k = p.tb.active_idx[n];
-                        cf gk = cmul(cscale(Gs[k], gsc), p.tb.B[k]);
-                        yph[Na + n] = sqrtf(gk.x * gk.x + gk.y * gk.y);
-                        yph[n] = atan2f(gk.y, gk.x);
+                    const float bphi = 2.0f * (float)p.backoff / (float)M;     // B[i] = e^{j pi bphi i}
+                    unsigned int ar[8];
+                    float ya[8];
+                    cf Bq[8];
+#pragma unroll
+                    for (unsigned int s = 0; s < 8; s++) {
+                        const unsigned int i = t + s * T;
+                        ar[s] = p.tb.act_rank[i];
+                        float sn, cs;
+                        sincospif(bphi * (float)i, &sn, &cs);
+                        Bq[s] = make_float2(cs, sn);
+                    }
+#pragma unroll
+                    for (unsigned int s = 0; s < 8; s++) {
+                        if (ar[s] == 0xffffu) continue;
+                        const cf gk = cmul(cscale(g[s], gsc), Bq[s]);
+                        ya[s] = sqrtf(gk.x * gk.x + gk.y * gk.y);
+                        yph[ar[s]] = atan2_fast(gk.y, gk.x);
                     }
                     __syncthreads();
+                    PH(12);
                     if (wid == 0) {
                         float a, b;
                         warp_unwrap(yph, nullptr, Na, true, lane, a, b);
                     }
                     __syncthreads();
+                    PH(13);
                     double ca[10];
 #pragma unroll
                     for (int i = 0; i < 10; i++) ca[i] = 0.0;
-                    for (unsigned int n = t; n < Na; n += T) {
-                        const double ya = (double)yph[Na + n], yg = (double)yph[n];
+#pragma unroll
+                    for (unsigned int s = 0; s < 8; s++) {
+                        if (ar[s] == 0xffffu) continue;
+                        const double yav = (double)ya[s], yg = (double)yph[ar[s]];
+                        const double * pr = p.tb.eqfit_P + (size_t)ar[s] * 5;
 #pragma unroll
                         for (int r = 0; r < 5; r++) {
-                            const double pr = p.tb.eqfit_P[(size_t)r * Na + n];
-                            ca[r] += pr * ya;
-                            ca[5 + r] += pr * yg;
+                            const double pv = __ldg(pr + r);
+                            ca[r] = fma(pv, yav, ca[r]);
+                            ca[5 + r] = fma(pv, yg, ca[5 + r]);
                         }
                     }
 #pragma unroll
@@ -472,21 +519,22 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
                             ca[i] = a;
                         }
                     }
+                    PH(14);
 #pragma unroll
                     for (unsigned int s = 0; s < 8; s++) {
-                        const unsigned int i = t + s * T;
                         if (rk[s] == 0xffffu) { Rr[s] = make_float2(0.f, 0.f); continue; }
                         const double xv = (double)(fxs[s] / (float)M);
                         const double va = (((ca[4] * xv + ca[3]) * xv + ca[2]) * xv + ca[1]) * xv + ca[0];
                         const double vg = (((ca[9] * xv + ca[8]) * xv + ca[7]) * xv + ca[6]) * xv + ca[5];
-                        float A = (float)va, thv = (float)vg;
+                        const float A = (float)va;
+                        float thv = (float)vg;
+                        thv = fmaf(-6.28318530717958647692f, rintf(thv * 0.15915494309189533577f), thv);
                         float sn, cs;
-                        sincosf(thv, &sn, &cs);
-                        cf G = make_float2(A * cs, A * sn);
-                        cf B = p.tb.B[i];
-                        float d = G.x * G.x + G.y * G.y;
-                        cf num = cmulc(B, G);
-                        Rr[s] = make_float2(num.x / d, num.y / d);
+                        __sincosf(thv, &sn, &cs);
+                        // R = B / G = B conj(G) / |G|^2 with G = A e^{j thv}
+                        const float inv = __frcp_rn(A);
+                        const cf num = cmulc(Bq[s], make_float2(cs, sn));
+                        Rr[s] = make_float2(num.x * inv, num.y * inv);
                     }
                     if (t == 0) {
                         S->state = ST_RX;
@@ -495,7 +543,7 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
                     }
                 }
             }
-            PH(7);
+            PH(7 + state);
             continue;                        // loop top synchronises
         }
 
@@ -535,7 +583,7 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
                     float dphi = p0 - S->phi_prime;
                     while (dphi > PI_F) dphi -= 2 * PI_F;
                     while (dphi < -PI_F) dphi += 2 * PI_F;
-                    S->nco_dtheta += nco_constrain_dev(1e-3f * dphi);
+                    S->nco_dtheta += nco_constrain_small(1e-3f * dphi);
                 }
                 S->phi_prime = p0;
                 S->num_symbols++;

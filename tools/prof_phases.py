@@ -16,8 +16,8 @@ out = (C.c_ulonglong * 16)()
 L.b2_debug_sync8_prof(out, 1)
 rx.execute_device(x.data_ptr(), len(period) * reps); rx.poll()
 L.b2_debug_sync8_prof(out, 0)
-names = ["top wait", "consume+pass1", "fft rest", "eq+pilots", "fit", "derot+demap", "pack+emit", "preamble post", "-", "-", "-", "-"]
-tot = sum(out[:12])
+names = ["top wait", "consume+pass1", "fft rest", "eq+pilots", "fit", "derot+demap", "pack+emit", "seek", "s0a", "s0b", "s1 rest(eval)", "s1 fft..accept", "s1 yph", "s1 unwrap", "s1 P*y+reduce", "-"]
+tot = sum(out[:16])
 print("timing", rx.last_timing())
 for i, n in enumerate(names):
     print("%-14s %10d cycles %5.1f%%" % (n, out[i], 100.0 * out[i] / tot))
