@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(K, 1) analyzer8_kernel(const AnalyzerParams p)
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    tw[r] = p.fft.tw[r];
+    f8_twt_build<K, 1>(tw, p.fft.tw, r, K);          // per-pass twiddle tables in lane order
     if (r < P - 1) rw[2 * JB + r] = nco_cexp_pi(p.theta0 + (L0 + r) * K * p.dtheta);
     if (r >= 32 && r < 32 + JB) rw[r - 32] = nco_cexp_pi(p.theta0 + (L0 + P - 1 + (r - 32)) * K * p.dtheta);
     __syncthreads();
@@ -108,8 +108,17 @@ __global__ void __launch_bounds__(K, 1) analyzer8_kernel(const AnalyzerParams p)
         const unsigned int nb = min(JB, B1 - (B0 + k * JB));
         const cf * rwk = rw + (k & 1) * JB;
         mbar_wait(bar, k & 1);
+        if (p.row_alt) {
+            // the NCO of multichannelrx advances by a multiple of pi per block (K*dtheta = -(N-1) pi,
+            // lib/multichannelrx.cc:98): one phasor per round, the sign alternates or stays
+            const cf w0 = cmul(rwk[0], colw);
+            const cf w1 = p.row_alt < 0 ? make_float2(-w0.x, -w0.y) : w0;
 #pragma unroll
-        for (unsigned int i = 0; i < JB; i++) a[P - 1 + i] = mix_down(stage[i * K + r], cmul(rwk[i], colw));
+            for (unsigned int i = 0; i < JB; i++) a[P - 1 + i] = mix_down(stage[i * K + r], (i & 1) ? w1 : w0);
+        } else {
+#pragma unroll
+            for (unsigned int i = 0; i < JB; i++) a[P - 1 + i] = mix_down(stage[i * K + r], cmul(rwk[i], colw));
+        }
         __syncthreads();                                 // stage consumed
         if (k + 1 < nrounds) {
             if (r == 0) {
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(K, 1) analyzer8_kernel(const AnalyzerParams p)
         // K-point forward FFT of row g by group g
         cf v[8];
         f8_load<K>(v, j, bufA + g * BUF);
-        f8_run<K, 1, -1>(v, j, bufB + g * BUF, bufA + g * BUF, tw, [] { __syncthreads(); });
+        f8_run<K, 1, -1>(v, j, bufB + g * BUF, bufA + g * BUF, nullptr, [] { __syncthreads(); }, nullptr, tw);
 
         // channels 0..N-1 -> out[c][col0 + block], via a transposed tile
 #pragma unroll
@@ -190,9 +199,12 @@ bool analyzer8_supported(const AnalyzerParams & p)
     return p.P == A8_P && (p.K == 64 || p.K == 128 || p.K == 256 || p.K == 512) && p.N * 2 == p.K;
 }
 
-cudaError_t analyzer8_launch(const AnalyzerParams & p, cudaStream_t st)
+cudaError_t analyzer8_launch(const AnalyzerParams & p0, cudaStream_t st)
 {
-    if (p.nblocks == 0) return cudaSuccess;
+    if (p0.nblocks == 0) return cudaSuccess;
+    AnalyzerParams p = p0;
+    const uint32_t kd = p.K * p.dtheta;
+    p.row_alt = (kd == 0u) ? 1 : ((kd == 0x80000000u) ? -1 : 0);
     switch (p.K) {
     case 64:  return analyzer8_launch_t<64>(p, st);
     case 128: return analyzer8_launch_t<128>(p, st);

@@ -2,8 +2,9 @@
 // threads, every thread holding 8 points (v[s] <-> element j + s*N/8 for thread j) before the
 // first pass and after the last one.  Passes are radix 8 as far as N allows, the last one
 // radix 2/4 where log2 N is not a multiple of 3; between passes the points are exchanged
-// through two ping-pong shared-memory buffers (skewed, one pad element per 8, so both the
-// scattered stores and the strided loads are bank-conflict free).  The output is in NATURAL
+// through two ping-pong shared-memory buffers (XOR-swizzled, p ^ ((p >> 3) & 15), which makes the
+// scattered stores of every pass and the strided loads of the next one bank-conflict free for
+// every N from 64 to 4096 -- modelled exhaustively).  The output is in NATURAL
 // order, so the transform needs neither a bit-reversal pass nor a permutation table.
 //
 // This is the K-point transform inside firpfbch_crcf_analyzer_execute
@@ -14,8 +15,8 @@
 
 namespace b2 {
 
-__host__ __device__ constexpr unsigned int f8_pad(unsigned int i) { return i + (i >> 3); }
-__host__ __device__ constexpr unsigned int f8_buf_elems(unsigned int n) { return n + (n >> 3) + 8; }
+__host__ __device__ constexpr unsigned int f8_pad(unsigned int i) { return i ^ ((i >> 3) & 15u); }
+__host__ __device__ constexpr unsigned int f8_buf_elems(unsigned int n) { return n; }
 
 template <int DIR> __device__ __forceinline__ void f8_dft(cf & a0, cf & a1) { dft2<DIR>(a0, a1); }
 template <int DIR> __device__ __forceinline__ void f8_dft(cf & a0, cf & a1, cf & a2, cf & a3)
@@ -28,8 +29,11 @@ template <int DIR> __device__ __forceinline__ void f8_dft(cf & a0, cf & a1, cf &
 // twiddle + butterflies of one pass; Ns = product of the radices of the earlier passes.
 // The twiddles of a thread do not change from one transform to the next, so a persistent
 // kernel may keep them in registers: twr != nullptr -> twr[u*(R-1) + q-1] (see f8_tw_init).
+// A third source, for kernels short of registers: twt = per-pass table in the order the lanes read
+// it, twt[(q-1)*Ns + k] (conflict-free; built once per CTA by f8_twt_build).
 template <unsigned int N, unsigned int Ns, unsigned int R, int DIR>
-__device__ __forceinline__ void f8_pass(cf (&v)[8], unsigned int j, const cf * __restrict__ tw, const cf * twr = nullptr)
+__device__ __forceinline__ void f8_pass(cf (&v)[8], unsigned int j, const cf * __restrict__ tw, const cf * twr = nullptr,
+                                        const cf * __restrict__ twt = nullptr)
 {
     constexpr unsigned int T = N / 8, U = 8 / R;
 #pragma unroll
@@ -38,7 +42,7 @@ __device__ __forceinline__ void f8_pass(cf (&v)[8], unsigned int j, const cf * _
             const unsigned int k = (j + u * T) & (Ns - 1);
 #pragma unroll
             for (unsigned int q = 1; q < R; q++) {
-                cf w = twr ? twr[u * (R - 1) + q - 1] : tw[k * q * (N / (Ns * R))];
+                cf w = twr ? twr[u * (R - 1) + q - 1] : (twt ? twt[(q - 1) * Ns + k] : tw[k * q * (N / (Ns * R))]);
                 if (DIR > 0) w.y = -w.y;
                 v[u + q * U] = cmul(v[u + q * U], w);
             }
@@ -92,18 +96,38 @@ __device__ __forceinline__ void f8_tw_init(cf * twr, unsigned int j, const cf * 
     if constexpr (Ns * R < N) f8_tw_init<N, Ns * R>(twr + (Ns > 1 ? U * (R - 1) : 0), j, tw);
 }
 
+// ordered per-pass tables (see f8_pass): total size and construction by `nthreads` threads
+__host__ __device__ constexpr unsigned int f8_twt_elems(unsigned int n, unsigned int ns)
+{
+    return ns >= n ? 0u : (ns > 1 ? (f8_radix(n, ns) - 1) * ns : 0u) + f8_twt_elems(n, ns * f8_radix(n, ns));
+}
+template <unsigned int N, unsigned int Ns>
+__device__ __forceinline__ void f8_twt_build(cf * twt, const cf * __restrict__ tw, unsigned int tid, unsigned int nthreads)
+{
+    constexpr unsigned int R = f8_radix(N, Ns);
+    if constexpr (Ns > 1) {
+        for (unsigned int e = tid; e < (R - 1) * Ns; e += nthreads) {
+            const unsigned int q = e / Ns + 1, k = e % Ns;
+            twt[e] = tw[k * q * (N / (Ns * R))];
+        }
+    }
+    if constexpr (Ns * R < N) f8_twt_build<N, Ns * R>(twt + (Ns > 1 ? (R - 1) * Ns : 0), tw, tid, nthreads);
+}
+
 // passes from Ns on; `sync` is the barrier of the N/8 threads that carry this transform
 template <unsigned int N, unsigned int Ns, int DIR, typename Sync>
 __device__ __forceinline__ void f8_run(cf (&v)[8], unsigned int j, cf * __restrict__ bufA, cf * __restrict__ bufB,
-                                       const cf * __restrict__ tw, Sync sync, const cf * twr = nullptr)
+                                       const cf * __restrict__ tw, Sync sync, const cf * twr = nullptr,
+                                       const cf * __restrict__ twt = nullptr)
 {
     constexpr unsigned int R = f8_radix(N, Ns), U = 8 / R;
-    f8_pass<N, Ns, R, DIR>(v, j, tw, twr);
+    f8_pass<N, Ns, R, DIR>(v, j, tw, twr, twt);
     if constexpr (Ns * R < N) {
         f8_store<N, Ns, R>(v, j, bufA);
         sync();
         f8_load<N>(v, j, bufA);
-        f8_run<N, Ns * R, DIR, Sync>(v, j, bufB, bufA, tw, sync, twr ? twr + (Ns > 1 ? U * (R - 1) : 0) : nullptr);
+        f8_run<N, Ns * R, DIR, Sync>(v, j, bufB, bufA, tw, sync, twr ? twr + (Ns > 1 ? U * (R - 1) : 0) : nullptr,
+                                     twt ? twt + (Ns > 1 ? (R - 1) * Ns : 0) : nullptr);
     }
 }
 

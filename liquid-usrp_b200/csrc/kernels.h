@@ -20,6 +20,7 @@ struct AnalyzerParams {
     unsigned int nblocks;       // output blocks this launch; block b reads rows b .. b+P-1
     const float * taps;         // [P][K]: taps[n*K + i] = h[i + n*K]
     uint32_t theta0, dtheta;    // NCO phase of logical sample 0, phase step per sample
+    int row_alt;                // set by the launcher: K*dtheta == 0 (+1) or pi (-1) mod 2 pi, else 0
     cf * out;                   // out[c*out_stride + out_col0 + b]
     size_t out_stride, out_col0;
     FftDev fft;                 // K-point plan (perm / tw in global memory)
