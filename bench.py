@@ -277,6 +277,8 @@ def main():
                     "of BASELINE configs[4]'s 2^31; 2.1 GB of input per step, far larger than L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"])
+    ap.add_argument("--receivers", type=int, default=1, help="extra leg: R independent receivers sharing this GPU (reported under "
+                    "'multi_receiver', never as the headline): shows that one receiver is bound by its 256 serial chains")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -403,6 +405,27 @@ def main():
                          "path": {"alg_bytes_per_sample": B_ALG_PATH, "achieved": n_step * B_ALG_PATH / (kt_avg[3] * 1e-3) / 1e9,
                                   "frac": n_step * B_ALG_PATH / (kt_avg[3] * 1e-3) / 1e9 / peak}},
             "clocks": clk.summary()}
+    if args.receivers > 1:
+        rxs = [rx] + [pkg.MultichannelRx(w["N"], w["M"], w["cp"], w["taper"], device=local_rank, max_batch=n_step) for _ in range(args.receivers - 1)]
+
+        def drive(r, k):
+            for _ in range(k):
+                r.execute_device(d_x.data_ptr(), n_step)
+                r.poll_view()
+        for phase_steps in (2, args.steps):
+            ths = [threading.Thread(target=drive, args=(r, phase_steps)) for r in rxs]
+            barrier()
+            tm = time.perf_counter()
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            barrier()
+            tm = time.perf_counter() - tm
+        line["multi_receiver"] = {"receivers": args.receivers, "value": args.receivers * n_step * args.steps / tm / 1e6, "unit": "Msamples/s",
+                                  "note": "aggregate of independent 256-channel receivers on ONE GPU, each fed the same device-resident stream"}
+        for r in rxs[1:]:
+            r.close()
     if rank == 0 and not args.no_cpu:
         cores = cpu_cores()
         ncpu, tcpu, _nf, per_step = cpu_receivers(period, cores, 2, seconds=10.0)

@@ -167,6 +167,10 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     sp.M = M; sp.cp = cp; sp.M2 = M / 2; sp.backoff = plan.backoff;
     sp.M_pilot = plan.M_pilot; sp.M_data = plan.M_data; sp.M_S0 = plan.M_S0; sp.M_S1 = plan.M_S1;
     sp.thresh = plan.thresh; sp.pilot_sx = plan.pilot_sx; sp.pilot_sxx = plan.pilot_sxx;
+    {
+        const float a = (float)plan.backoff * 2.0f * 3.14159274101257324219f / (float)M;
+        sp.b_cos = cosf(a); sp.b_sin = sinf(a);
+    }
     for (int i = 0; i < 9; i++) sp.qam_alpha[i] = 1.0f;
     sp.qam_alpha[2] = 1.0f / sqrtf(2.0f); sp.qam_alpha[4] = 1.0f / sqrtf(10.0f);
     sp.qam_alpha[6] = 1.0f / sqrtf(42.0f); sp.qam_alpha[8] = 1.0f / sqrtf(170.0f);

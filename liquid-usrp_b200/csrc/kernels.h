@@ -95,6 +95,7 @@ struct SyncParams {
     unsigned int M, cp, M2, backoff;
     unsigned int M_pilot, M_data, M_S0, M_S1;
     float thresh, pilot_sx, pilot_sxx;
+    float b_cos, b_sin;         // e^{j 2 pi backoff / M}: rotation of the S1 metric (ofdmframesync_execute_S1)
     float qam_alpha[9];         // 1/sqrt(2,10,42,170) at index bps = 2,4,6,8
     unsigned int streams;
     const cf * in;              // in[s*in_stride + t], t < nsamples

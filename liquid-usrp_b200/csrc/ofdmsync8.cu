@@ -130,7 +130,7 @@ extern "C" int b2_debug_sync8_prof(unsigned long long * out, int reset)
 #endif
 
 template <unsigned int M>
-__global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncParams p)   // <= 128 registers: 8 streams of M = 512 per SM
+__global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync8_kernel(const SyncParams p)   // <= 168 registers at M = 512: 6 streams per SM
 {
     constexpr unsigned int T = M / 8, NW = T / 32, M2 = M / 2;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -275,7 +275,6 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
         const unsigned int adv = min(need, avail);
         const bool fire = (adv == need);
         const unsigned int off = (state == ST_RX) ? cp - p.backoff : cp;    // FFT window offset in the sample window
-        const bool fused = fire && (adv >= W - off);                        // FFT window made of new samples only
         const bool mixing = (state != ST_SEEK) && ((th | dth) != 0u);     // e^{-j0} = 1 exactly
         unsigned int head2 = head + adv;
         while (head2 >= W) head2 -= W;
@@ -287,43 +286,15 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
 #pragma unroll
             for (unsigned int s = 0; s < 8; s++) {
                 const unsigned int j = off + t + s * T;
-                cf x = stg[(pos + j) & SZM];
-                if (mixing) x = mix_down(x, nco_cexp_fast(th + j * dth));
+                const cf x = mix_down(stg[(pos + j) & SZM], nco_cexp_fast(th + j * dth));     // e^{-j0} = 1 exactly
                 v[s] = x;
                 hist[j] = x;
             }
             for (unsigned int jj = t; jj < cp; jj += T) {
                 const unsigned int j = (jj < off) ? jj : jj + M;
-                cf x = stg[(pos + j) & SZM];
-                if (mixing) x = mix_down(x, nco_cexp_fast(th + j * dth));
-                hist[j] = x;
+                hist[j] = mix_down(stg[(pos + j) & SZM], nco_cexp_fast(th + j * dth));
             }
             head2 = 0;
-        } else if (fused) {
-            const unsigned int j0 = adv - (W - off);                        // first new sample inside the FFT window
-#pragma unroll
-            for (unsigned int s = 0; s < 8; s++) {
-                const unsigned int j = j0 + t + s * T;
-                cf x = stg[(pos + j) & SZM];
-                if (mixing) x = mix_down(x, nco_cexp_fast(th + j * dth));
-                v[s] = x;
-                if (j + W >= adv) {
-                    unsigned int k = head + j;
-                    while (k >= W) k -= W;
-                    hist[k] = x;
-                }
-            }
-            // the new samples outside the FFT window: [0, j0) and [j0 + M, adv)
-            for (unsigned int jj = t; jj < adv - M; jj += T) {
-                const unsigned int j = (jj < j0) ? jj : jj + M;
-                if (j + W >= adv) {
-                    cf x = stg[(pos + j) & SZM];
-                    if (mixing) x = mix_down(x, nco_cexp_fast(th + j * dth));
-                    unsigned int k = head + j;
-                    while (k >= W) k -= W;
-                    hist[k] = x;
-                }
-            }
         } else {
             for (unsigned int j = t; j < adv; j += T) {
                 if (j + W >= adv) {
@@ -396,16 +367,21 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
             }
             __syncthreads();
             float mr = 0.f, mi = 0.f, cr = 0.f, ci = 0.f;
+            // s_hat = sum G[i+step] conj(G[i]) over the training subcarriers (ref = 0 elsewhere, so the
+            // products of the odd subcarriers of S0 vanish by themselves)
 #pragma unroll
             for (unsigned int s = 0; s < 8; s++) {
                 const unsigned int i = t + s * T;
-                if ((i & (step - 1)) == 0) {
-                    cf g2 = Gs[(i + step) & (M - 1)];
-                    cf tt = cmulc(g2, g[s]);
-                    mr += tt.x; mi += tt.y;
-                }
-                if (state == ST_S0A) G0[i] = g[s];
-                else if (state == ST_S0B) { cf tt = cmulc(g[s], G0[i]); cr += tt.x; ci += tt.y; }
+                const cf g2 = Gs[(i + step) & (M - 1)];
+                const cf tt = cmulc(g2, g[s]);
+                mr += tt.x; mi += tt.y;
+            }
+            if (state == ST_S0A) {
+#pragma unroll
+                for (unsigned int s = 0; s < 8; s++) G0[t + s * T] = g[s];
+            } else if (state == ST_S0B) {
+#pragma unroll
+                for (unsigned int s = 0; s < 8; s++) { const cf tt = cmulc(g[s], G0[t + s * T]); cr += tt.x; ci += tt.y; }
             }
             if (state == ST_SEEK) cr = en;
             block_sum4(mr, mi, cr, ci);
@@ -444,9 +420,10 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
                 if (t == 0) {
                     S->num_symbols++;
                     cf s_hat = make_float2(mr / (float)p.M_S1 * S->g0, mi / (float)p.M_S1 * S->g0);
-                    float a = (float)p.backoff * 2.0f * PI_F / (float)M;
-                    s_hat = cmul(s_hat, make_float2(cosf(a), sinf(a)));
-                    int accept = (hypotf(s_hat.x, s_hat.y) > p.thresh) && (fabsf(atan2f(s_hat.y, s_hat.x)) < 0.1f * PI_F);
+                    s_hat = cmul(s_hat, make_float2(p.b_cos, p.b_sin));
+                    // |s_hat| > thresh and |arg s_hat| < 0.1 pi, without hypotf / atan2f
+                    int accept = (s_hat.x * s_hat.x + s_hat.y * s_hat.y > p.thresh * p.thresh) &&
+                                 (s_hat.x > 0.f) && (fabsf(s_hat.y) < 0.32491969623290632616f * s_hat.x);
                     red[110] = (float)accept;
                     if (!accept) {
                         if (S->num_symbols == 16) phy_reset();
@@ -474,6 +451,13 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
                         sincospif(bphi * (float)i, &sn, &cs);
                         Bq[s] = make_float2(cs, sn);
                     }
+                    double pv[8][5];                 // own rows of the fit matrix, fetched while the phases unwrap
+#pragma unroll
+                    for (unsigned int s = 0; s < 8; s++) {
+                        const double * pr = p.tb.eqfit_P + (size_t)(ar[s] == 0xffffu ? 0u : ar[s]) * 5;
+#pragma unroll
+                        for (int r = 0; r < 5; r++) pv[s][r] = __ldg(pr + r);
+                    }
 #pragma unroll
                     for (unsigned int s = 0; s < 8; s++) {
                         if (ar[s] == 0xffffu) continue;
@@ -483,10 +467,7 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
                     }
                     __syncthreads();
                     PH(12);
-                    if (wid == 0) {
-                        float a, b;
-                        warp_unwrap(yph, nullptr, Na, true, lane, a, b);
-                    }
+                    if (wid == 0) warp_unwrap_seg(yph, Na, lane);
                     __syncthreads();
                     PH(13);
                     double ca[10];
@@ -496,12 +477,10 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
                     for (unsigned int s = 0; s < 8; s++) {
                         if (ar[s] == 0xffffu) continue;
                         const double yav = (double)ya[s], yg = (double)yph[ar[s]];
-                        const double * pr = p.tb.eqfit_P + (size_t)ar[s] * 5;
 #pragma unroll
                         for (int r = 0; r < 5; r++) {
-                            const double pv = __ldg(pr + r);
-                            ca[r] = fma(pv, yav, ca[r]);
-                            ca[5 + r] = fma(pv, yg, ca[5 + r]);
+                            ca[r] = fma(pv[s][r], yav, ca[r]);
+                            ca[5 + r] = fma(pv[s][r], yg, ca[5 + r]);
                         }
                     }
 #pragma unroll
@@ -598,8 +577,7 @@ __global__ void __launch_bounds__(M / 8, 512 / (M / 8)) sync8_kernel(const SyncP
         {
             const float p0 = red[111], p1 = red[112];
 #pragma unroll
-            for (unsigned int s = 0; s < 8; s++) {
-                if (rk[s] == 0xffffu) { v[s] = make_float2(0.f, 0.f); continue; }
+            for (unsigned int s = 0; s < 8; s++) {       // null subcarriers carry 0 (their equaliser tap is 0)
                 float thv = __fadd_rn(p0, __fmul_rn(p1, fxs[s]));
                 float sn, cs;
                 __sincosf(thv, &sn, &cs);

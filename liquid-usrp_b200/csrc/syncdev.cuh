@@ -98,6 +98,49 @@ __device__ __forceinline__ void warp_unwrap(float * y, const float * __restrict_
     }
 }
 
+// the same unwrap for long arrays (the S1 gain phases, one per active subcarrier), in place: each
+// lane walks one contiguous segment twice -- first to count its 2*pi steps, then, after a warp
+// scan of the counts, to apply them -- instead of 32 elements per warp-wide iteration
+__device__ __forceinline__ void warp_unwrap_seg(float * y, unsigned int n, unsigned int lane)
+{
+    const unsigned int L = (n + 31) / 32;
+    const unsigned int lo = min(n, lane * L), hi = min(n, lo + L);
+    const float before = (lo > 0 && lo < n) ? y[lo - 1] : 0.f;      // raw value left of the segment
+    int total = 0;
+    {
+        float prev = before;
+        for (unsigned int i = lo; i < hi; i++) {
+            const float raw = y[i];
+            if (i > 0) {
+                const float d = raw - prev;
+                total += (d > PI_F) ? -1 : ((d < -PI_F) ? 1 : 0);
+            }
+            prev = raw;
+        }
+    }
+    int incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned int)o) incl += t;
+    }
+    __syncwarp();                                                    // every lane has read its `before`
+    int k = incl - total;
+    float prev = before;
+    for (unsigned int i = lo; i < hi; i++) {
+        const float raw = y[i];
+        if (i > 0) {
+            const float d = raw - prev;
+            k += (d > PI_F) ? -1 : ((d < -PI_F) ? 1 : 0);
+        }
+        prev = raw;
+        float yy = raw;
+        for (int q = k; q > 0; q--) yy += 2 * PI_F;
+        for (int q = k; q < 0; q++) yy -= 2 * PI_F;
+        y[i] = yy;
+    }
+}
+
 // solve the 5x5 normal equations sum_c S[r+c] p[c] = b[r] (Gaussian elimination, partial pivoting)
 __device__ __forceinline__ void solve5(const double * __restrict__ S, const double * __restrict__ b, double * __restrict__ coef)
 {
