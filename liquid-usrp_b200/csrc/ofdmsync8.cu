@@ -30,7 +30,7 @@ namespace b2 {
 
 struct S8Layout {
     unsigned int SZ;
-    size_t off_st, off_red, off_dsum, off_stg, off_hist, off_fa, off_fb, off_G0, off_yc, off_px, off_ref, off_sym, off_pseq, total;
+    size_t off_st, off_red, off_dsum, off_stg, off_hist, off_fa, off_fb, off_G0, off_yc, off_px, off_sym, off_pseq, total;
 };
 // ~31 KB for M = 512: two streams per SM leave room for the channelizer CTA of the next chunk.
 // Gs (training-symbol gains of the current event) aliases FFT buffer B and yph (phases handed to
@@ -53,7 +53,6 @@ __host__ __device__ static inline S8Layout s8_layout(unsigned int M, unsigned in
     L.off_G0 = o;   o += (size_t)M * sizeof(cf);
     L.off_yc = o;   o += (size_t)(Mp + 4) * sizeof(cf);
     L.off_px = o;   o += (size_t)(Mp + 4) * sizeof(float);
-    L.off_ref = o;  o += (size_t)2 * M;                                 // S0 | S1 training signs, int8
     L.off_sym = o;  o += 304;                                           // 288 header bits
     L.off_pseq = o; o += 256;
     L.total = (o + 15) & ~(size_t)15;
@@ -154,7 +153,6 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync
     float * yph = (float *)(last_load_from_b ? fb : fa);               // [0..Na) y / y_arg, [Na..2Na) y_abs
     cf * yc = (cf *)(smem + L.off_yc);                  // pilots of the current symbol, sign removed
     float * pilot_x = (float *)(smem + L.off_px);
-    int8_t * refS = (int8_t *)(smem + L.off_ref);
     uint8_t * sym = (uint8_t *)(smem + L.off_sym);
     uint8_t * pilot_seq = (uint8_t *)(smem + L.off_pseq);
     const unsigned int SZM = L.SZ - 1, PF = L.SZ - 2;
@@ -187,6 +185,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync
     // ---- persistent state and tables
     cf Rr[8];
     unsigned int rk[8];
+    float ref_s0[8], ref_s1[8];              // training symbols (+-1 / 0) of own subcarriers
     {
         const uint32_t * src = (const uint32_t *)(p.st + sidx);
         uint32_t * dst = (uint32_t *)S;
@@ -201,8 +200,8 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync
             G0[i] = g0[i];
             Rr[s] = gR[i];
             rk[s] = p.tb.sc_rank[i];
-            refS[i] = (int8_t)p.tb.S0[i];
-            refS[M + i] = (int8_t)p.tb.S1[i];
+            ref_s0[s] = p.tb.S0[i];
+            ref_s1[s] = p.tb.S1[i];
         }
         for (unsigned int i = t; i < Mp; i += T) pilot_x[i] = p.tb.pilot_x[i];
         for (unsigned int i = t; i < 255; i += T) pilot_seq[i] = p.tb.pilot_seq[i];
@@ -296,13 +295,22 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync
             }
             head2 = 0;
         } else {
-            for (unsigned int j = t; j < adv; j += T) {
-                if (j + W >= adv) {
-                    cf x = stg[(pos + j) & SZM];
-                    if (mixing) x = mix_down(x, nco_cexp_fast(th + j * dth));
-                    unsigned int k = head + j;
-                    while (k >= W) k -= W;
-                    hist[k] = x;
+            // only the last W of the new samples can survive in the window
+            const unsigned int jlo = adv > W ? adv - W : 0u;
+            unsigned int k = head + jlo + t;
+            while (k >= W) k -= W;
+            const unsigned int kstep = T % W;            // T < W for every supported shape
+            if (mixing) {
+                for (unsigned int j = jlo + t; j < adv; j += T) {
+                    hist[k] = mix_down(stg[(pos + j) & SZM], nco_cexp_fast(th + j * dth));
+                    k += kstep;
+                    if (k >= W) k -= W;
+                }
+            } else {
+                for (unsigned int j = jlo + t; j < adv; j += T) {
+                    hist[k] = stg[(pos + j) & SZM];
+                    k += kstep;
+                    if (k >= W) k -= W;
                 }
             }
             __syncthreads();
@@ -354,14 +362,13 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync
         if (state != ST_RX) {
             // ---- preamble events.  G[i] = X[i]*ref[i]*gain on the training subcarriers
             const bool long_seq = (state == ST_S1);
-            const int8_t * __restrict__ ref = long_seq ? refS + M : refS;
             const unsigned int step = long_seq ? 1u : 2u;
             const float gain = sqrtf((float)(long_seq ? p.M_S1 : p.M_S0)) / (float)M;
             cf g[8];
 #pragma unroll
             for (unsigned int s = 0; s < 8; s++) {
                 const unsigned int i = t + s * T;
-                const float r = (float)ref[i];
+                const float r = long_seq ? ref_s1[s] : ref_s0[s];
                 g[s] = make_float2(v[s].x * r * gain, v[s].y * r * gain);
                 Gs[i] = g[s];
             }
@@ -534,6 +541,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync
         }
         __syncthreads();
         PH(3);
+        float fit_p0 = 0.f;
         if (wid == 0) {
             for (unsigned int n = lane; n < Mp; n += 32) {
                 const unsigned int q = (ppos + n) % 255u;
@@ -553,25 +561,28 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync
                 const float np = (float)Mp, sx = p.pilot_sx, sxx = p.pilot_sxx;
                 float den = __fsub_rn(__fmul_rn(np, sxx), __fmul_rn(sx, sx));
                 float p1 = __fdiv_rn(__fsub_rn(__fmul_rn(np, sxy), __fmul_rn(sx, sy)), den);
-                float p0 = __fdiv_rn(__fsub_rn(sy, __fmul_rn(p1, sx)), np);
+                fit_p0 = __fdiv_rn(__fsub_rn(sy, __fmul_rn(p1, sx)), np);
                 const float alpha = 0.3f;
                 p1 = __fadd_rn(__fmul_rn(alpha, p1), __fmul_rn(1 - alpha, S->p1_prime));
                 S->p1_prime = p1;
-                red[111] = p0; red[112] = p1;
-                if (S->num_symbols > 0) {
-                    float dphi = p0 - S->phi_prime;
-                    while (dphi > PI_F) dphi -= 2 * PI_F;
-                    while (dphi < -PI_F) dphi += 2 * PI_F;
-                    S->nco_dtheta += nco_constrain_small(1e-3f * dphi);
-                }
-                S->phi_prime = p0;
-                S->num_symbols++;
-                S->pilot_pos = (ppos + Mp) % 255u;
-                S->timer = (int)(M + cp);    // liquid sets this unconditionally (also after a reset below)
+                red[111] = fit_p0; red[112] = p1;
             }
         }
         __syncthreads();
         PH(4);
+        if (t == 0) {
+            // NCO trim and symbol bookkeeping: off the path of the other threads, who only need p0 / p1
+            if (S->num_symbols > 0) {
+                float dphi = fit_p0 - S->phi_prime;
+                while (dphi > PI_F) dphi -= 2 * PI_F;
+                while (dphi < -PI_F) dphi += 2 * PI_F;
+                S->nco_dtheta += nco_constrain_small(1e-3f * dphi);
+            }
+            S->phi_prime = fit_p0;
+            S->num_symbols++;
+            S->pilot_pos = (ppos + Mp) % 255u;
+            S->timer = (int)(M + cp);    // liquid sets this unconditionally (also after a reset below)
+        }
 
         // ---- derotate own subcarriers
         {
