@@ -490,6 +490,9 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
         if (N >= 32 && sync8_supported(M) && K >= 64) {
             unsigned int want = 64;
             if (const char * e = getenv("B2_SYNC_SMS")) { long v = atol(e); if (v >= 8 && v <= 136) want = (unsigned int)v; }
+            // every chain must be resident at once (a chain that waits for an SM stalls the pipeline):
+            // the synchroniser kernel fits 4 CTAs of M/8 <= 64 threads per SM
+            want = std::max(want, std::min(136u, ((N + 3) / 4 + 7) / 8 * 8));
             if (sm_partition_create(q->part, device, want)) {
                 q->stream = q->part.big_stream[0];
                 q->sstream = q->part.small_stream;

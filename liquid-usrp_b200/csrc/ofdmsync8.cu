@@ -129,7 +129,7 @@ extern "C" int b2_debug_sync8_prof(unsigned long long * out, int reset)
 #endif
 
 template <unsigned int M>
-__global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync8_kernel(const SyncParams p)   // <= 168 registers at M = 512: 6 streams per SM
+__global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync8_kernel(const SyncParams p)   // <= 255 registers at M = 512: 4 streams per SM
 {
     constexpr unsigned int T = M / 8, NW = T / 32, M2 = M / 2;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -251,34 +251,43 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync
     };
     auto bsync = [] { __syncthreads(); };
 
+    // per-event registers; `pre` = this event's samples are already consumed, mixed and through the
+    // first FFT pass (done by the previous payload event, see the pipelined tail of the RX path)
+    bool pre = false;
+    int state = 0, timer = 0, fstate = 0;
+    unsigned int head = 0, ppos = 0, hstart = 0, pstart = 0, bps = 0, ms = 0, mod_len = 0, adv = 0, head2 = 0, off = 0;
+    uint32_t th = 0, dth = 0;
+    float en = 0.f;
+    cf v[8];
+
     while (true) {
+      if (!pre) {
         PH(6);
         if (pos + NEED_MAX <= done_frontier) cp_async_wait_group<1>();
         else cp_async_wait_group<0>();
         __syncthreads();                     // staged samples + state of the previous event visible
         PH(0);
         // ---- advance to the next event (or to the end of this launch's samples)
-        const int state = S->state;
-        const int timer = S->timer;
-        const unsigned int head = S->ring_head;
-        const uint32_t th = S->nco_theta, dth = S->nco_dtheta;
-        const unsigned int ppos = S->pilot_pos;
-        const int fstate = S->fstate;
-        const unsigned int hstart = S->header_sym_idx, pstart = S->payload_sym_idx;
-        const unsigned int bps = S->bps_payload, ms = S->ms_payload, mod_len = S->payload_mod_len;
+        state = S->state;
+        timer = S->timer;
+        head = S->ring_head;
+        th = S->nco_theta; dth = S->nco_dtheta;
+        ppos = S->pilot_pos;
+        fstate = S->fstate;
+        hstart = S->header_sym_idx; pstart = S->payload_sym_idx;
+        bps = S->bps_payload; ms = S->ms_payload; mod_len = S->payload_mod_len;
         unsigned int need;
         if (state == ST_SEEK) need = (timer < (int)M) ? (unsigned int)((int)M - timer) : 1u;
         else if (state == ST_S0A || state == ST_S0B) need = (timer < (int)M2) ? (unsigned int)((int)M2 - timer) : 1u;
         else need = (timer > 1) ? (unsigned int)timer : 1u;
         const unsigned int avail = p.nsamples - pos;
-        const unsigned int adv = min(need, avail);
+        adv = min(need, avail);
         const bool fire = (adv == need);
-        const unsigned int off = (state == ST_RX) ? cp - p.backoff : cp;    // FFT window offset in the sample window
+        off = (state == ST_RX) ? cp - p.backoff : cp;                     // FFT window offset in the sample window
         const bool mixing = (state != ST_SEEK) && ((th | dth) != 0u);     // e^{-j0} = 1 exactly
-        unsigned int head2 = head + adv;
+        head2 = head + adv;
         while (head2 >= W) head2 -= W;
 
-        cf v[8];
         if (state == ST_RX && adv == W) {
             // steady state of a frame: the whole window is replaced, so it is rewritten from slot 0
             // (head2 = 0) and the FFT window starts `off` samples in
@@ -335,7 +344,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync
             }
             break;
         }
-        float en = 0.f;
+        en = 0.f;
         if (state == ST_SEEK) {
 #pragma unroll
             for (unsigned int s = 0; s < 8; s++) en += v[s].x * v[s].x + v[s].y * v[s].y;
@@ -347,6 +356,8 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync
         f8_store<M, 1, 8>(v, t, fa);
         __syncthreads();
         PH(1);
+      }
+      pre = false;
         if (t == 0) {
             S->ring_head = head2;
             if (state != ST_SEEK) S->nco_theta = th + adv * dth;
@@ -566,22 +577,94 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 384 : 512) / (M / 8)) sync
                 p1 = __fadd_rn(__fmul_rn(alpha, p1), __fmul_rn(1 - alpha, S->p1_prime));
                 S->p1_prime = p1;
                 red[111] = fit_p0; red[112] = p1;
+                // NCO trim (the next symbol is mixed with it)
+                uint32_t nd = dth;
+                if (S->num_symbols > 0) {
+                    float dphi = fit_p0 - S->phi_prime;
+                    while (dphi > PI_F) dphi -= 2 * PI_F;
+                    while (dphi < -PI_F) dphi += 2 * PI_F;
+                    nd += nco_constrain_small(1e-3f * dphi);
+                }
+                S->nco_dtheta = nd;
+                red[116] = __uint_as_float(nd);
             }
         }
+        // can the next event be started right behind this barrier?  (steady state of a payload: the
+        // frame goes on, a whole symbol is available, no debug tap)  Its samples must have landed.
+        const unsigned int take_now = (fstate == FS_PAYLOAD) ? min(p.M_data, mod_len - pstart) : 0u;
+        const bool pipe = (fstate == FS_PAYLOAD) && (pstart + take_now < mod_len) && (p.nsamples - pos >= W) && (p.tap_cap == 0);
+        if (pipe) cp_async_wait_group<0>();
         __syncthreads();
         PH(4);
         if (t == 0) {
-            // NCO trim and symbol bookkeeping: off the path of the other threads, who only need p0 / p1
-            if (S->num_symbols > 0) {
-                float dphi = fit_p0 - S->phi_prime;
-                while (dphi > PI_F) dphi -= 2 * PI_F;
-                while (dphi < -PI_F) dphi += 2 * PI_F;
-                S->nco_dtheta += nco_constrain_small(1e-3f * dphi);
-            }
+            // symbol bookkeeping: off the path of the other threads, who only need p0 / p1 / the NCO step
             S->phi_prime = fit_p0;
             S->num_symbols++;
             S->pilot_pos = (ppos + Mp) % 255u;
             S->timer = (int)(M + cp);    // liquid sets this unconditionally (also after a reset below)
+        }
+
+        if (pipe) {
+            // ---- pipelined tail: the next symbol's samples are mixed and taken through the first FFT
+            //      pass in the same stretch of code that derotates and demaps this symbol, so the two
+            //      dependency chains interleave and the loop-top barrier + state reload disappear
+            const uint32_t dth2 = __float_as_uint(red[116]);
+            const uint32_t th2 = th + adv * dth;             // phase after this event's samples
+            const unsigned int off2 = cp - p.backoff;
+            cf v2[8];
+#pragma unroll
+            for (unsigned int s = 0; s < 8; s++) {
+                const unsigned int j = off2 + t + s * T;
+                const cf x = mix_down(stg[(pos + j) & SZM], nco_cexp_fast(th2 + j * dth2));
+                v2[s] = x;
+                hist[j] = x;
+            }
+            for (unsigned int jj = t; jj < cp; jj += T) {
+                const unsigned int j = (jj < off2) ? jj : jj + M;
+                hist[j] = mix_down(stg[(pos + j) & SZM], nco_cexp_fast(th2 + j * dth2));
+            }
+            {
+                const float p0 = red[111], p1 = red[112];
+#pragma unroll
+                for (unsigned int s = 0; s < 8; s++) {
+                    float thv = __fadd_rn(p0, __fmul_rn(p1, fxs[s]));
+                    float sn, cs;
+                    __sincosf(thv, &sn, &cs);
+                    v[s] = cmul(v[s], make_float2(cs, -sn));
+                }
+            }
+            f8_pass<M, 1, 8, -1>(v2, t, tw);
+            f8_store<M, 1, 8>(v2, t, fa);
+            {
+                uint8_t * dst = penc + pstart;
+                const float alpha = p.qam_alpha[bps];
+#define B2_DEMAP(EXPR)                                                              \
+                _Pragma("unroll")                                                   \
+                for (unsigned int s = 0; s < 8; s++) {                              \
+                    const unsigned int r = rk[s];                                   \
+                    if (r < take_now) { const cf x = v[s]; dst[r] = (uint8_t)(EXPR); } \
+                }
+                if (ms == 40) { B2_DEMAP((x.x > 0 ? 0u : 1u) + (x.y > 0 ? 0u : 2u)) }
+                else if (ms == 39) { B2_DEMAP(x.x > 0 ? 0u : 1u) }
+                else if (bps == 6) { B2_DEMAP(demod_qam_t<3>(x, alpha)) }
+                else if (bps == 4) { B2_DEMAP(demod_qam_t<2>(x, alpha)) }
+                else if (bps == 8) { B2_DEMAP(demod_qam_t<4>(x, alpha)) }
+                else { B2_DEMAP(demod_qam_t<1>(x, alpha)) }
+#undef B2_DEMAP
+            }
+            if (t == 0) S->payload_sym_idx = pstart + take_now;
+            __syncthreads();                 // first FFT exchange of the next event
+            PH(5);
+            // the next event, as the loop top would have found it
+#pragma unroll
+            for (unsigned int s = 0; s < 8; s++) v[s] = v2[s];
+            pstart += take_now;
+            ppos = (ppos + Mp) % 255u;
+            th = th2; dth = dth2;
+            timer = (int)W; adv = W; head = 0; head2 = 0; off = off2;
+            pos += W;
+            pre = true;
+            continue;
         }
 
         // ---- derotate own subcarriers
