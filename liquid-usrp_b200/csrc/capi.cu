@@ -189,6 +189,8 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     for (unsigned int i = 0; i < fftM.npass; i++) sp.fft.radices |= fftM.radix[i] << (4 * i);
     sp.fft.perm = t_perm.as<uint16_t>(); sp.fft.tw = t_tw.as<cf>();
     sync_smem = sync_smem_bytes(sp);
+    const bool fast_sync = sync8_supported(M) && plan.M_pilot + plan.M_data >= 5 && getenv("B2_SYNC_GENERIC") == nullptr;
+    if (fast_sync) sync_smem = sync8_smem_bytes(sp);          // the kernel sync_launch() will pick
     if (sync_smem > 227 * 1024) return b2_fail(B2_ERR_UNSUPPORTED, "M=%u needs %zu bytes of shared memory per stream", M, sync_smem);
     B2_CUDA(sync_configure(sync_smem));
     sync_threads = (M >= 512) ? 256 : 128;

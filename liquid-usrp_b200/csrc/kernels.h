@@ -123,6 +123,7 @@ void sync_state_init(SyncState & s, unsigned int M, unsigned int cp);
 cudaError_t sync_reset_launch(SyncState * st, unsigned int streams, cudaStream_t stream);
 // register-resident fast path (ofdmsync8.cu), M/8 threads per stream; sync_launch() picks it
 bool sync8_supported(unsigned int M);
+size_t sync8_smem_bytes(const SyncParams & p);
 cudaError_t sync8_launch(const SyncParams & p, cudaStream_t st);
 
 // ------------------------------------------------------------------ packet decode

@@ -894,6 +894,8 @@ static cudaError_t sync8_launch_t(const SyncParams & p, size_t smem_bytes, cudaS
     return cudaGetLastError();
 }
 
+size_t sync8_smem_bytes(const SyncParams & p) { return s8_layout(p.M, p.cp, p.M_pilot + p.M_data, p.M_pilot).total; }
+
 bool sync8_supported(unsigned int M) { return M == 256 || M == 512 || M == 1024 || M == 2048 || M == 4096; }
 
 cudaError_t sync8_launch(const SyncParams & p, cudaStream_t st)

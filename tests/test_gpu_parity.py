@@ -25,6 +25,11 @@ CASES = {
     "golay_outer_h128": (4, 128, 16, 4, MOD_QAM16, FEC_GOLAY2412, FEC_HAMMING128, 97, 2, 0.0),
     "noisy_30dB": (8, 64, 16, 4, MOD_QPSK, FEC_NONE, FEC_HAMMING128, 150, 3, 0.03),
     "noisy_v27": (4, 256, 32, 8, MOD_QAM16, FEC_CONV_V27, FEC_NONE, 200, 2, 0.05),
+    # the register-resident synchroniser's other FFT plans: 4 passes (8,8,8,2 / 8,8,8,4 / 8^4)
+    "m1024_2ch_qam16_h128": (2, 1024, 128, 32, MOD_QAM16, FEC_NONE, FEC_HAMMING128, 900, 2, 0.0),
+    "m2048_1ch_qpsk": (1, 2048, 64, 16, MOD_QPSK, FEC_NONE, FEC_NONE, 700, 2, 0.0),
+    "m4096_1ch_qam64": (1, 4096, 256, 64, MOD_QAM64, FEC_NONE, FEC_NONE, 3000, 2, 0.0),
+    "m256_qam256_golay": (4, 256, 32, 8, MOD_QAM256, FEC_GOLAY2412, FEC_NONE, 500, 3, 0.0),
 }
 
 
