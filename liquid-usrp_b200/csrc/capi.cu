@@ -531,7 +531,7 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
             (!q->sstream && cudaStreamCreateWithFlags(&q->sstream, cudaStreamNonBlocking) != cudaSuccess) ||
             cudaEventCreate(&q->ev_begin) != cudaSuccess || cudaEventCreate(&q->ev_end) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaStreamCreate failed"); break; }
         // chunk of the pipeline: long enough to amortise launches, short enough to overlap stages
-        q->chunk_blocks = std::max(64u, (1u << 24) / K);
+        q->chunk_blocks = std::max(64u, (1u << 25) / K);
         if (const char * e = getenv("B2_CHUNK_BLOCKS")) { long v = atol(e); if (v >= 1) q->chunk_blocks = (unsigned int)v; }
         if ((rc = q->core.init(M, cp, taper, p, N, q->tcap, device, q->sstream, decode_stream))) break;
         B2_CUDA(cudaMemsetAsync(q->d_stage.p, 0, q->d_stage.bytes, q->stream));
@@ -601,8 +601,12 @@ static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device)
     size_t copied = 0;                                       // samples of x already on their way into the stage
     unsigned int nchunks = 0;
     if (T > 0) B2_TRY(q->core.begin_batch());
-    for (size_t b0 = 0; b0 < T; b0 += q->chunk_blocks, nchunks++) {
-        const size_t tc = std::min((size_t)q->chunk_blocks, T - b0);
+    // chunk schedule: short chunks first (the synchronisers start early), then doubling up to chunk_blocks
+    size_t next_tc = std::max<size_t>(64, q->chunk_blocks / 8);
+    for (size_t b0 = 0, tc = 0; b0 < T; b0 += tc, nchunks++) {
+        tc = std::min(next_tc, T - b0);
+        if (T - b0 - tc < next_tc / 4) tc = T - b0;           // no tiny tail chunk
+        next_tc = std::min<size_t>(q->chunk_blocks, next_tc * 2);
         const bool last = b0 + tc == T;
         if (q->aev.size() <= nchunks) {
             b2_mcrx_s::AnEv e;
