@@ -601,12 +601,17 @@ static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device)
     size_t copied = 0;                                       // samples of x already on their way into the stage
     unsigned int nchunks = 0;
     if (T > 0) B2_TRY(q->core.begin_batch());
-    // chunk schedule: short chunks first (the synchronisers start early), then doubling up to chunk_blocks
-    size_t next_tc = std::max<size_t>(64, q->chunk_blocks / 8);
+    // chunk schedule: short chunks first (the synchronisers start early), doubling up to chunk_blocks, and
+    // halving again towards the end (the D2H + host ordering of the last chunk is the tail of the call)
+    const size_t cb = q->chunk_blocks, cmin = std::max<size_t>(64, cb / 8);
+    size_t next_tc = cmin;
     for (size_t b0 = 0, tc = 0; b0 < T; b0 += tc, nchunks++) {
-        tc = std::min(next_tc, T - b0);
-        if (T - b0 - tc < next_tc / 4) tc = T - b0;           // no tiny tail chunk
-        next_tc = std::min<size_t>(q->chunk_blocks, next_tc * 2);
+        const size_t left = T - b0;
+        tc = next_tc;
+        while (tc > cmin && left < 2 * tc - cmin) tc /= 2;   // ramp down: ... cb/2, cb/4, cb/8 fit in what is left
+        tc = std::min(tc, left);
+        if (left - tc < cmin / 2) tc = left;                  // no tiny tail chunk
+        next_tc = std::min(cb, next_tc * 2);
         const bool last = b0 + tc == T;
         if (q->aev.size() <= nchunks) {
             b2_mcrx_s::AnEv e;
