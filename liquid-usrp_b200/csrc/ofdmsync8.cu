@@ -42,6 +42,8 @@ __host__ __device__ static inline S8Layout s8_layout(unsigned int M, unsigned in
     const unsigned int W = M + cp;
     L.SZ = 256;
     while (L.SZ < W + M / 2 + 64) L.SZ <<= 1;
+    // two events deep where it is cheap (<= 32 KB): the newest prefetch group may then stay in flight
+    if (L.SZ < 2 * W + M / 2 + 64 && L.SZ * 2 * sizeof(cf) <= 32768) L.SZ <<= 1;
     size_t o = 0;
     L.off_st = o;   o += (sizeof(SyncState) + 15) & ~(size_t)15;
     L.off_red = o;  o += 160 * sizeof(float);
@@ -162,23 +164,29 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
     uint8_t * penc = p.penc + (size_t)sidx * p.penc_cap;
     const bool al16 = (((size_t)in) & 15) == 0;
 
-    // ---- sample prefetch: ring slot = stream position & SZM
+    // ---- sample prefetch: ring slot = stream position & SZM.  Issued by the LAST warp only, at the
+    //      points of an event where that warp would otherwise wait for warp 0 (pilot fit, metric maths);
+    //      every thread tracks the frontiers, the issuing warp owns the cp.async groups.
     unsigned int fetched = 0, done_frontier = 0;
+    const bool pf_warp = (wid == NW - 1);
+    const unsigned int tp = lane;
     auto prefetch = [&](unsigned int upto) {
         unsigned int hi = upto;
         if (al16 && hi < p.nsamples) hi &= ~1u;
         done_frontier = fetched;
         if (hi > fetched) {
-            if (al16) {
-                const unsigned int even_hi = hi & ~1u;
-                for (unsigned int i = fetched + 2 * t; i < even_hi; i += 2 * T) cp_async16(&stg[i & SZM], in + i);
-                if ((hi & 1u) && t == 0) cp_async8(&stg[(hi - 1) & SZM], in + hi - 1);
-            } else {
-                for (unsigned int i = fetched + t; i < hi; i += T) cp_async8(&stg[i & SZM], in + i);
+            if (pf_warp) {
+                if (al16) {
+                    const unsigned int even_hi = hi & ~1u;
+                    for (unsigned int i = fetched + 2 * tp; i < even_hi; i += 64) cp_async16(&stg[i & SZM], in + i);
+                    if ((hi & 1u) && tp == 0) cp_async8(&stg[(hi - 1) & SZM], in + hi - 1);
+                } else {
+                    for (unsigned int i = fetched + tp; i < hi; i += 32) cp_async8(&stg[i & SZM], in + i);
+                }
             }
             fetched = hi;
         }
-        cp_async_commit();
+        if (pf_warp) cp_async_commit();
     };
     prefetch(min(PF, p.nsamples));
 
@@ -365,12 +373,12 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
             if (state == ST_SEEK || state == ST_S0A || state == ST_S0B) S->timer = timer + (int)adv;
             else S->timer = timer - (int)adv;
         }
-        prefetch(min(pos + PF, p.nsamples));
         f8_load<M>(v, t, fa);
         f8_run<M, 8, -1>(v, t, fb, fa, tw, bsync, twr);
         PH(2);
 
         if (state != ST_RX) {
+            prefetch(min(pos + PF, p.nsamples));
             // ---- preamble events.  G[i] = X[i]*ref[i]*gain on the training subcarriers
             const bool long_seq = (state == ST_S1);
             const unsigned int step = long_seq ? 1u : 2u;
@@ -552,6 +560,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         }
         __syncthreads();
         PH(3);
+        prefetch(min(pos + PF, p.nsamples));     // last warp, while warp 0 fits the pilots
         float fit_p0 = 0.f;
         if (wid == 0) {
             for (unsigned int n = lane; n < Mp; n += 32) {
@@ -593,7 +602,10 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         // frame goes on, a whole symbol is available, no debug tap)  Its samples must have landed.
         const unsigned int take_now = (fstate == FS_PAYLOAD) ? min(p.M_data, mod_len - pstart) : 0u;
         const bool pipe = (fstate == FS_PAYLOAD) && (pstart + take_now < mod_len) && (p.nsamples - pos >= W) && (p.tap_cap == 0);
-        if (pipe) cp_async_wait_group<0>();
+        if (pipe) {
+            if (pos + W <= done_frontier) cp_async_wait_group<1>();
+            else cp_async_wait_group<0>();
+        }
         __syncthreads();
         PH(4);
         if (t == 0) {
