@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
     cf twr[f8_tw_count(M, 8) + 1];           // this thread's twiddles of the passes after the first
     f8_tw_init<M, 8>(twr, t, p.fft.tw);
     const cf * tw = nullptr;                 // no table at run time
+    const float px0 = lane < Mp ? p.tb.pilot_x[lane] : 0.f, px1 = lane + 32 < Mp ? p.tb.pilot_x[lane + 32] : 0.f;
     float fxs[8];                            // signed subcarrier index of own subcarriers
     unsigned int pilot_mask = 0;
 #pragma unroll
@@ -563,15 +564,53 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         prefetch(min(pos + PF, p.nsamples));     // last warp, while warp 0 fits the pilots
         float fit_p0 = 0.f;
         if (wid == 0) {
-            for (unsigned int n = lane; n < Mp; n += 32) {
-                const unsigned int q = (ppos + n) % 255u;
-                const float pil = pilot_seq[q] ? 1.0f : -1.0f;
-                const cf c = yc[n];
-                yph[n] = atan2_fast(c.y * pil, c.x * pil);
-            }
-            __syncwarp();
             float sy, sxy;
-            warp_unwrap(yph, pilot_x, Mp, false, lane, sy, sxy);
+            if (Mp <= 64) {
+                // at most two pilots per lane (n = lane, lane + 32): phases, unwrap and sums stay in registers
+                const bool v0 = lane < Mp, v1 = lane + 32 < Mp;
+                float raw0 = 0.f, raw1 = 0.f;
+                if (v0) {
+                    const float pil = pilot_seq[(ppos + lane) % 255u] ? 1.0f : -1.0f;
+                    const cf c = yc[lane];
+                    raw0 = atan2_fast(c.y * pil, c.x * pil);
+                }
+                if (v1) {
+                    const float pil = pilot_seq[(ppos + lane + 32) % 255u] ? 1.0f : -1.0f;
+                    const cf c = yc[lane + 32];
+                    raw1 = atan2_fast(c.y * pil, c.x * pil);
+                }
+                float prev0 = __shfl_up_sync(0xffffffffu, raw0, 1);
+                float prev1 = __shfl_up_sync(0xffffffffu, raw1, 1);
+                const float last0 = __shfl_sync(0xffffffffu, raw0, 31);
+                if (lane == 0) prev1 = last0;
+                int k0 = 0, k1 = 0;
+                if (v0 && lane > 0) { const float d = raw0 - prev0; k0 = (d > PI_F) ? -1 : ((d < -PI_F) ? 1 : 0); }
+                if (v1) { const float d = raw1 - prev1; k1 = (d > PI_F) ? -1 : ((d < -PI_F) ? 1 : 0); }
+                if (__any_sync(0xffffffffu, (k0 | k1) != 0)) {        // rare: most symbols need no unwrapping
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int a = __shfl_up_sync(0xffffffffu, k0, o), b = __shfl_up_sync(0xffffffffu, k1, o);
+                        if (lane >= (unsigned int)o) { k0 += a; k1 += b; }
+                    }
+                    k1 += __shfl_sync(0xffffffffu, k0, 31);
+                }
+                float yy0 = raw0, yy1 = raw1;
+                for (int q = k0; q > 0; q--) yy0 += 2 * PI_F;
+                for (int q = k0; q < 0; q++) yy0 -= 2 * PI_F;
+                for (int q = k1; q > 0; q--) yy1 += 2 * PI_F;
+                for (int q = k1; q < 0; q++) yy1 -= 2 * PI_F;
+                sy = (v0 ? yy0 : 0.f) + (v1 ? yy1 : 0.f);
+                sxy = (v0 ? px0 * yy0 : 0.f) + (v1 ? px1 * yy1 : 0.f);
+            } else {
+                for (unsigned int n = lane; n < Mp; n += 32) {
+                    const unsigned int q = (ppos + n) % 255u;
+                    const float pil = pilot_seq[q] ? 1.0f : -1.0f;
+                    const cf c = yc[n];
+                    yph[n] = atan2_fast(c.y * pil, c.x * pil);
+                }
+                __syncwarp();
+                warp_unwrap(yph, pilot_x, Mp, false, lane, sy, sxy);
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 sy += __shfl_xor_sync(0xffffffffu, sy, o);
