@@ -217,6 +217,25 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
     cf twr[f8_tw_count(M, 8) + 1];           // this thread's twiddles of the passes after the first
     f8_tw_init<M, 8>(twr, t, p.fft.tw);
     const cf * tw = nullptr;                 // no table at run time
+    unsigned int ar[8];                      // rank of own subcarriers among the active ones (fft-shifted order)
+    cf Bq[8];                                // B[i] = e^{j 2 pi backoff i / M}: timing back-off of the S1 gain estimate
+    {
+        const float bphi = 2.0f * (float)p.backoff / (float)M;
+#pragma unroll
+        for (unsigned int s = 0; s < 8; s++) {
+            const unsigned int i = t + s * T;
+            ar[s] = p.tb.act_rank[i];
+            float sn, cs;
+            sincospif(bphi * (float)i, &sn, &cs);
+            Bq[s] = make_float2(cs, sn);
+        }
+    }
+    // header de-interleaver walks (n = 36): lane l < 18 swaps bytes 2l <-> 2 walk[v][l] + 1 in pass v
+    unsigned int hwalk[4] = {0, 0, 0, 0};
+    if (lane < 18) {
+#pragma unroll
+        for (int vq = 0; vq < 4; vq++) hwalk[vq] = p.tb.hdr_walk[18 * vq + lane];
+    }
     const float px0 = lane < Mp ? p.tb.pilot_x[lane] : 0.f, px1 = lane + 32 < Mp ? p.tb.pilot_x[lane + 32] : 0.f;
     float fxs[8];                            // signed subcarrier index of own subcarriers
     unsigned int pilot_mask = 0;
@@ -466,18 +485,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                     // thread works on its own 8 subcarriers, only the phase unwrap (sequential in the
                     // fft-shifted visiting order) goes through shared memory.
                     const float gsc = (float)M / sqrtf((float)Na);
-                    const float bphi = 2.0f * (float)p.backoff / (float)M;     // B[i] = e^{j pi bphi i}
-                    unsigned int ar[8];
                     float ya[8];
-                    cf Bq[8];
-#pragma unroll
-                    for (unsigned int s = 0; s < 8; s++) {
-                        const unsigned int i = t + s * T;
-                        ar[s] = p.tb.act_rank[i];
-                        float sn, cs;
-                        sincospif(bphi * (float)i, &sn, &cs);
-                        Bq[s] = make_float2(cs, sn);
-                    }
                     double pv[8][5];                 // own rows of the fit matrix, fetched while the phases unwrap
 #pragma unroll
                     for (unsigned int s = 0; s < 8; s++) {
@@ -494,8 +502,15 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                     }
                     __syncthreads();
                     PH(12);
-                    if (wid == 0) warp_unwrap_seg(yph, Na, lane);
-                    __syncthreads();
+                    {
+                        // unwrap only if some neighbouring pair is more than pi apart (smooth channels: never)
+                        int wraps = 0;
+                        for (unsigned int n = t + 1; n < Na; n += T) wraps |= fabsf(yph[n] - yph[n - 1]) > PI_F;
+                        if (__syncthreads_or(wraps)) {
+                            if (wid == 0) warp_unwrap_seg(yph, Na, lane);
+                            __syncthreads();
+                        }
+                    }
                     PH(13);
                     double ca[10];
 #pragma unroll
@@ -806,9 +821,10 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                     for (unsigned int i = lane; i < 36; i += 32) hb[i] = S->header_bits[i] ^ mask[i & 3];
                     __syncwarp();
                     const uint8_t ilmask[4] = {0xff, 0x0f, 0x55, 0x33};
+#pragma unroll
                     for (int vq = 3; vq >= 0; vq--) {
                         if (lane < 18) {
-                            unsigned int j = p.tb.hdr_walk[18 * vq + lane];
+                            unsigned int j = hwalk[vq];
                             uint8_t mk = ilmask[vq];
                             uint8_t a = hb[2 * lane], b = hb[2 * j + 1];
                             hb[2 * lane] = (uint8_t)((a & ~mk) | (b & mk));
@@ -866,11 +882,10 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                 unsigned long long offb = 0;
                 unsigned int e2 = (emit == 2) ? S->payload_enc_len : 0u;
                 unsigned int m2 = (emit == 2) ? S->payload_mod_len : 0u;      // symbols, one byte each
+                // (both reservations are issued back to back; an overflowing frame is flagged, not stored)
+                if (m2) offb = atomicAdd((unsigned long long *)(p.counters + 2), (unsigned long long)((m2 + 15u) & ~15u));
                 int ok = slot < p.recs_cap;
-                if (ok && m2) {
-                    offb = atomicAdd((unsigned long long *)(p.counters + 2), (unsigned long long)((m2 + 15u) & ~15u));
-                    if (offb + ((m2 + 15u) & ~15u) > p.arena_cap) ok = 0;
-                }
+                if (m2 && offb + ((m2 + 15u) & ~15u) > p.arena_cap) ok = 0;
                 if (!ok) { atomicExch(&p.counters[1], 1u); red[115] = -1.f; }
                 else {
                     FrameRec r;

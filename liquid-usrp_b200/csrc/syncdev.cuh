@@ -182,10 +182,12 @@ __device__ __forceinline__ void solve5(const double * __restrict__ S, const doub
 }
 
 // CRC-32 with a 16-entry nibble table (frame header: 14 bytes)
+static __constant__ uint32_t b2_crc_nibble_table[16] = {
+    0x00000000u, 0x1DB71064u, 0x3B6E20C8u, 0x26D930ACu, 0x76DC4190u, 0x6B6B51F4u, 0x4DB26158u, 0x5005713Cu,
+    0xEDB88320u, 0xF00F9344u, 0xD6D6A3E8u, 0xCB61B38Cu, 0x9B64C2B0u, 0x86D3D2D4u, 0xA00AE278u, 0xBDBDF21Cu};
 __device__ __forceinline__ uint32_t crc32_nibble(const uint8_t * m, unsigned int n)
 {
-    const uint32_t T[16] = {0x00000000u, 0x1DB71064u, 0x3B6E20C8u, 0x26D930ACu, 0x76DC4190u, 0x6B6B51F4u, 0x4DB26158u, 0x5005713Cu,
-                            0xEDB88320u, 0xF00F9344u, 0xD6D6A3E8u, 0xCB61B38Cu, 0x9B64C2B0u, 0x86D3D2D4u, 0xA00AE278u, 0xBDBDF21Cu};
+    const uint32_t * T = b2_crc_nibble_table;
     uint32_t key = ~0u;
     for (unsigned int i = 0; i < n; i++) {
         key ^= m[i];
