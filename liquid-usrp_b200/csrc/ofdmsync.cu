@@ -677,6 +677,7 @@ __global__ void sync_reset_kernel(SyncState * st, unsigned int streams)
     S->s_hat0_re = 0.f; S->s_hat0_im = 0.f;
     S->phi_prime = 0.f; S->p1_prime = 0.f;
     S->state = ST_SEEK;
+    for (int k = 0; k < 36; k++) S->header_bits[k] = 0;      // ofdmsync8.cu ORs the header bits in
 }
 cudaError_t sync_reset_launch(SyncState * st, unsigned int streams, cudaStream_t stream)
 {

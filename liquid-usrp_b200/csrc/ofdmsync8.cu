@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         S->state = ST_SEEK;
     };
     auto flex_reset = [&]() {                // ofdmflexframesync_reset
+        for (int i = 0; i < 9; i++) ((uint32_t *)S->header_bits)[i] = 0u;
         S->fstate = FS_HEADER;
         S->header_sym_idx = 0;
         S->payload_sym_idx = 0;
@@ -784,14 +785,18 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
             // header: BPSK, 288 symbols; EVM is measured on them (framesyncstats_s.evm)
             const unsigned int take = min(p.M_data, 288u - hstart);
             float ev = 0.f;
+            // hard bits go straight into the 288-bit header word array (MSB first inside every byte; the
+            // array is cleared when a frame starts), one shared-memory atomicOr per 1-bit
+            uint32_t * hwords = (uint32_t *)S->header_bits;
 #pragma unroll
             for (unsigned int s = 0; s < 8; s++) {
                 const unsigned int r = rk[s];
                 if (r < take) {
                     const cf x = v[s];
-                    unsigned int b = x.x > 0 ? 0u : 1u;
-                    sym[r] = (uint8_t)b;
-                    float dr = x.x - (b ? -1.0f : 1.0f);
+                    const unsigned int b = x.x > 0 ? 0u : 1u;
+                    const unsigned int gb = hstart + r;
+                    if (b) atomicOr(&hwords[gb >> 5], 1u << (8u * ((gb >> 3) & 3u) + 7u - (gb & 7u)));
+                    const float dr = x.x - (b ? -1.0f : 1.0f);
                     ev += dr * dr + x.y * x.y;
                 }
             }
@@ -799,16 +804,6 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                 float z0 = 0.f, z1 = 0.f, z2 = 0.f;
                 block_sum4(ev, z0, z1, z2);
                 if (NW == 1) __syncthreads();
-            }
-            const unsigned int j0 = hstart >> 3, j1 = (hstart + take - 1) >> 3;
-            for (unsigned int j = j0 + t; j <= j1; j += T) {
-                unsigned int vv = 0;
-                for (unsigned int b = 0; b < 8; b++) {
-                    unsigned int bit = 8 * j + b;
-                    if (bit >= hstart && bit < hstart + take) vv |= (unsigned int)sym[bit - hstart] << (7 - b);
-                }
-                if (8 * j < hstart) vv |= S->header_bits[j];
-                S->header_bits[j] = (uint8_t)vv;
             }
             if (t == 0) { S->evm_hat += ev; S->header_sym_idx = hstart + take; }
             if (hstart + take == 288u) {
@@ -875,8 +870,8 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         }
 
         if (emit) {
-            __syncthreads();
-            // append a frame record (+ encoded payload) to the output of this launch
+            // append a frame record (+ the payload symbols) to the output of this launch; thread 0 reserves
+            // the slots, one barrier publishes them together with every thread's symbol stores
             if (t == 0) {
                 unsigned int slot = atomicAdd(&p.counters[0], 1u);
                 unsigned long long offb = 0;
@@ -920,8 +915,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                 const uint4 * src = (const uint4 *)penc;
                 for (unsigned int i = t; i < (m2 + 15) / 16; i += T) dst[i] = src[i];
             }
-            __syncthreads();
-            if (t == 0) {
+            if (t == 0) {                    // the loop-top barrier orders this against everybody's next reads
                 flex_reset();
                 S->timer = (int)(M + cp);    // survives the reset, as in liquid
             }
