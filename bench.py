@@ -47,10 +47,11 @@ WORKLOAD = dict(name="multichannelrx N=256 M=512 cp=64 taper=16 qam64 fec=none p
                 N=256, M=512, cp=64, taper=16, payload=1200)
 B_ALG_PATH = 16.10          # 8 B in + 4 B channelizer out + 4 B sync in + 0.10 B payload, per wideband sample
 B_ALG = {"analyzer_kernel": 12.0, "sync_kernel": 4.10, "packet_decode_kernel": 0.20}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures summarised under
-# profiles/ (bytes for one launch of the profiled size; null where no capture exists)
-# (profiles/r01_analyzer8_pipelined.txt, r01_sync8_pipelined.txt, r01_decode_pipelined.txt: launches of one 2^24-sample chunk)
-TRAFFIC = {"analyzer_kernel": 179.7e6, "sync_kernel": 72.9e6, "packet_decode_kernel": 2.6e6}
+# DRAM traffic measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one --set full capture per kernel,
+# profiles/r01_{analyzer8,sync8,decode}_pipelined.txt: a 4,194,304-sample chunk of this workload), as bytes per wideband
+# sample; bench reports it per launch of the average chunk of the step, like `achieved`
+TRAFFIC_PER_SAMPLE = {"analyzer_kernel": (33.670912e6 + 0.328448e6) / 4194304, "sync_kernel": 20.314368e6 / 4194304,
+                      "packet_decode_kernel": 0.454144e6 / 4194304}
 
 
 def peaks():
@@ -381,7 +382,7 @@ def main():
     def roof(i):
         ach = n_step * B_ALG[names[i]] / (kt_avg[i] * 1e-3) / 1e9
         return {"alg_bytes_per_sample": B_ALG[names[i]], "launches_per_step": nchunks, "avg_launch_ms": kt_avg[i] / nchunks,
-                "achieved": ach, "frac": ach / peak, "traffic": TRAFFIC.get(names[i])}
+                "achieved": ach, "frac": ach / peak, "traffic": TRAFFIC_PER_SAMPLE[names[i]] * n_step / nchunks}
     per_kernel = {names[i]: roof(i) for i in range(3)}
     achieved = per_kernel[names[dom]]["achieved"]
     line = {"metric": METRIC, "value": total / dt / 1e6, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -398,7 +399,7 @@ def main():
                                     "note": "stages of successive chunks overlap on separate streams / SM partitions; the three sums can exceed the call"},
             "host_ms_per_step": {"execute_call": 1e3 * t_exec / args.steps, "poll_call": 1e3 * t_poll / args.steps},
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": TRAFFIC.get(names[dom]), "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": per_kernel[names[dom]]["traffic"], "peak_source": peak_src,
                          "alg_bytes_per_sample": B_ALG[names[dom]],
                          "note": "the dominant kernel is the per-channel synchroniser, 256 serial chains bound by event latency, not by HBM (DESIGN.md)",
                          "kernels": per_kernel,
