@@ -12,6 +12,7 @@
 //                 codeword pair), convolutional r1/2 K=7 (hard-decision Viterbi, one warp per
 //                 frame: lane L owns states 2L, 2L+1; decisions ballot-packed, 64 bit per step).
 //   CRC-32      : 32 lanes x bytewise CRC of a slice, slices merged with x^(8n) mod P products.
+#include <mutex>
 #include "kernels.h"
 #include "fec.cuh"
 
@@ -284,7 +285,8 @@ __device__ uint32_t crc32_warp(const uint8_t * m, unsigned int n, unsigned int l
 }
 
 // ------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketParams p, uint2 * vit_ws, size_t vit_ws_stride)
+__global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketParams p, uint2 * vit_ws, size_t vit_ws_stride,
+                                                                      int * vit_locks, unsigned int vit_slots)
 {
     __shared__ unsigned int scratch[PK_THREADS / 32];
     __shared__ uint2 stage[PK_TB_STEPS];
@@ -304,7 +306,21 @@ __global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketP
         uint8_t * A = p.arena + off;
         uint8_t * Bf = p.scratch + off;
         uint8_t * D = p.decoded + off;
-        uint2 * ws = vit_ws + (size_t)blockIdx.x * vit_ws_stride;
+        // The Viterbi decision workspace is shared by every handle of the device (kernels of different
+        // handles may run concurrently): a CTA that needs it claims a free slot and releases it after
+        // the frame.  Frames without a convolutional stage never touch it.
+        __shared__ unsigned int s_slot;
+        uint2 * ws = nullptr;
+        const bool need_ws = (fec0 == 11 || fec1 == 11);
+        if (need_ws) {
+            if (tid == 0) {
+                unsigned int sl = blockIdx.x % vit_slots;
+                while (atomicCAS(&vit_locks[sl], 0, 1) != 0) sl = (sl + 1) % vit_slots;
+                s_slot = sl;
+            }
+            __syncthreads();
+            ws = vit_ws + (size_t)s_slot * vit_ws_stride;
+        }
         int ok = 1;
         const unsigned int sym_bps = p.aux[ri].sym_bps;
         if (sym_bps) {
@@ -351,7 +367,10 @@ __global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketP
             if (tid == 0) s_valid = valid;
         }
         __syncthreads();
-        if (tid == 0) rec->payload_valid = s_valid;
+        if (tid == 0) {
+            rec->payload_valid = s_valid;
+            if (need_ws) { __threadfence(); atomicExch(&vit_locks[s_slot], 0); }
+        }
         __syncthreads();
     }
 }
@@ -596,26 +615,35 @@ cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_o
     return cudaGetLastError();
 }
 
-static uint2 * g_vit_ws[16] = {nullptr};
-static size_t g_vit_ws_stride[16] = {0};
-static int g_vit_ws_grid[16] = {0};
+struct VitWorkspace { uint2 * ws = nullptr; int * locks = nullptr; size_t stride = 0; unsigned int slots = 0; };
+static VitWorkspace g_vit[16];
+static std::mutex g_vit_mutex;
 
 cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t st)
 {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 16) dev = 0;
-    // Viterbi decision workspace: 8 bytes per trellis step per CTA, sized for the largest packet
-    const size_t steps = 8ull * (65535 + 4 + 2) * 2 + 64;       // also covers v27 as outer code over an inner code
-    if (!g_vit_ws[dev] || g_vit_ws_grid[dev] < grid) {
-        if (g_vit_ws[dev]) cudaFree(g_vit_ws[dev]);
-        cudaError_t e = cudaMalloc(&g_vit_ws[dev], (size_t)grid * steps * sizeof(uint2));
-        if (e != cudaSuccess) { g_vit_ws[dev] = nullptr; return e; }
-        g_vit_ws_stride[dev] = steps;
-        g_vit_ws_grid[dev] = grid;
+    VitWorkspace w;
+    {
+        std::lock_guard<std::mutex> guard(g_vit_mutex);
+        VitWorkspace & g = g_vit[dev];
+        if (!g.ws) {
+            // Viterbi decision workspace: 8 bytes per trellis step per slot, sized for the largest packet
+            // (also covers v27 as outer code over an inner code); allocated once per device, never moved
+            const size_t steps = 8ull * (65535 + 4 + 2) * 2 + 64;
+            const unsigned int slots = 128;
+            cudaError_t e = cudaMalloc(&g.ws, (size_t)slots * steps * sizeof(uint2));
+            if (e != cudaSuccess) { g.ws = nullptr; return e; }
+            e = cudaMalloc(&g.locks, slots * sizeof(int));
+            if (e == cudaSuccess) e = cudaMemset(g.locks, 0, slots * sizeof(int));
+            if (e != cudaSuccess) { cudaFree(g.ws); g.ws = nullptr; return e; }
+            g.stride = steps; g.slots = slots;
+        }
+        w = g;
     }
     packet_plain_kernel<<<grid, PKF_WARPS * 32, 0, st>>>(p);
-    packet_decode_kernel<<<grid, PK_THREADS, 0, st>>>(p, g_vit_ws[dev], g_vit_ws_stride[dev]);
+    packet_decode_kernel<<<grid, PK_THREADS, 0, st>>>(p, w.ws, w.stride, w.locks, w.slots);
     return cudaGetLastError();
 }
 
