@@ -332,6 +332,18 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                 hist[j] = mix_down(stg[(pos + j) & SZM], nco_cexp_fast(th + j * dth));
             }
             head2 = 0;
+        } else if (state == ST_SEEK && adv == M) {
+            // idle seek: the M new samples ARE the FFT window (no NCO while seeking); push and gather at once
+            unsigned int k = head + t;
+            while (k >= W) k -= W;
+#pragma unroll
+            for (unsigned int s = 0; s < 8; s++) {
+                const cf x = stg[(pos + t + s * T) & SZM];
+                v[s] = x;
+                hist[k] = x;
+                k += T;
+                if (k >= W) k -= W;
+            }
         } else {
             // only the last W of the new samples can survive in the window
             const unsigned int jlo = adv > W ? adv - W : 0u;
@@ -436,10 +448,10 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                 if (t == 0) {
                     float gg = (float)M / cr;
                     cf s_hat = make_float2(mr / (float)p.M_S0 * gg, mi / (float)p.M_S0 * gg);
-                    float tau_hat = atan2f(s_hat.y, s_hat.x) * (float)M2 / (2 * PI_F);
                     S->g0 = gg;
                     S->timer = 0;
                     if (hypotf(s_hat.x, s_hat.y) > p.thresh) {
+                        float tau_hat = atan2f(s_hat.y, s_hat.x) * (float)M2 / (2 * PI_F);
                         int dt = (int)roundf(tau_hat);
                         S->timer = (int)((M + (unsigned int)dt) % M2) + (int)M;
                         S->state = ST_S0A;
