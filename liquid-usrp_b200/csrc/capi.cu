@@ -89,6 +89,8 @@ struct SyncCore {
     // `after`: event on another stream that must complete before the synchroniser may read `in`
     int launch_chunk(const cf * in, size_t in_stride, unsigned int nsamples, cudaEvent_t after);
     int end_batch();
+    void fetch_timing();
+    bool timing_stale = false;
     int collect();
     int poll(b2_frame_rec * recs, size_t recs_cap, size_t * n_recs, uint8_t * payloads, size_t payloads_cap, size_t * n_payload_bytes);
     int poll_view(const b2_frame_rec ** recs, size_t * n_recs, const uint8_t ** payloads, size_t * n_payload_bytes);
@@ -376,24 +378,33 @@ int SyncCore::end_batch()
 
     last_used = std::min(h_range[chunk].arena_used, arena_cap);
     rc = collect();
-    last_ms[1] = 0.f; last_ms[2] = 0.f;
-    if (timing) {
-        for (unsigned int i = 0; i < chunk; i++) {
-            float a = 0.f, b = 0.f;
-            cudaEventElapsedTime(&a, cev[i].s0, cev[i].s1);
-            cudaEventElapsedTime(&b, cev[i].d0, cev[i].d1);
-            last_ms[1] += a; last_ms[2] += b;
-        }
-    }
+    timing_stale = true;                     // the per-kernel sums are computed when somebody asks (fetch_timing)
     return rc;
+}
+
+// per-kernel device times of the last batch, from the chunk events (valid until the next batch)
+void SyncCore::fetch_timing()
+{
+    if (!timing_stale) return;
+    timing_stale = false;
+    last_ms[1] = 0.f; last_ms[2] = 0.f;
+    if (!timing) return;
+    for (unsigned int i = 0; i < chunk; i++) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, cev[i].s0, cev[i].s1);
+        cudaEventElapsedTime(&b, cev[i].d0, cev[i].d1);
+        last_ms[1] += a; last_ms[2] += b;
+    }
 }
 
 // end of a batch: overflow flag and the debug tap
 int SyncCore::collect()
 {
+    // the overflow flag came back with the last chunk's mark; only the debug tap needs another trip
+    if (h_range[chunk].pad) return b2_fail(B2_ERR_OVERFLOW, "internal: frame output arena overflow");
+    if (!tap_cap) return B2_OK;
     B2_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     B2_CUDA(cudaStreamSynchronize(stream));
-    if (h_counters[1]) return b2_fail(B2_ERR_OVERFLOW, "internal: frame output arena overflow");
     const unsigned int ntap = std::min(h_counters[4], tap_cap);
     if (ntap) {
         size_t o = tap_chan.size();
@@ -456,8 +467,21 @@ struct b2_mcrx_s {
     struct AnEv { cudaEvent_t copied, a0, a1; };
     std::vector<AnEv> aev;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    unsigned int timed_chunks = 0;       // chunks of the last call whose events await mcrx_fetch_timing()
     SyncCore core;
 };
+
+// device times of the last call, computed from the events when somebody asks for them
+static void mcrx_fetch_timing(b2_mcrx_s * q)
+{
+    q->core.fetch_timing();
+    if (!q->timed_chunks) return;
+    q->core.last_ms[0] = 0.f;
+    if (q->core.timing)
+        for (unsigned int i = 0; i < q->timed_chunks; i++) { float a = 0.f; cudaEventElapsedTime(&a, q->aev[i].a0, q->aev[i].a1); q->core.last_ms[0] += a; }
+    cudaEventElapsedTime(&q->core.last_ms[3], q->ev_begin, q->ev_end);
+    q->timed_chunks = 0;
+}
 
 static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device);
 
@@ -603,7 +627,8 @@ static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device)
     if (T > 0) B2_TRY(q->core.begin_batch());
     // chunk schedule: short chunks first (the synchronisers start early), doubling up to chunk_blocks, and
     // halving again towards the end (the D2H + host ordering of the last chunk is the tail of the call)
-    const size_t cb = q->chunk_blocks, cmin = std::max<size_t>(64, cb / 8);
+    size_t cb = q->chunk_blocks, cmin = std::max<size_t>(64, cb / 8);
+    if (const char * e = getenv("B2_CHUNK_MIN_BLOCKS")) { long v = atol(e); if (v >= 1) cmin = std::min<size_t>(cb, (size_t)v); }
     size_t next_tc = cmin;
     for (size_t b0 = 0, tc = 0; b0 < T; b0 += tc, nchunks++) {
         const size_t left = T - b0;
@@ -675,10 +700,8 @@ static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device)
     B2_CUDA(cudaEventRecord(q->ev_end, q->stream));
     B2_CUDA(cudaEventSynchronize(q->ev_end));
     if (T > 0) {
-        q->core.last_ms[0] = 0.f;
-        if (q->core.timing)
-            for (unsigned int i = 0; i < nchunks; i++) { float a = 0.f; cudaEventElapsedTime(&a, q->aev[i].a0, q->aev[i].a1); q->core.last_ms[0] += a; }
-        cudaEventElapsedTime(&q->core.last_ms[3], q->ev_begin, q->ev_end);
+        q->timed_chunks = nchunks;
+        if (getenv("B2_DUMP_TIMELINE")) { mcrx_fetch_timing(q); }
         if (q->core.timing && getenv("B2_DUMP_TIMELINE")) {
             // per chunk: begin/end of the channelizer, synchroniser and decode kernels, ms since the call began
             for (unsigned int i = 0; i < nchunks; i++) {
@@ -756,6 +779,8 @@ extern "C" int b2_mcrx_read_symbols(b2_mcrx * q, uint32_t * channel, uint64_t * 
 extern "C" int b2_mcrx_last_timing(b2_mcrx * q, float ms[4])
 {
     if (!q || !ms) return b2_fail(B2_ERR_ARG, "null argument");
+    cudaSetDevice(q->device);
+    mcrx_fetch_timing(q);
     for (int i = 0; i < 4; i++) ms[i] = q->core.last_ms[i];
     return B2_OK;
 }
@@ -934,6 +959,8 @@ extern "C" int b2_ofdmsync_poll_view(b2_ofdmsync * q, const b2_frame_rec ** recs
 extern "C" int b2_ofdmsync_last_timing(b2_ofdmsync * q, float ms[4])
 {
     if (!q || !ms) return b2_fail(B2_ERR_ARG, "null argument");
+    cudaSetDevice(q->device);
+    q->core.fetch_timing();
     for (int i = 0; i < 4; i++) ms[i] = q->core.last_ms[i];
     return B2_OK;
 }

@@ -130,7 +130,7 @@ cudaError_t sync8_launch(const SyncParams & p, cudaStream_t st);
 // de-interleave + FEC decode + CRC of every completed frame (liquid packetizer_decode, called
 // from inside ofdmflexframesync_execute in the reference)
 struct RangeMark {               // output counters after a chunk's synchroniser
-    unsigned int nrec, pad;
+    unsigned int nrec, pad;      // pad carries the overflow flag (counters[1])
     unsigned long long arena_used;
 };
 struct PacketParams {

@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(PKF_WARPS * 32) packet_plain_kernel(const Pack
 __global__ void record_mark_kernel(const unsigned int * counters, RangeMark * mark_out)
 {
     RangeMark m;
-    m.nrec = counters[0]; m.pad = 0;
+    m.nrec = counters[0]; m.pad = counters[1];           // pad: overflow flag so far
     m.arena_used = *(const unsigned long long *)(counters + 2);
     *mark_out = m;
 }
