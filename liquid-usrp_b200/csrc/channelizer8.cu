@@ -131,13 +131,10 @@ __global__ void __launch_bounds__(K, 1) analyzer8_kernel(const AnalyzerParams p)
         // polyphase FIR out of registers: block i of the round uses a[i .. i+P-1], newest first
 #pragma unroll
         for (unsigned int i = 0; i < JB; i++) {
-            float ar = 0.f, ai = 0.f;
+            cf acc = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int n = P - 1; n >= 0; n--) {               // oldest sample first, as dotprod_crcf
-                ar = fmaf(h[n], a[i + P - 1 - n].x, ar);
-                ai = fmaf(h[n], a[i + P - 1 - n].y, ai);
-            }
-            bufA[i * BUF + f8_pad(r)] = make_float2(ar, ai);
+            for (int n = P - 1; n >= 0; n--) acc = cfma_real(h[n], a[i + P - 1 - n], acc);   // oldest sample first, as dotprod_crcf
+            bufA[i * BUF + f8_pad(r)] = acc;
         }
 #pragma unroll
         for (unsigned int q = 0; q < P - 1; q++) a[q] = a[q + JB];

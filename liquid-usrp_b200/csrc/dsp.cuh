@@ -10,11 +10,64 @@ namespace b2 {
 
 typedef float2 cf;
 
-__device__ __forceinline__ cf cmul(cf a, cf b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ cf cmulc(cf a, cf b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); } // a*conj(b)
-__device__ __forceinline__ cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ cf cscale(cf a, float s) { return make_float2(a.x * s, a.y * s); }
+// Packed FP32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: one instruction per complex add, scale or
+// multiply-accumulate instead of two; ptxas folds the re/im swaps and per-half sign flips of the complex
+// products and of the +-j rotations into operand modifiers).  Same IEEE rounding per component as the scalar ops.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ cf f2_unpack(unsigned long long v)
+{
+    cf r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ cf f2_add(cf a, cf b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ cf f2_sub(cf a, cf b)
+{
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ cf f2_mul(cf a, cf b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ cf f2_fma(cf a, cf b, cf c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)), "l"(f2_pack(c.x, c.y)));
+    return f2_unpack(d);
+}
+
+// a*b = a.x*(b.x, b.y) + (-t.x, t.y) with t = a.y*(b.y, b.x): FMUL2 + FFMA2, the swap and the per-half
+// sign are operand modifiers
+__device__ __forceinline__ cf cmul(cf a, cf b)
+{
+    const cf t = f2_mul(make_float2(a.y, a.y), make_float2(b.y, b.x));
+    return f2_fma(make_float2(a.x, a.x), b, make_float2(-t.x, t.y));
+}
+// a*conj(b) = b.x*(a.x, a.y) + (t.x, -t.y) with t = b.y*(a.y, a.x)
+__device__ __forceinline__ cf cmulc(cf a, cf b)
+{
+    const cf t = f2_mul(make_float2(b.y, b.y), make_float2(a.y, a.x));
+    return f2_fma(make_float2(b.x, b.x), a, make_float2(t.x, -t.y));
+}
+__device__ __forceinline__ cf cadd(cf a, cf b) { return f2_add(a, b); }
+__device__ __forceinline__ cf csub(cf a, cf b) { return f2_sub(a, b); }
+__device__ __forceinline__ cf cscale(cf a, float s) { return f2_mul(a, make_float2(s, s)); }
+// acc + h*x, real tap times complex sample (the polyphase FIR inner step)
+__device__ __forceinline__ cf cfma_real(float h, cf x, cf acc) { return f2_fma(make_float2(h, h), x, acc); }
 
 // e^{+j theta} for a uint32 phase (2*pi <-> 2^32): cos/sin of (int32)theta * pi / 2^31
 __device__ __forceinline__ cf nco_cexp(uint32_t theta)
@@ -40,7 +93,7 @@ __device__ __forceinline__ cf nco_cexp_fast(uint32_t theta)
     __sincosf(t, &s, &c);
     return make_float2(c, s);
 }
-__device__ __forceinline__ cf mix_down(cf x, cf w) { return make_float2(x.x * w.x + x.y * w.y, x.y * w.x - x.x * w.y); } // x*conj(w)
+__device__ __forceinline__ cf mix_down(cf x, cf w) { return cmulc(x, w); } // x*conj(w)
 __device__ __forceinline__ cf mix_up(cf x, cf w) { return cmul(x, w); }
 
 // radians -> uint32 phase, same rounding as the host (design.h nco_constrain)
@@ -84,11 +137,10 @@ template <int DIR> __device__ __forceinline__ void dft8(cf * v)
     dft4<DIR>(e);
     dft4<DIR>(o);
     // w8^1 = (1 + DIR*j)/sqrt2, w8^2 = DIR*j, w8^3 = (-1 + DIR*j)/sqrt2
-    cf t1 = DIR < 0 ? make_float2((o[1].x + o[1].y) * h, (o[1].y - o[1].x) * h)
-                    : make_float2((o[1].x - o[1].y) * h, (o[1].y + o[1].x) * h);
+    // w8^1 x = (x + DIR*j*x) * h,  w8^3 x = (-x + DIR*j*x) * h
+    cf t1 = cscale(cadd(o[1], mul_j<DIR>(o[1])), h);
     cf t2 = mul_j<DIR>(o[2]);
-    cf t3 = DIR < 0 ? make_float2((-o[3].x + o[3].y) * h, (-o[3].y - o[3].x) * h)
-                    : make_float2((-o[3].x - o[3].y) * h, (-o[3].y + o[3].x) * h);
+    cf t3 = cscale(csub(mul_j<DIR>(o[3]), o[3]), h);
     v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
     v[1] = cadd(e[1], t1);   v[5] = csub(e[1], t1);
     v[2] = cadd(e[2], t2);   v[6] = csub(e[2], t2);
