@@ -463,6 +463,7 @@ struct b2_mcrx_s {
     // decode on core.dstream; chunk c of a call flows through all four while chunk c+1 follows
     cudaStream_t cstream = nullptr, sstream = nullptr;
     SmPartition part;                    // SMs split between the synchroniser chains and the throughput kernels
+    cudaStream_t spare_stream = nullptr; // the partition stream this handle does not use (destroyed with it)
     unsigned int chunk_blocks = 0;
     struct AnEv { cudaEvent_t copied, a0, a1; };
     std::vector<AnEv> aev;
@@ -522,7 +523,10 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
             if (sm_partition_create(q->part, device, want)) {
                 q->stream = q->part.big_stream[0];
                 q->sstream = q->part.small_stream;
-                decode_stream = q->part.big_stream[1];
+                // packet decode: beside the channelizer (default) or beside the synchronisers (B2_DECODE_WITH_SYNC=1)
+                const bool with_sync = getenv("B2_DECODE_WITH_SYNC") != nullptr;
+                decode_stream = with_sync ? q->part.small_stream2 : q->part.big_stream[1];
+                q->spare_stream = with_sync ? q->part.big_stream[1] : q->part.small_stream2;
             }
         }
         if (!q->stream && cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaStreamCreate failed"); break; }
@@ -580,6 +584,7 @@ extern "C" int b2_mcrx_destroy(b2_mcrx * q)
     if (q->stream) cudaStreamDestroy(q->stream);
     if (q->sstream) cudaStreamDestroy(q->sstream);
     if (q->cstream) cudaStreamDestroy(q->cstream);
+    if (q->spare_stream) cudaStreamDestroy(q->spare_stream);
     delete q;
     return B2_OK;
 }

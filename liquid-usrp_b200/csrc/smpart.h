@@ -8,6 +8,7 @@ struct SmPartition {
     bool ok = false;
     unsigned int small_sms = 0, big_sms = 0;
     cudaStream_t small_stream = nullptr;         // synchroniser chains
+    cudaStream_t small_stream2 = nullptr;        // a second stream on the same SM set
     cudaStream_t big_stream[2] = {nullptr, nullptr};   // channelizer, packet decode
 };
 // streams of a (cached, per device) partition with `small_sms` SMs in the small set; false when the
