@@ -48,10 +48,10 @@ WORKLOAD = dict(name="multichannelrx N=256 M=512 cp=64 taper=16 qam64 fec=none p
 B_ALG_PATH = 16.10          # 8 B in + 4 B channelizer out + 4 B sync in + 0.10 B payload, per wideband sample
 B_ALG = {"analyzer_kernel": 12.0, "sync_kernel": 4.10, "packet_decode_kernel": 0.20}
 # DRAM traffic measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one --set full capture per kernel,
-# profiles/r01_{analyzer8,sync8,decode}_pipelined.txt: a 4,194,304-sample chunk of this workload), as bytes per wideband
+# profiles/r01_{analyzer8,sync8,decode}_pipelined.txt: a 33,554,432-sample chunk of this workload), as bytes per wideband
 # sample; bench reports it per launch of the average chunk of the step, like `achieved`
-TRAFFIC_PER_SAMPLE = {"analyzer_kernel": (33.670912e6 + 0.328448e6) / 4194304, "sync_kernel": 20.314368e6 / 4194304,
-                      "packet_decode_kernel": 0.454144e6 / 4194304}
+TRAFFIC_PER_SAMPLE = {"analyzer_kernel": (272.111360e6 + 109.252096e6) / 33554432, "sync_kernel": (137.936896e6 + 9.240832e6) / 33554432,
+                      "packet_decode_kernel": 4.816384e6 / 33554432}
 
 
 def peaks():
