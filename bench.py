@@ -427,7 +427,7 @@ def main():
                                   "note": "aggregate of independent 256-channel receivers on ONE GPU, each fed the same device-resident stream"}
         for r in rxs[1:]:
             r.close()
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:       # reported baseline: rank 0 at N = 1 only
         cores = cpu_cores()
         ncpu, tcpu, _nf, per_step = cpu_receivers(period, cores, 2, seconds=10.0)
         n1, t1, _nf1, _ = cpu_receivers(period, 1, 2, seconds=4.0)
