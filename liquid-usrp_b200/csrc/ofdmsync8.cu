@@ -219,16 +219,11 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
     const cf * tw = nullptr;                 // no table at run time
     unsigned int ar[8];                      // rank of own subcarriers among the active ones (fft-shifted order)
     cf Bq[8];                                // B[i] = e^{j 2 pi backoff i / M}: timing back-off of the S1 gain estimate
-    {
-        const float bphi = 2.0f * (float)p.backoff / (float)M;
 #pragma unroll
-        for (unsigned int s = 0; s < 8; s++) {
-            const unsigned int i = t + s * T;
-            ar[s] = p.tb.act_rank[i];
-            float sn, cs;
-            sincospif(bphi * (float)i, &sn, &cs);
-            Bq[s] = make_float2(cs, sn);
-        }
+    for (unsigned int s = 0; s < 8; s++) {
+        const unsigned int i = t + s * T;
+        ar[s] = p.tb.act_rank[i];
+        Bq[s] = p.tb.B[i];
     }
     // header de-interleaver walks (n = 36): lane l < 18 swaps bytes 2l <-> 2 walk[v][l] + 1 in pass v
     unsigned int hwalk[4] = {0, 0, 0, 0};
@@ -287,8 +282,11 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
     unsigned int head = 0, ppos = 0, hstart = 0, pstart = 0, bps = 0, ms = 0, mod_len = 0, adv = 0, head2 = 0, off = 0;
     uint32_t th = 0, dth = 0;
     float en = 0.f;
+    float r_p1p = 0.f, r_phip = 0.f;         // pilot-fit memory (p1_prime, phi_prime) and symbol count of the frame,
+    unsigned int r_nsym = 0;                 // register copies so that the fit does not wait on shared memory
     cf v[8];
 
+    PH(15);                                   // (profile build) launch set-up
     while (true) {
       if (!pre) {
         PH(6);
@@ -305,6 +303,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         fstate = S->fstate;
         hstart = S->header_sym_idx; pstart = S->payload_sym_idx;
         bps = S->bps_payload; ms = S->ms_payload; mod_len = S->payload_mod_len;
+        r_p1p = S->p1_prime; r_phip = S->phi_prime; r_nsym = S->num_symbols;
         unsigned int need;
         if (state == ST_SEEK) need = (timer < (int)M) ? (unsigned int)((int)M - timer) : 1u;
         else if (state == ST_S0A || state == ST_S0B) need = (timer < (int)M2) ? (unsigned int)((int)M2 - timer) : 1u;
@@ -490,7 +489,6 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                     }
                 }
                 __syncthreads();
-                PH(11);
                 if (red[110] != 0.f) {
                     // G *= M/sqrt(Na) * B ; smooth |G| and arg G with an order-4 polynomial over the
                     // active subcarriers (liquid ofdmframesync_estimate_eqgain_poly); R = B / G.
@@ -514,7 +512,6 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                         yph[ar[s]] = atan2_fast(gk.y, gk.x);
                     }
                     __syncthreads();
-                    PH(12);
                     {
                         // unwrap only if some neighbouring pair is more than pi apart (smooth channels: never)
                         int wraps = 0;
@@ -524,7 +521,6 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                             __syncthreads();
                         }
                     }
-                    PH(13);
                     double ca[10];
 #pragma unroll
                     for (int i = 0; i < 10; i++) ca[i] = 0.0;
@@ -553,7 +549,6 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                             ca[i] = a;
                         }
                     }
-                    PH(14);
 #pragma unroll
                     for (unsigned int s = 0; s < 8; s++) {
                         if (rk[s] == 0xffffu) { Rr[s] = make_float2(0.f, 0.f); continue; }
@@ -577,7 +572,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                     }
                 }
             }
-            PH(7 + state);
+            PH(12);
             continue;                        // loop top synchronises
         }
 
@@ -607,6 +602,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                     const cf c = yc[lane + 32];
                     raw1 = atan2_fast(c.y * pil, c.x * pil);
                 }
+                PH(8);
                 float prev0 = __shfl_up_sync(0xffffffffu, raw0, 1);
                 float prev1 = __shfl_up_sync(0xffffffffu, raw1, 1);
                 const float last0 = __shfl_sync(0xffffffffu, raw0, 31);
@@ -639,24 +635,25 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                 __syncwarp();
                 warp_unwrap(yph, pilot_x, Mp, false, lane, sy, sxy);
             }
+            PH(9);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 sy += __shfl_xor_sync(0xffffffffu, sy, o);
                 sxy += __shfl_xor_sync(0xffffffffu, sxy, o);
             }
+            PH(10);
             if (lane == 0) {
                 const float np = (float)Mp, sx = p.pilot_sx, sxx = p.pilot_sxx;
                 float den = __fsub_rn(__fmul_rn(np, sxx), __fmul_rn(sx, sx));
                 float p1 = __fdiv_rn(__fsub_rn(__fmul_rn(np, sxy), __fmul_rn(sx, sy)), den);
                 fit_p0 = __fdiv_rn(__fsub_rn(sy, __fmul_rn(p1, sx)), np);
                 const float alpha = 0.3f;
-                p1 = __fadd_rn(__fmul_rn(alpha, p1), __fmul_rn(1 - alpha, S->p1_prime));
-                S->p1_prime = p1;
+                p1 = __fadd_rn(__fmul_rn(alpha, p1), __fmul_rn(1 - alpha, r_p1p));
                 red[111] = fit_p0; red[112] = p1;
                 // NCO trim (the next symbol is mixed with it)
                 uint32_t nd = dth;
-                if (S->num_symbols > 0) {
-                    float dphi = fit_p0 - S->phi_prime;
+                if (r_nsym > 0) {
+                    float dphi = fit_p0 - r_phip;
                     while (dphi > PI_F) dphi -= 2 * PI_F;
                     while (dphi < -PI_F) dphi += 2 * PI_F;
                     nd += nco_constrain_small(1e-3f * dphi);
@@ -667,6 +664,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         }
         // can the next event be started right behind this barrier?  (steady state of a payload: the
         // frame goes on, a whole symbol is available, no debug tap)  Its samples must have landed.
+        PH(11);
         const unsigned int take_now = (fstate == FS_PAYLOAD) ? min(p.M_data, mod_len - pstart) : 0u;
         const bool pipe = (fstate == FS_PAYLOAD) && (pstart + take_now < mod_len) && (p.nsamples - pos >= W) && (p.tap_cap == 0);
         if (pipe) {
@@ -677,8 +675,9 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         PH(4);
         if (t == 0) {
             // symbol bookkeeping: off the path of the other threads, who only need p0 / p1 / the NCO step
-            S->phi_prime = fit_p0;
-            S->num_symbols++;
+            S->phi_prime = red[111];
+            S->p1_prime = red[112];
+            S->num_symbols = r_nsym + 1;
             S->pilot_pos = (ppos + Mp) % 255u;
             S->timer = (int)(M + cp);    // liquid sets this unconditionally (also after a reset below)
         }
@@ -740,6 +739,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
             pstart += take_now;
             ppos = (ppos + Mp) % 255u;
             th = th2; dth = dth2;
+            r_phip = red[111]; r_p1p = red[112]; r_nsym += 1;
             timer = (int)W; adv = W; head = 0; head2 = 0; off = off2;
             pos += W;
             pre = true;
