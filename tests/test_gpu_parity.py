@@ -30,6 +30,11 @@ CASES = {
     "m2048_1ch_qpsk": (1, 2048, 64, 16, MOD_QPSK, FEC_NONE, FEC_NONE, 700, 2, 0.0),
     "m4096_1ch_qam64": (1, 4096, 256, 64, MOD_QAM64, FEC_NONE, FEC_NONE, 3000, 2, 0.0),
     "m256_qam256_golay": (4, 256, 32, 8, MOD_QAM256, FEC_GOLAY2412, FEC_NONE, 500, 3, 0.0),
+    # BASELINE configs[4] at its full width (the oracle receiver needs ~1 s for two frames per channel)
+    "c5_full_256ch_qam64": (256, 512, 64, 16, MOD_QAM64, FEC_NONE, FEC_NONE, 1200, 2, 0.0),
+    "c5_full_256ch_qam64_30dB": (256, 512, 64, 16, MOD_QAM64, FEC_NONE, FEC_NONE, 1200, 2, 0.03),
+    # BASELINE configs[2] at its full width: 64 channels, M = 256, 16-QAM, conv r1/2 K=7
+    "c3_full_64ch_qam16_v27": (64, 256, 32, 8, MOD_QAM16, FEC_CONV_V27, FEC_NONE, 1200, 2, 0.0),
 }
 
 
