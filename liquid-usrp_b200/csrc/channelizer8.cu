@@ -11,14 +11,13 @@
 //     previous 8 are being transformed;
 //   * thread r OWNS COLUMN r: the last P-1 mixed samples of its column live in registers and
 //     slide by 8 per round, so a staged sample is read from shared memory exactly once and the
-//     FIR is 28 FMAs per output out of registers;
+//     FIR is 14 packed FFMA2 (real tap x complex sample) per output out of registers;
 //   * the 8 FIR rows are transformed by 8 groups of K/8 threads, one row each, with the
 //     register-resident Stockham radix-8 FFT of fft8.cuh (8 points per thread, two exchanges
 //     for K = 512); only the N kept channels are written, transposed through shared memory so
 //     that each channel receives one contiguous 64-byte run per round.
-// Shared memory is 130 KB at K = 512 (one CTA per SM), leaving room for two synchroniser CTAs
-// of the previous chunk on the same SM (capi.cu runs the stages of successive chunks on
-// different CUDA streams).
+// Shared memory is 122 KB and the register file is full at K = 512 (one 512-thread CTA per SM), which is
+// why the synchroniser chains get their own SMs (smpart.cu) instead of sharing these.
 #include "kernels.h"
 #include "fft8.cuh"
 

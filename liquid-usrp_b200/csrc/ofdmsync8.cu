@@ -11,16 +11,23 @@
 //     registers from the first FFT pass to the demapper (Stockham radix-8, natural-order output,
 //     fft8.cuh), together with their equaliser taps R[k] and subcarrier roles;
 //   * the NCO mix-down happens on the way from the staging ring into the first FFT pass;
-//   * a payload OFDM symbol costs 5 CTA barriers of 2 warps: loop top, 2 FFT exchanges,
-//     pilots -> warp 0 (atan2 / unwrap / line fit / NCO trim), fit -> all; the demapped symbols
-//     leave as one byte each (bit packing is throughput work, done by packet.cu off the chain);
+//   * a steady-state payload symbol costs 4 CTA barriers of 2 warps: 2 FFT exchanges, pilots -> warp 0
+//     (polynomial atan2 / unwrap / line fit / NCO trim, all in registers), fit -> all.  Its tail is
+//     PIPELINED: the next symbol's samples are mixed and taken through the first FFT pass in the same
+//     stretch of code that derotates and demaps this symbol, so there is no loop-top barrier and no
+//     state reload between payload symbols, and two dependency chains interleave;
+//   * the demapped symbols leave as one byte each (bit packing is throughput work, done by packet.cu
+//     off the chain); header bits are packed with shared-memory atomicOr;
 //   * the S1 equaliser-gain polynomial fit is a constant 5 x Na matrix (design.h) applied to the
-//     measured |G| / arg G instead of a per-frame normal-equation solve;
-//   * samples are prefetched two events ahead with 16-byte cp.async into a ring addressed by
-//     stream position; cp.async.wait_group 1 leaves the newest group in flight.
-// The CTAs are tiny (2 warps, ~50 KB of shared memory), so the 256 streams of the north-star
-// shape occupy < 1 warp per SM scheduler and the analysis channelizer of the next chunk runs
-// beside them on the same SMs (capi.cu pipelines the two on separate CUDA streams).
+//     measured |G| / arg G instead of a per-frame normal-equation solve, and unwraps only if needed;
+//   * samples are prefetched two events ahead with 16-byte cp.async into a ring addressed by stream
+//     position, by the LAST warp while warp 0 fits the pilots; cp.async.wait_group 1 leaves the
+//     newest group in flight;
+//   * complex arithmetic is packed FP32x2 (FADD2 / FMUL2 / FFMA2, dsp.cuh); FFT twiddles, equaliser
+//     taps, training signs, S1 tables and header de-interleaver walks live in registers.
+// A chain is 2 warps, <= 255 registers and ~39 KB of shared memory: 4 chains per SM, 256 chains on the
+// 80-SM partition capi.cu / smpart.cu give the synchronisers, the channelizer of the next chunk
+// running on the other SMs.
 #include "kernels.h"
 #include "fec.cuh"
 #include "syncdev.cuh"
@@ -32,7 +39,7 @@ struct S8Layout {
     unsigned int SZ;
     size_t off_st, off_red, off_dsum, off_stg, off_hist, off_fa, off_fb, off_G0, off_yc, off_px, off_sym, off_pseq, total;
 };
-// ~31 KB for M = 512: two streams per SM leave room for the channelizer CTA of the next chunk.
+// ~39 KB for M = 512 (16 KB of it the staging ring).
 // Gs (training-symbol gains of the current event) aliases FFT buffer B and yph (phases handed to
 // warp 0) aliases FFT buffer A: both are only touched between the last FFT pass of an event and
 // the top barrier of the next one (which of the two is safe for Gs depends on the pass count).
