@@ -359,8 +359,8 @@ def main():
     for _ in range(args.steps):
         rc = L.b2_mcrx_execute(rx.h, C.c_void_p(h_x.data_ptr()), n_step)
         assert rc == 0
-        recs, pl = rx.poll()
-        d2h += recs.nbytes + len(pl) + 32
+        recs, pl = rx.poll_view()                    # records + decoded payloads, already DMA'd into pinned host memory
+        d2h += recs.nbytes + len(pl) + 24 * rx.last_launches()[1]
     barrier()
     dt_e2e = time.perf_counter() - t1
     clk.stop_flag = True
