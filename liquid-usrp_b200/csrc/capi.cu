@@ -104,7 +104,7 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     if (M < 8 || (M & 1) || cp < 1 || cp > M || taper > cp) return b2_fail(B2_ERR_ARG, "invalid OFDM configuration (M=%u cp=%u taper=%u)", M, cp, taper);
     if (ofdm_plan(plan, M, cp, taper, p) != 0) return b2_fail(B2_ERR_ARG, "invalid subcarrier allocation");
     if (M < 16 || M > 4096 || fft_plan(fftM, M) != 0)
-        return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA path needs a power-of-two number of subcarriers in [16, 4096] (got %u)", M);
+        return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA path needs an even number of subcarriers in [16, 4096] whose prime factors are <= 13 (got %u)", M);
     // tables
     std::vector<cf> B(M);
     {
@@ -497,8 +497,11 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
     if (cp < 1) return b2_fail(B2_ERR_ARG, "cyclic prefix length must be at least 1");
     if (taper > cp) return b2_fail(B2_ERR_ARG, "taper length cannot exceed cyclic prefix length");
     unsigned int K = 2 * N;
-    if ((K & (K - 1)) || K > 1024)
-        return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA channelizer needs a power-of-two channel count <= 512 (got %u)", N);
+    {
+        FftPlan probe;
+        if (K > 1024 || fft_plan(probe, K) != 0)
+            return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA channelizer needs a channel count <= 512 whose prime factors are <= 13 (got %u)", N);
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return b2_fail(B2_ERR_CUDA, "no CUDA device available");
     if (device < 0 || device >= ndev) return b2_fail(B2_ERR_ARG, "invalid device ordinal %d", device);
@@ -506,7 +509,7 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
     b2_mcrx * q = new b2_mcrx_s;
     q->device = device;
     q->N = N; q->K = K; q->lgK = ceil_log2(K);
-    q->TB = std::max(4u, 4096u / K);
+    q->TB = (4096u / K >= 8u) ? (std::min(256u, 4096u / K) & ~7u) : 4u;     // blocks per tile: a multiple of the kernel's JB (8 or 4)
     if (max_batch == 0) max_batch = (size_t)1 << 22;
     max_batch = std::max(max_batch, (size_t)4 * K);
     q->max_batch = max_batch;

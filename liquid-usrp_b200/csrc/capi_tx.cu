@@ -56,7 +56,7 @@ int GenBank::init(unsigned int N_, unsigned int M, unsigned int cp, unsigned int
     if (M < 8 || (M & 1) || cp < 1 || cp > M || taper > cp) return b2_fail(B2_ERR_ARG, "invalid OFDM configuration (M=%u cp=%u taper=%u)", M, cp, taper);
     if (ofdm_plan(plan, M, cp, taper, p) != 0) return b2_fail(B2_ERR_ARG, "invalid subcarrier allocation");
     if (M < 16 || M > 4096 || fft_plan(fftM, M) != 0)
-        return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA path needs a power-of-two number of subcarriers in [16, 4096] (got %u)", M);
+        return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA path needs an even number of subcarriers in [16, 4096] whose prime factors are <= 13 (got %u)", M);
     std::vector<float> s0, s1;
     ofdm_training_time(plan, s0, s1);
     std::vector<uint16_t> sc_rank(M, 0xffff);
@@ -230,15 +230,18 @@ extern "C" int b2_mctx_create(unsigned int N, unsigned int M, unsigned int cp, u
     if (cp < 1) return b2_fail(B2_ERR_ARG, "cyclic prefix length must be at least 1");
     if (taper > cp) return b2_fail(B2_ERR_ARG, "taper length cannot exceed cyclic prefix length");
     unsigned int K = 2 * N;
-    if ((K & (K - 1)) || K > 1024)
-        return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA channelizer needs a power-of-two channel count <= 512 (got %u)", N);
+    {
+        FftPlan probe;
+        if (K > 1024 || fft_plan(probe, K) != 0)
+            return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA channelizer needs a channel count <= 512 whose prime factors are <= 13 (got %u)", N);
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return b2_fail(B2_ERR_CUDA, "no CUDA device available");
     if (device < 0 || device >= ndev) return b2_fail(B2_ERR_ARG, "invalid device ordinal %d", device);
     B2_CUDA(cudaSetDevice(device));
     b2_mctx * q = new b2_mctx_s;
     q->device = device; q->N = N; q->K = K; q->lgK = ceil_log2(K); q->W = M + cp;
-    q->TB = (K <= 512) ? std::max(8u, 4096u / K) : 2u;
+    q->TB = (K <= 512) ? (std::min(256u, std::max(8u, 4096u / K)) & ~7u) : 2u;   // a multiple of the kernel's JB (8 or 2)
     int rc = B2_OK;
     do {
         if (cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaStreamCreate failed"); break; }

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(AN_THREADS, 1) analyzer_kernel(const AnalyzerP
         {
             const unsigned int total = (new_hi - new_lo) * K;
             for (unsigned int e = tid; e < total; e += AN_THREADS) {
-                unsigned int g = new_lo + (e >> p.lgK), r = e & (K - 1);
+                unsigned int g = new_lo + e / K, r = e % K;
                 unsigned int slot = g % RR;
                 cf w = cmul(roww[slot], colw[r]);
                 cf * px = ring + (size_t)slot * K + r;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(AN_THREADS, 1) analyzer_kernel(const AnalyzerP
 
         // polyphase FIR: thread owns column r for JB consecutive blocks
         for (unsigned int it = tid; it < groups * K; it += AN_THREADS) {
-            const unsigned int jb = it >> p.lgK, r = it & (K - 1);
+            const unsigned int jb = it / K, r = it % K;
             if (jb * JB >= nb) continue;
             float h[AN_P];
 #pragma unroll
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) synth_kernel(const SynthParams 
         for (unsigned int g = tid; g < nb; g += SY_THREADS) roww[g] = nco_cexp_pi(p.theta0 + (tb0 + g) * K * p.dtheta);
         __syncthreads();
         for (unsigned int it = tid; it < groups * K; it += SY_THREADS) {
-            const unsigned int jb = it >> p.lgK, r = it & (K - 1);
+            const unsigned int jb = it / K, r = it % K;
             if (jb * JB >= nb) continue;
             float h[SY_P];
 #pragma unroll

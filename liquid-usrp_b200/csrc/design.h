@@ -237,16 +237,28 @@ static inline unsigned int fft_inpos(unsigned int idx, unsigned int L, const uns
     return s * (idx % R) + fft_inpos(idx / R, s, radix, t - 1);
 }
 
-// n must be a power of two >= 2
+// n >= 2 with no prime factor above 13 (liquid's FFT takes any size; the reference programs default
+// to M = 48 subcarriers).  The power-of-two part is split into radix-2/4/8 passes, every odd
+// prime factor p is a radix-p pass of its own (a p x p DFT per butterfly), at most 8 passes.
 static inline int fft_plan(FftPlan & f, unsigned int n)
 {
-    if (n < 2 || (n & (n - 1))) return -1;
-    unsigned int lg = ceil_log2(n);
+    if (n < 2) return -1;
     f.n = n; f.npass = 0;
+    unsigned int odd = n, lg = 0;
+    while ((odd & 1u) == 0) { odd >>= 1; lg++; }
+    // odd prime factors first (they work on the shortest strides)
+    for (unsigned int p = 3; p <= 13 && odd > 1; p += 2) {
+        while (odd % p == 0) {
+            if (f.npass >= 8) return -1;
+            f.radix[f.npass++] = p;
+            odd /= p;
+        }
+    }
+    if (odd != 1) return -1;
     unsigned int rem = lg;
     // experiment knob: B2_FFT_MAX_RADIX=4 builds the plan from radix-4 (and one radix-2) passes
     if (const char * e = getenv("B2_FFT_MAX_RADIX")) {
-        if (atoi(e) == 4) {
+        if (atoi(e) == 4 && (n & (n - 1)) == 0) {
             if (rem & 1) { f.radix[f.npass++] = 2; rem -= 1; }
             while (rem >= 2) { f.radix[f.npass++] = 4; rem -= 2; }
         }
@@ -257,6 +269,7 @@ static inline int fft_plan(FftPlan & f, unsigned int n)
     else if (rem % 3 == 1) { f.radix[f.npass++] = 2; rem -= 1; }
     else if (rem % 3 == 2) { f.radix[f.npass++] = 4; rem -= 2; }
     while (rem >= 3) { f.radix[f.npass++] = 8; rem -= 3; }
+    if (f.npass > 8) return -1;
     f.perm.resize(n);
     for (unsigned int i = 0; i < n; i++) f.perm[i] = (uint16_t)fft_inpos(i, n, f.radix, (int)f.npass - 1);
     f.tw.resize(2 * (size_t)n);
@@ -323,6 +336,21 @@ static inline std::vector<double> eqgain_fit_matrix(const OfdmPlan & o)
 static inline void host_fft(std::vector<float> & re, std::vector<float> & im, int dir)
 {
     const unsigned int n = (unsigned int)re.size();
+    if (n & (n - 1)) {
+        // not a power of two (M = 48, ...): plain DFT, accumulated in double (construction time only)
+        std::vector<float> xr(re), xi(im);
+        for (unsigned int k = 0; k < n; k++) {
+            double sr = 0.0, si = 0.0;
+            for (unsigned int i = 0; i < n; i++) {
+                double a = (double)dir * 2.0 * M_PI * (double)(((unsigned long long)k * i) % n) / (double)n;
+                double c = cos(a), s = sin(a);
+                sr += (double)xr[i] * c - (double)xi[i] * s;
+                si += (double)xr[i] * s + (double)xi[i] * c;
+            }
+            re[k] = (float)sr; im[k] = (float)si;
+        }
+        return;
+    }
     unsigned int lg = ceil_log2(n);
     for (unsigned int i = 0; i < n; i++) {
         unsigned int r = 0;

@@ -153,7 +153,7 @@ template <int PAD> __device__ __forceinline__ unsigned int phys(unsigned int i) 
 
 struct FftDev {
     unsigned int n, npass;
-    unsigned int radices;      // radix of pass t in bits [4t, 4t+4)
+    unsigned int radices;      // radix of pass t in bits [4t, 4t+4) (2, 4, 8, or an odd prime <= 13)
     const uint16_t * perm;     // input permutation (device or shared)
     const cf * tw;             // forward twiddles e^{-j 2 pi k / n}
 };
@@ -195,12 +195,62 @@ __device__ __forceinline__ void fft_pass(cf * buf, unsigned int ld, unsigned int
     }
 }
 
+// the same pass for ANY transform length and radix (sizes that are not powers of two: M = 48, K = 6, ...):
+// integer division instead of shifts, a direct R x R DFT per butterfly.  L = sub-transform length
+// after this pass.
+template <int DIR, int PAD>
+__device__ __noinline__ void fft_pass_any(cf * buf, unsigned int ld, unsigned int nfft, unsigned int n, unsigned int L, unsigned int R,
+                                          const cf * __restrict__ tw, unsigned int tid, unsigned int nthreads)
+{
+    const unsigned int s = L / R, per = n / R, tstep = n / L, rstep = n / R;
+    const unsigned int total = nfft * per;
+    for (unsigned int w = tid; w < total; w += nthreads) {
+        const unsigned int f = w / per, b = w - f * per;
+        const unsigned int blk = b / s, j = b - blk * s;
+        cf * x = buf + (size_t)f * ld;
+        const unsigned int i0 = blk * L + j;
+        cf v[13], y[13];
+        for (unsigned int r = 0; r < R; r++) {
+            cf a = x[phys<PAD>(i0 + r * s)];
+            if (s > 1 && r > 0) {
+                cf t = tw[j * r * tstep];
+                if (DIR > 0) t.y = -t.y;
+                a = cmul(a, t);
+            }
+            v[r] = a;
+        }
+        for (unsigned int q = 0; q < R; q++) {
+            cf acc = v[0];
+            unsigned int m = 0;
+            for (unsigned int r = 1; r < R; r++) {
+                m += q;
+                if (m >= R) m -= R;
+                cf t = tw[m * rstep];
+                if (DIR > 0) t.y = -t.y;
+                acc = cadd(acc, cmul(v[r], t));
+            }
+            y[q] = acc;
+        }
+        for (unsigned int q = 0; q < R; q++) x[phys<PAD>(i0 + q * s)] = y[q];
+    }
+}
+
 // in-place DIT over data already stored in permuted order; natural-order output.
 // All threads of the CTA must call; ends with a __syncthreads().
 template <int DIR, int PAD>
 __device__ __forceinline__ void fft_inplace(cf * buf, unsigned int ld, unsigned int nfft, const FftDev & f,
                                             unsigned int tid, unsigned int nthreads)
 {
+    if (f.n & (f.n - 1)) {                       // not a power of two
+        unsigned int L = 1;
+        for (unsigned int t = 0; t < f.npass; t++) {
+            const unsigned int R = (f.radices >> (4 * t)) & 15u;
+            L *= R;
+            fft_pass_any<DIR, PAD>(buf, ld, nfft, f.n, L, R, f.tw, tid, nthreads);
+            __syncthreads();
+        }
+        return;
+    }
     const unsigned int lgn = 31u - (unsigned int)__clz((int)f.n);
     unsigned int lgL = 0;
     for (unsigned int t = 0; t < f.npass; t++) {

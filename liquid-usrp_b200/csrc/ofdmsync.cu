@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
                 float r = ref[i];
                 cf g = make_float2(X[PX(i)].x * r * gain, X[PX(i)].y * r * gain);
                 if ((i & (step - 1)) == 0) {
-                    unsigned int i2 = (i + step) & (M - 1);
+                    unsigned int i2 = i + step; if (i2 >= M) i2 -= M;
                     float r2 = ref[i2];
                     cf g2 = make_float2(X[PX(i2)].x * r2 * gain, X[PX(i2)].y * r2 * gain);
                     cf t = cmulc(g2, g);
@@ -706,7 +706,7 @@ cudaError_t sync_launch(const SyncParams & p, int threads, size_t smem_bytes, cu
     static const bool force_generic = getenv("B2_SYNC_GENERIC") != nullptr;
     if (!force_generic && sync8_supported(p.M) && p.M_pilot + p.M_data >= 5) return sync8_launch(p, st);
     // the fixed-size instances assume the default pass plan of design.h fft_plan()
-    const bool std_plan = p.fft.radices == fft_static_radices(p.M);
+    const bool std_plan = (p.M & (p.M - 1)) == 0 && p.fft.radices == fft_static_radices(p.M);
     if (std_plan && threads == 256) {
         switch (p.M) {
         case 64:   return sync_launch_t<64, 256>(p, threads, smem_bytes, st);

@@ -98,6 +98,22 @@ def test_reference_programs_run_end_to_end(tmp_path):
         assert any("channel: %u " % c in l for l in lines)
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "multichannel_rx")), reason="reference programs not prebuilt")
+def test_reference_programs_with_their_default_arguments(tmp_path):
+    """the same two programs with NO shape arguments: one channel, M = 48, cp 6, taper 4
+    (src/multichannel_tx.cc:59-68, src/multichannel_rx.cc:88-95) -- not a power of two"""
+    f = tmp_path / "air48.cf32"
+    env = dict(os.environ, B2_UHD_TX_FILE=str(f), B2_UHD_TX_MAX_SAMPLES=str(200000))
+    r = subprocess.run([os.path.join(BIN, "multichannel_tx")], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    assert f.stat().st_size >= 200000 * 8
+    env = dict(os.environ, B2_UHD_RX_FILE=str(f))
+    r = subprocess.run([os.path.join(BIN, "multichannel_rx"), "-t", "30", "-v"], env=env, capture_output=True, text=True, timeout=300)
+    lines = [l for l in r.stdout.splitlines() if "rx packet id" in l]
+    assert len(lines) >= 4, (len(lines), r.stdout[-1500:], r.stderr[-500:])
+    assert not any("INVALID" in l for l in lines)
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "ofdmflexframe_tx")), reason="reference programs not prebuilt")
 def test_reference_ofdmflexframe_programs(tmp_path):
     """src/ofdmflexframe_tx.cc -> file -> src/ofdmflexframe_rx.cc over the ofdmtxrx class"""

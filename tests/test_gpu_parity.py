@@ -30,6 +30,13 @@ CASES = {
     "m2048_1ch_qpsk": (1, 2048, 64, 16, MOD_QPSK, FEC_NONE, FEC_NONE, 700, 2, 0.0),
     "m4096_1ch_qam64": (1, 4096, 256, 64, MOD_QAM64, FEC_NONE, FEC_NONE, 3000, 2, 0.0),
     "m256_qam256_golay": (4, 256, 32, 8, MOD_QAM256, FEC_GOLAY2412, FEC_NONE, 500, 3, 0.0),
+    # sizes that are not powers of two: the reference programs default to M = 48, cp 6, taper 4, one channel
+    # (src/multichannel_rx.cc:88-95); channel counts 3, 5, 6, 7 give K = 6, 10, 12, 14 point filterbanks
+    "ref_defaults_m48_1ch": (1, 48, 6, 4, MOD_QPSK, FEC_NONE, FEC_HAMMING128, 100, 3, 0.0),
+    "n3_m48_qam16": (3, 48, 6, 4, MOD_QAM16, FEC_NONE, FEC_NONE, 120, 2, 0.0),
+    "n6_m80_h128": (6, 80, 10, 4, MOD_QPSK, FEC_NONE, FEC_HAMMING128, 100, 2, 0.0),
+    "n5_m96_v27": (5, 96, 12, 4, MOD_QAM16, FEC_CONV_V27, FEC_NONE, 150, 2, 0.0),
+    "n7_m120_qam64": (7, 120, 12, 4, MOD_QAM64, FEC_NONE, FEC_NONE, 200, 2, 0.0),
     # BASELINE configs[4] at its full width (the oracle receiver needs ~1 s for two frames per channel)
     "c5_full_256ch_qam64": (256, 512, 64, 16, MOD_QAM64, FEC_NONE, FEC_NONE, 1200, 2, 0.0),
     "c5_full_256ch_qam64_30dB": (256, 512, 64, 16, MOD_QAM64, FEC_NONE, FEC_NONE, 1200, 2, 0.03),
@@ -188,14 +195,15 @@ def test_idle_channels_corruption_and_noise_only():
 def test_channelizer_output_matches_oracle():
     import orc
     from b2 import pkg
-    for N in (1, 8, 32, 64, 128, 256):      # K = 64..512 take the column-per-thread kernel (channelizer8.cu)
+    for N in (1, 3, 5, 7, 8, 11, 12, 32, 64, 128, 256):      # K = 64..512 take the column-per-thread kernel (channelizer8.cu)
         K = 2 * N
         rng = np.random.default_rng(N)
         T = 700
         x = (rng.standard_normal(T * K) + 1j * rng.standard_normal(T * K)).astype(np.complex64)
         L = orc.lib()
         q = L.firpfbch_crcf_create_kaiser(0, K, 7, 60.0)
-        off = np.float32(-0.5 * (N - 1) / N * np.pi)       # lib/multichannelrx.cc:98 (double product -> float)
+        # lib/multichannelrx.cc:98: -0.5f*(float)(N-1) / (float)N in float, times M_PI in double, stored as float
+        off = np.float32(float(np.float32(np.float32(-0.5) * np.float32(N - 1)) / np.float32(N)) * np.pi)
         u = L.orc_nco_constrain(off)
         n = np.arange(T * K, dtype=np.uint64)
         th = ((n * np.uint64(u)) & np.uint64(0xffffffff)).astype(np.uint32).astype(np.int32)
@@ -262,8 +270,12 @@ def test_error_codes_match_reference_throws():
             pkg.MultichannelRx(*args)
         assert e.value.code == -1
     with pytest.raises(pkg.B2Error) as e:
-        pkg.MultichannelRx(3, 64, 16, 4)          # legal for liquid, outside the CUDA path
+        pkg.MultichannelRx(17, 64, 16, 4)         # legal for liquid, outside the CUDA path (prime factor 17 > 13)
     assert e.value.code == -2
+    with pytest.raises(pkg.B2Error) as e:
+        pkg.MultichannelRx(2, 38, 6, 4)           # M = 2 * 19
+    assert e.value.code == -2
+    pkg.MultichannelRx(3, 48, 6, 4).close()       # odd channel counts and the reference's default M are fine
 
 
 def test_stagewise_and_sharded_world1_equal_monolithic():

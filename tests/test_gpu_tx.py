@@ -21,6 +21,10 @@ TX_CASES = {
     "c3_16ch_qam16_v27": (16, 256, 32, 8, MOD_QAM16, FEC_CONV_V27, FEC_NONE, 300),
     "c5_shape_32ch_qam64": (32, 512, 64, 16, MOD_QAM64, FEC_NONE, FEC_NONE, 1200),
     "1ch_qam256_golay": (1, 128, 16, 4, MOD_QAM256, FEC_GOLAY2412, FEC_NONE, 77),
+    # not powers of two: the reference programs' default OFDM shape and odd channel counts
+    "ref_defaults_m48_1ch": (1, 48, 6, 4, MOD_QPSK, FEC_NONE, FEC_HAMMING128, 100),
+    "n3_m48_qam16": (3, 48, 6, 4, MOD_QAM16, FEC_NONE, FEC_NONE, 120),
+    "n6_m80_h128": (6, 80, 10, 4, MOD_QPSK, FEC_NONE, FEC_HAMMING128, 100),
 }
 
 
