@@ -131,3 +131,18 @@ def test_reference_ofdmflexframe_programs(tmp_path):
     import re
     m = re.search(r"valid packets\s*:\s*(\d+)", out)
     assert m and int(m.group(1)) >= 5, out[-1500:]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "ofdmflexframe_tx")), reason="reference programs not prebuilt")
+def test_reference_ofdmflexframe_programs_default_shape(tmp_path):
+    """the single-link programs with their default OFDM shape (M = 48, cp 6, taper 4: src/ofdmflexframe_tx.cc:64-66)"""
+    f = tmp_path / "link48.cf32"
+    env = dict(os.environ, B2_UHD_TX_FILE=str(f))
+    r = subprocess.run([os.path.join(BIN, "ofdmflexframe_tx"), "-N", "6", "-P", "200"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    env = dict(os.environ, B2_UHD_RX_FILE=str(f))
+    r = subprocess.run([os.path.join(BIN, "ofdmflexframe_rx"), "-t", "2"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    import re
+    m = re.search(r"valid packets\s*:\s*(\d+)", r.stdout)
+    assert m and int(m.group(1)) >= 5, r.stdout[-1500:]
