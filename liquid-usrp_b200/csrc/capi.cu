@@ -104,7 +104,7 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     if (M < 8 || (M & 1) || cp < 1 || cp > M || taper > cp) return b2_fail(B2_ERR_ARG, "invalid OFDM configuration (M=%u cp=%u taper=%u)", M, cp, taper);
     if (ofdm_plan(plan, M, cp, taper, p) != 0) return b2_fail(B2_ERR_ARG, "invalid subcarrier allocation");
     if (M < 16 || M > 4096 || fft_plan(fftM, M) != 0)
-        return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA path needs an even number of subcarriers in [16, 4096] whose prime factors are <= 13 (got %u)", M);
+        return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA path needs an even number of subcarriers in [16, 4096] whose prime factors are <= 41 (got %u)", M);
     // tables
     std::vector<cf> B(M);
     {
@@ -188,7 +188,7 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     sp.tb.B = t_B.as<cf>(); sp.tb.sc_rank = t_rank.as<uint16_t>(); sp.tb.eqfit_P = t_P.as<double>(); sp.tb.act_rank = t_arank.as<uint16_t>();
     sp.fft.n = fftM.n; sp.fft.npass = fftM.npass;
     sp.fft.radices = 0;
-    for (unsigned int i = 0; i < fftM.npass; i++) sp.fft.radices |= fftM.radix[i] << (4 * i);
+    for (unsigned int i = 0; i < fftM.npass; i++) sp.fft.radices |= fft_radix_code(fftM.radix[i]) << (4 * i);
     sp.fft.perm = t_perm.as<uint16_t>(); sp.fft.tw = t_tw.as<cf>();
     sync_smem = sync_smem_bytes(sp);
     const bool fast_sync = sync8_supported(M) && plan.M_pilot + plan.M_data >= 5 && getenv("B2_SYNC_GENERIC") == nullptr;
@@ -500,7 +500,7 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
     {
         FftPlan probe;
         if (K > 1024 || fft_plan(probe, K) != 0)
-            return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA channelizer needs a channel count <= 512 whose prime factors are <= 13 (got %u)", N);
+            return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA channelizer needs a channel count <= 512 whose prime factors are <= 41 (got %u)", N);
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return b2_fail(B2_ERR_CUDA, "no CUDA device available");
@@ -627,7 +627,7 @@ static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device)
     ap.out = q->d_chan.as<cf>(); ap.out_stride = q->tcap;
     ap.fft.n = K; ap.fft.npass = q->fftK.npass;
     ap.fft.radices = 0;
-    for (unsigned int i = 0; i < q->fftK.npass; i++) ap.fft.radices |= q->fftK.radix[i] << (4 * i);
+    for (unsigned int i = 0; i < q->fftK.npass; i++) ap.fft.radices |= fft_radix_code(q->fftK.radix[i]) << (4 * i);
     ap.fft.perm = q->t_perm.as<uint16_t>(); ap.fft.tw = q->t_tw.as<cf>();
 
     size_t copied = 0;                                       // samples of x already on their way into the stage
@@ -836,7 +836,7 @@ extern "C" int b2_mcrx_channelize_device(b2_mcrx * q, const float * x_dev, size_
     ap.theta0 = (uint32_t)((uint64_t)sample_offset) * q->nco_dtheta;
     ap.out = (cf *)out_dev; ap.out_stride = out_stride; ap.out_col0 = 0;
     ap.fft.n = q->K; ap.fft.npass = q->fftK.npass; ap.fft.radices = 0;
-    for (unsigned int i = 0; i < q->fftK.npass; i++) ap.fft.radices |= q->fftK.radix[i] << (4 * i);
+    for (unsigned int i = 0; i < q->fftK.npass; i++) ap.fft.radices |= fft_radix_code(q->fftK.radix[i]) << (4 * i);
     ap.fft.perm = q->t_perm.as<uint16_t>(); ap.fft.tw = q->t_tw.as<cf>();
     B2_CUDA(analyzer_launch(ap, q->an_grid, q->an_smem, q->stream));
     return B2_OK;

@@ -56,7 +56,7 @@ int GenBank::init(unsigned int N_, unsigned int M, unsigned int cp, unsigned int
     if (M < 8 || (M & 1) || cp < 1 || cp > M || taper > cp) return b2_fail(B2_ERR_ARG, "invalid OFDM configuration (M=%u cp=%u taper=%u)", M, cp, taper);
     if (ofdm_plan(plan, M, cp, taper, p) != 0) return b2_fail(B2_ERR_ARG, "invalid subcarrier allocation");
     if (M < 16 || M > 4096 || fft_plan(fftM, M) != 0)
-        return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA path needs an even number of subcarriers in [16, 4096] whose prime factors are <= 13 (got %u)", M);
+        return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA path needs an even number of subcarriers in [16, 4096] whose prime factors are <= 41 (got %u)", M);
     std::vector<float> s0, s1;
     ofdm_training_time(plan, s0, s1);
     std::vector<uint16_t> sc_rank(M, 0xffff);
@@ -80,7 +80,7 @@ int GenBank::init(unsigned int N_, unsigned int M, unsigned int cp, unsigned int
     fp.s0 = t_s0.as<cf>(); fp.s1 = t_s1.as<cf>(); fp.taper_w = t_taper.as<float>();
     fp.sc_rank = t_rank.as<uint16_t>(); fp.pilot_seq = t_seq.as<uint8_t>();
     fp.fft.n = M; fp.fft.npass = fftM.npass; fp.fft.radices = 0;
-    for (unsigned int i = 0; i < fftM.npass; i++) fp.fft.radices |= fftM.radix[i] << (4 * i);
+    for (unsigned int i = 0; i < fftM.npass; i++) fp.fft.radices |= fft_radix_code(fftM.radix[i]) << (4 * i);
     fp.fft.perm = t_perm.as<uint16_t>(); fp.fft.tw = t_tw.as<cf>();
     B2_TRY(ensure_capacity(packet_enc_len(1200, CRC_32, FEC_CONV_V27, FEC_HAMMING128), 8 * packet_enc_len(1200, CRC_32, FEC_CONV_V27, FEC_HAMMING128)));
     B2_CUDA(cudaMemsetAsync(d_post.p, 0, d_post.bytes, stream));
@@ -233,7 +233,7 @@ extern "C" int b2_mctx_create(unsigned int N, unsigned int M, unsigned int cp, u
     {
         FftPlan probe;
         if (K > 1024 || fft_plan(probe, K) != 0)
-            return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA channelizer needs a channel count <= 512 whose prime factors are <= 13 (got %u)", N);
+            return b2_fail(B2_ERR_UNSUPPORTED, "the CUDA channelizer needs a channel count <= 512 whose prime factors are <= 41 (got %u)", N);
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return b2_fail(B2_ERR_CUDA, "no CUDA device available");
@@ -347,7 +347,7 @@ static int mctx_generate_chunk(b2_mctx * q, cf * out_dev, size_t n_calls)
     sp.theta0 = q->nco_theta; sp.dtheta = q->nco_dtheta;
     sp.out = out_dev;
     sp.fft.n = K; sp.fft.npass = q->fftK.npass; sp.fft.radices = 0;
-    for (unsigned int i = 0; i < q->fftK.npass; i++) sp.fft.radices |= q->fftK.radix[i] << (4 * i);
+    for (unsigned int i = 0; i < q->fftK.npass; i++) sp.fft.radices |= fft_radix_code(q->fftK.radix[i]) << (4 * i);
     sp.fft.perm = q->t_perm.as<uint16_t>(); sp.fft.tw = q->t_tw.as<cf>();
     B2_CUDA(synth_launch(sp, q->syn_grid, q->syn_smem, q->stream));
     cudaEventRecord(q->ev[2], q->stream);

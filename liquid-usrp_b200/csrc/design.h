@@ -237,7 +237,7 @@ static inline unsigned int fft_inpos(unsigned int idx, unsigned int L, const uns
     return s * (idx % R) + fft_inpos(idx / R, s, radix, t - 1);
 }
 
-// n >= 2 with no prime factor above 13 (liquid's FFT takes any size; the reference programs default
+// n >= 2 with no prime factor above 41 (liquid's FFT takes any size; the reference programs default
 // to M = 48 subcarriers).  The power-of-two part is split into radix-2/4/8 passes, every odd
 // prime factor p is a radix-p pass of its own (a p x p DFT per butterfly), at most 8 passes.
 static inline int fft_plan(FftPlan & f, unsigned int n)
@@ -247,7 +247,7 @@ static inline int fft_plan(FftPlan & f, unsigned int n)
     unsigned int odd = n, lg = 0;
     while ((odd & 1u) == 0) { odd >>= 1; lg++; }
     // odd prime factors first (they work on the shortest strides)
-    for (unsigned int p = 3; p <= 13 && odd > 1; p += 2) {
+    for (unsigned int p = 3; p <= 41 && odd > 1; p += 2) {
         while (odd % p == 0) {
             if (f.npass >= 8) return -1;
             f.radix[f.npass++] = p;

@@ -151,9 +151,21 @@ template <int DIR> __device__ __forceinline__ void dft8(cf * v)
 // multiple of the bank count (channelizer FFT rows)
 template <int PAD> __device__ __forceinline__ unsigned int phys(unsigned int i) { return PAD == 2 ? i + (i >> 3) : (PAD ? i + (i >> 5) : i); }
 
+// 4-bit code of a pass radix: 2, 4, 8 and the odd primes up to 13 stand for themselves, the spare codes
+// carry the primes 17 .. 41
+__host__ __device__ constexpr unsigned int fft_radix_code(unsigned int R)
+{
+    return R <= 13 ? R : (R == 17 ? 1u : R == 19 ? 6u : R == 23 ? 9u : R == 29 ? 10u : R == 31 ? 12u : R == 37 ? 14u : 15u);
+}
+__host__ __device__ constexpr unsigned int fft_radix_of(unsigned int code)
+{
+    return code == 1 ? 17u : code == 6 ? 19u : code == 9 ? 23u : code == 10 ? 29u : code == 12 ? 31u : code == 14 ? 37u : code == 15 ? 41u : code;
+}
+constexpr unsigned int FFT_MAX_RADIX = 41;
+
 struct FftDev {
     unsigned int n, npass;
-    unsigned int radices;      // radix of pass t in bits [4t, 4t+4) (2, 4, 8, or an odd prime <= 13)
+    unsigned int radices;      // fft_radix_code of pass t in bits [4t, 4t+4)
     const uint16_t * perm;     // input permutation (device or shared)
     const cf * tw;             // forward twiddles e^{-j 2 pi k / n}
 };
@@ -209,7 +221,7 @@ __device__ __noinline__ void fft_pass_any(cf * buf, unsigned int ld, unsigned in
         const unsigned int blk = b / s, j = b - blk * s;
         cf * x = buf + (size_t)f * ld;
         const unsigned int i0 = blk * L + j;
-        cf v[13], y[13];
+        cf v[FFT_MAX_RADIX], y[FFT_MAX_RADIX];
         for (unsigned int r = 0; r < R; r++) {
             cf a = x[phys<PAD>(i0 + r * s)];
             if (s > 1 && r > 0) {
@@ -244,7 +256,7 @@ __device__ __forceinline__ void fft_inplace(cf * buf, unsigned int ld, unsigned 
     if (f.n & (f.n - 1)) {                       // not a power of two
         unsigned int L = 1;
         for (unsigned int t = 0; t < f.npass; t++) {
-            const unsigned int R = (f.radices >> (4 * t)) & 15u;
+            const unsigned int R = fft_radix_of((f.radices >> (4 * t)) & 15u);
             L *= R;
             fft_pass_any<DIR, PAD>(buf, ld, nfft, f.n, L, R, f.tw, tid, nthreads);
             __syncthreads();

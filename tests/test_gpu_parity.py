@@ -37,6 +37,7 @@ CASES = {
     "n6_m80_h128": (6, 80, 10, 4, MOD_QPSK, FEC_NONE, FEC_HAMMING128, 100, 2, 0.0),
     "n5_m96_v27": (5, 96, 12, 4, MOD_QAM16, FEC_CONV_V27, FEC_NONE, 150, 2, 0.0),
     "n7_m120_qam64": (7, 120, 12, 4, MOD_QAM64, FEC_NONE, FEC_NONE, 200, 2, 0.0),
+    "n17_m58_qpsk": (17, 58, 8, 4, MOD_QPSK, FEC_NONE, FEC_HAMMING128, 100, 2, 0.0),
     # BASELINE configs[4] at its full width (the oracle receiver needs ~1 s for two frames per channel)
     "c5_full_256ch_qam64": (256, 512, 64, 16, MOD_QAM64, FEC_NONE, FEC_NONE, 1200, 2, 0.0),
     "c5_full_256ch_qam64_30dB": (256, 512, 64, 16, MOD_QAM64, FEC_NONE, FEC_NONE, 1200, 2, 0.03),
@@ -195,7 +196,7 @@ def test_idle_channels_corruption_and_noise_only():
 def test_channelizer_output_matches_oracle():
     import orc
     from b2 import pkg
-    for N in (1, 3, 5, 7, 8, 11, 12, 32, 64, 128, 256):      # K = 64..512 take the column-per-thread kernel (channelizer8.cu)
+    for N in (1, 3, 5, 7, 8, 11, 12, 17, 31, 32, 64, 128, 256):      # K = 64..512 take the column-per-thread kernel (channelizer8.cu)
         K = 2 * N
         rng = np.random.default_rng(N)
         T = 700
@@ -270,10 +271,10 @@ def test_error_codes_match_reference_throws():
             pkg.MultichannelRx(*args)
         assert e.value.code == -1
     with pytest.raises(pkg.B2Error) as e:
-        pkg.MultichannelRx(17, 64, 16, 4)         # legal for liquid, outside the CUDA path (prime factor 17 > 13)
+        pkg.MultichannelRx(43, 64, 16, 4)         # legal for liquid, outside the CUDA path (prime factor 43 > 41)
     assert e.value.code == -2
     with pytest.raises(pkg.B2Error) as e:
-        pkg.MultichannelRx(2, 38, 6, 4)           # M = 2 * 19
+        pkg.MultichannelRx(2, 86, 6, 4)           # M = 2 * 43
     assert e.value.code == -2
     pkg.MultichannelRx(3, 48, 6, 4).close()       # odd channel counts and the reference's default M are fine
 
