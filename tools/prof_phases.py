@@ -1,3 +1,5 @@
+"""per-phase cycle profile of the register-resident synchroniser (CTA 0, one launch of the bench workload):
+   make -C liquid-usrp_b200 prof && python tools/prof_phases.py   (swaps the profile build in for this process only)"""
 import sys, os, ctypes as C, shutil
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 shutil.copy("/root/repo/liquid-usrp_b200/libb200ofdm_prof.so", "/root/repo/liquid-usrp_b200/libb200ofdm.so")
