@@ -518,7 +518,7 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
         // many channels: the synchroniser chains get their own SMs (smpart.cu); B2_SYNC_SMS sizes the set
         cudaStream_t decode_stream = nullptr;
         if (N >= 32 && sync8_supported(M) && K >= 64) {
-            unsigned int want = 80;
+            unsigned int want = 72;
             if (const char * e = getenv("B2_SYNC_SMS")) { long v = atol(e); if (v >= 8 && v <= 136) want = (unsigned int)v; }
             // every chain must be resident at once (a chain that waits for an SM stalls the pipeline):
             // the synchroniser kernel fits 4 CTAs of M/8 <= 64 threads per SM

@@ -26,7 +26,7 @@
 //   * complex arithmetic is packed FP32x2 (FADD2 / FMUL2 / FFMA2, dsp.cuh); FFT twiddles, equaliser
 //     taps, training signs, S1 tables and header de-interleaver walks live in registers.
 // A chain is 2 warps, <= 255 registers and ~39 KB of shared memory: 4 chains per SM, 256 chains on the
-// 80-SM partition capi.cu / smpart.cu give the synchronisers, the channelizer of the next chunk
+// 72-SM partition capi.cu / smpart.cu give the synchronisers, the channelizer of the next chunk
 // running on the other SMs.
 #include "kernels.h"
 #include "fec.cuh"
