@@ -44,7 +44,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOAD = dict(name="multichannelrx N=256 M=512 cp=64 taper=16 qam64 fec=none payload=1200B, all channels back-to-back",
-                N=256, M=512, cp=64, taper=16, payload=1200)
+                N=256, M=512, cp=64, taper=16, payload=1200, mod="qam64", bps=6, fec0="none", nd=356)
+# BASELINE.json configs[2], receive side: 64 channels, M = 256, 16-QAM, conv r1/2 K=7 (measured as an extra leg, "config64")
+WORKLOAD_64 = dict(name="multichannelrx N=64 M=256 cp=32 taper=8 qam16 fec0=conv-v27 payload=1200B, all channels back-to-back",
+                   N=64, M=256, cp=32, taper=8, payload=1200, mod="qam16", bps=4, fec0="v27", nd=178)
 B_ALG_PATH = 16.10          # 8 B in + 4 B channelizer out + 4 B sync in + 0.10 B payload, per wideband sample
 B_ALG = {"analyzer_kernel": 12.0, "sync_kernel": 4.10, "packet_decode_kernel": 0.20}
 # DRAM traffic measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one --set full capture per kernel,
@@ -62,19 +65,23 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_period(reps_for_check=1):
+def make_period(w=None):
     """one steady-state frame period of the workload from the CPU oracle transmitter
     -> (x[period] complex64, expected payload per channel, frame length in channel samples)"""
     import refmc
-    w = WORKLOAD
+    w = w or WORKLOAD
     L = refmc.ref_lib()
     N, M, cp = w["N"], w["M"], w["cp"]
     enc = w["payload"] + 4
-    nd = 356
-    nsym = 3 + 1 + -(-(-(-8 * enc // 6)) // nd) + 1
+    if w["fec0"] == "v27":
+        enc = (2 * (8 * enc + 6) + 7) // 8
+    nd = w["nd"]
+    nsym = 3 + -(-288 // nd) + -(-(-(-8 * enc // w["bps"])) // nd) + 1
     flen = nsym * (M + cp)
+    mod = {"qam64": refmc.MOD_QAM64, "qam16": refmc.MOD_QAM16}[w["mod"]]
+    fec0 = {"none": refmc.FEC_NONE, "v27": refmc.FEC_CONV_V27}[w["fec0"]]
     tx = refmc.McTx(L, N, M, cp, w["taper"])
-    x = tx.run(2 * flen, w["payload"], refmc.MOD_QAM64, refmc.FEC_NONE, refmc.FEC_NONE, seed=0xB2000000, gain=1.0 / N)
+    x = tx.run(2 * flen, w["payload"], mod, fec0, refmc.FEC_NONE, seed=0xB2000000, gain=1.0 / N)
     tx.close()
     K = 2 * N
     period = x[flen * K:2 * flen * K].copy()
@@ -203,6 +210,40 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def measure_config64(args, local_rank, pkg, barrier):
+    """BASELINE.json configs[2] on the receive side (64 channels, M = 256, 16-QAM, conv r1/2 K=7), device-resident
+    input, same protocol as the headline (extra leg, reported under "config64")"""
+    import torch
+    w = WORKLOAD_64
+    period, expected, flen = make_period(w)
+    reps = 48                                        # 60 M wideband samples, 481 MB per step
+    n_step = len(period) * reps
+    d_x = torch.from_numpy(period.view(np.float32)).cuda().repeat(reps).contiguous()
+    rx = pkg.MultichannelRx(w["N"], w["M"], w["cp"], w["taper"], device=local_rank, max_batch=n_step)
+    for _ in range(3):
+        rx.execute_device(d_x.data_ptr(), n_step)
+        recs, pl = rx.poll()
+    assert len(recs) >= w["N"] * (reps - 1) and int(recs["payload_valid"].min()) == 1
+    for i in (0, len(recs) // 2, len(recs) - 1):
+        c, o = int(recs["channel"][i]), int(recs["payload_offset"][i])
+        assert np.array_equal(pl[o:o + w["payload"]], expected[c][1])
+    steps = max(3, min(args.steps, 10))
+    kt = np.zeros(4)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rx.execute_device(d_x.data_ptr(), n_step)
+        kt += np.array(rx.last_timing())
+        rx.poll_view()
+    barrier()
+    dt = time.perf_counter() - t0
+    rx.close()
+    kt /= steps
+    return {"workload": w["name"], "value": n_step * steps / dt / 1e6, "unit": "Msamples/s", "ms_per_step": 1e3 * dt / steps,
+            "samples_per_step": n_step, "steps": steps,
+            "kernels_ms_per_step": {"analyzer_kernel": kt[0], "sync_kernel": kt[1], "packet_decode_kernel": kt[2], "call": kt[3]}}
+
+
 METRIC = "complex Msamples/s through multichannelrx (64ch OFDM) at 1/2/4/8 GPU vs CPU"
 
 
@@ -278,6 +319,7 @@ def main():
                     "of BASELINE configs[4]'s 2^31; 2.1 GB of input per step, far larger than L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"])
+    ap.add_argument("--no-config64", action="store_true", help="skip the extra 64-channel (BASELINE configs[2]) leg")
     ap.add_argument("--receivers", type=int, default=1, help="extra leg: R independent receivers sharing this GPU (reported under "
                     "'multi_receiver', never as the headline): shows that one receiver is bound by its 256 serial chains")
     args = ap.parse_args()
@@ -406,6 +448,8 @@ def main():
                          "path": {"alg_bytes_per_sample": B_ALG_PATH, "achieved": n_step * B_ALG_PATH / (kt_avg[3] * 1e-3) / 1e9,
                                   "frac": n_step * B_ALG_PATH / (kt_avg[3] * 1e-3) / 1e9 / peak}},
             "clocks": clk.summary()}
+    if not args.no_config64 and world == 1:
+        line["config64"] = measure_config64(args, local_rank, pkg, barrier)
     if args.receivers > 1:
         rxs = [rx] + [pkg.MultichannelRx(w["N"], w["M"], w["cp"], w["taper"], device=local_rank, max_batch=n_step) for _ in range(args.receivers - 1)]
 

@@ -36,7 +36,8 @@ struct SyncCore {
     DevBuf d_st, d_ring, d_G0, d_R, d_penc;
     size_t penc_cap = 0;
     // outputs
-    DevBuf d_recs, d_aux, d_arena, d_scratch, d_decoded, d_counters;
+    DevBuf d_recs, d_aux, d_arena, d_scratch, d_decoded, d_counters, d_vit;
+    unsigned int vit_ctas = 0, vit_steps = 16384;     // per-CTA Viterbi decision regions of the general decode kernel
     unsigned int recs_cap = 0;
     unsigned long long arena_cap = 0;
     // tap
@@ -200,6 +201,8 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     decode_grid = sms * 2;
+    vit_ctas = (unsigned int)sms * 6;
+    B2_TRY(d_vit.alloc(sizeof(uint2) * (size_t)vit_ctas * vit_steps));
     return reset_state();
 }
 
@@ -330,6 +333,7 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
     PacketParams pp;
     pp.recs = d_recs.as<FrameRec>(); pp.aux = d_aux.as<FrameAux>(); pp.range = range;
     pp.arena = d_arena.as<uint8_t>(); pp.scratch = d_scratch.as<uint8_t>(); pp.decoded = d_decoded.as<uint8_t>();
+    pp.vit_local = d_vit.as<uint2>(); pp.vit_local_steps = vit_steps; pp.vit_local_ctas = vit_ctas;
     if (timing) B2_CUDA(cudaEventRecord(e.d0, dstream));
     B2_CUDA(packet_decode_launch(pp, decode_grid, dstream));
     B2_CUDA(cudaEventRecord(e.d1, dstream));

@@ -139,6 +139,9 @@ struct PacketParams {
     uint8_t * arena;                 // encoded payloads (decoded in place / via scratch)
     uint8_t * scratch;               // same size as arena
     uint8_t * decoded;               // same size as arena; payload bytes end up at payload_offset
+    uint2 * vit_local;               // Viterbi decisions: vit_local_ctas regions of vit_local_steps trellis steps,
+    unsigned int vit_local_steps;    // one per CTA of the general decode kernel (null: device-wide slots only)
+    unsigned int vit_local_ctas;
 };
 cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t st);
 // mark_out = {counters[0], counters[2..3]} (records / arena bytes so far), one thread; runs between

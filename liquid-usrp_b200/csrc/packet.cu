@@ -170,7 +170,7 @@ __device__ void golay2412_decode_block(const uint8_t * enc, uint8_t * dec, unsig
 // libfec metric (|expected - received| with hard bits as 0/255), start metrics 0 / 63,
 // predecessor with the oldest bit set wins only on strictly smaller metric, chain back from 0.
 __device__ void viterbi27_decode(const uint8_t * enc, uint8_t * dec, unsigned int n, uint2 * decisions,
-                                 uint2 * stage, unsigned int tid)
+                                 uint2 * stage, unsigned int tid, bool in_smem)
 {
     const unsigned int nbits = 8 * n + 6;
     if (tid < 32) {
@@ -185,23 +185,32 @@ __device__ void viterbi27_decode(const uint8_t * enc, uint8_t * dec, unsigned in
             ex[i] = ((__popc(reg & 0x6d) & 1) << 1) | (__popc(reg & 0x4f) & 1);
         }
         unsigned int me = (L == 0) ? 0u : 63u, mo = 63u;      // metrics of states 2L, 2L+1
-        for (unsigned int t = 0; t < nbits; t++) {
-            unsigned int byte = enc[(2 * t) >> 3];
-            unsigned int r = (byte >> (6 - ((2 * t) & 7))) & 3u;            // (r0 << 1) | r1
-            // old metrics of states L and L+32
-            unsigned int a_e = __shfl_sync(0xffffffffu, me, L >> 1), a_o = __shfl_sync(0xffffffffu, mo, L >> 1);
-            unsigned int b_e = __shfl_sync(0xffffffffu, me, 16 + (L >> 1)), b_o = __shfl_sync(0xffffffffu, mo, 16 + (L >> 1));
-            unsigned int m_lo = (L & 1) ? a_o : a_e;
-            unsigned int m_hi = (L & 1) ? b_o : b_e;
-            unsigned int m0 = m_lo + 255u * __popc(ex[0] ^ r), m1 = m_hi + 255u * __popc(ex[2] ^ r);
-            unsigned int d_e = m1 < m0;
-            unsigned int ne = d_e ? m1 : m0;
-            m0 = m_lo + 255u * __popc(ex[1] ^ r); m1 = m_hi + 255u * __popc(ex[3] ^ r);
-            unsigned int d_o = m1 < m0;
-            unsigned int no = d_o ? m1 : m0;
-            me = ne; mo = no;
-            unsigned int be = __ballot_sync(0xffffffffu, d_e), bo = __ballot_sync(0xffffffffu, d_o);
-            if (L == 0) decisions[t] = make_uint2(be, bo);
+        // received bit pairs come 16 per 32-bit word (the buffers are 16-byte aligned and padded), the
+        // next word is fetched while the current one is consumed: no memory latency inside the trellis
+        const uint32_t * e32 = (const uint32_t *)enc;
+        uint32_t cur = e32[0];
+        for (unsigned int t0 = 0; t0 < nbits; t0 += 16) {
+            const uint32_t nxt = (t0 + 16 < nbits) ? e32[(t0 >> 4) + 1] : 0u;
+            const unsigned int kend = min(16u, nbits - t0);
+            for (unsigned int k = 0; k < kend; k++) {
+                const unsigned int byte = (cur >> (8 * (k >> 2))) & 0xffu;
+                const unsigned int r = (byte >> (6 - 2 * (k & 3))) & 3u;        // (r0 << 1) | r1
+                // old metrics of states L and L+32
+                unsigned int a_e = __shfl_sync(0xffffffffu, me, L >> 1), a_o = __shfl_sync(0xffffffffu, mo, L >> 1);
+                unsigned int b_e = __shfl_sync(0xffffffffu, me, 16 + (L >> 1)), b_o = __shfl_sync(0xffffffffu, mo, 16 + (L >> 1));
+                unsigned int m_lo = (L & 1) ? a_o : a_e;
+                unsigned int m_hi = (L & 1) ? b_o : b_e;
+                unsigned int m0 = m_lo + 255u * __popc(ex[0] ^ r), m1 = m_hi + 255u * __popc(ex[2] ^ r);
+                unsigned int d_e = m1 < m0;
+                unsigned int ne = d_e ? m1 : m0;
+                m0 = m_lo + 255u * __popc(ex[1] ^ r); m1 = m_hi + 255u * __popc(ex[3] ^ r);
+                unsigned int d_o = m1 < m0;
+                unsigned int no = d_o ? m1 : m0;
+                me = ne; mo = no;
+                unsigned int be = __ballot_sync(0xffffffffu, d_e), bo = __ballot_sync(0xffffffffu, d_o);
+                if (L == 0) decisions[t0 + k] = make_uint2(be, bo);
+            }
+            cur = nxt;
         }
     }
     for (unsigned int i = tid; i < n; i += PK_THREADS) dec[i] = 0;
@@ -210,15 +219,38 @@ __device__ void viterbi27_decode(const uint8_t * enc, uint8_t * dec, unsigned in
     __shared__ unsigned int tb_state;
     if (tid == 0) tb_state = 0;
     unsigned int hi = nbits;
+    if (in_smem) {
+        // the decisions already sit in shared memory: one walk, no staging
+        if (tid == 0) {
+            unsigned int s = 0, acc = 0;
+            for (unsigned int t = nbits; t-- > 0;) {
+                if (s & 1u) acc |= 0x80u >> (t & 7);
+                if ((t & 7) == 0) {
+                    if (t < 8 * n) dec[t >> 3] = (uint8_t)acc;
+                    acc = 0;
+                }
+                uint2 d = decisions[t];
+                unsigned int bit = (((s & 1u) ? d.y : d.x) >> (s >> 1)) & 1u;
+                s = (s >> 1) | (bit << 5);
+            }
+        }
+        hi = 0;
+    }
     while (hi > 0) {
-        unsigned int lo = hi > PK_TB_STEPS ? hi - PK_TB_STEPS : 0;
+        unsigned int lo = hi > PK_TB_STEPS ? ((hi - PK_TB_STEPS + 7u) & ~7u) : 0;     // chunks end on byte boundaries
         __syncthreads();
         for (unsigned int i = lo + tid; i < hi; i += PK_THREADS) stage[i - lo] = decisions[i];
         __syncthreads();
         if (tid == 0) {
-            unsigned int s = tb_state;
+            // every `lo` is a multiple of 8, so a decoded byte never straddles two chunks; the flush bits
+            // (t >= 8n) of the first chunk carry no data
+            unsigned int s = tb_state, acc = 0;
             for (unsigned int t = hi; t-- > lo;) {
-                if (t < 8 * n && (s & 1u)) dec[t >> 3] |= (uint8_t)(0x80u >> (t & 7));
+                if (s & 1u) acc |= 0x80u >> (t & 7);
+                if ((t & 7) == 0) {
+                    if (t < 8 * n) dec[t >> 3] = (uint8_t)acc;
+                    acc = 0;
+                }
                 uint2 d = stage[t - lo];
                 unsigned int bit = (((s & 1u) ? d.y : d.x) >> (s >> 1)) & 1u;
                 s = (s >> 1) | (bit << 5);
@@ -310,8 +342,15 @@ __global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketP
         // handles may run concurrently): a CTA that needs it claims a free slot and releases it after
         // the frame.  Frames without a convolutional stage never touch it.
         __shared__ unsigned int s_slot;
+        // typical frames use this CTA's own region of the handle's workspace (p.vit_local); only frames with a
+        // longer trellis take a slot of the device-wide one
         uint2 * ws = nullptr;
-        const bool need_ws = (fec0 == 11 || fec1 == 11);
+        const unsigned long long max_steps = 8ull * ((fec1 == 11) ? e0 : n0) + 6;      // longest trellis of this frame
+        const bool conv = (fec0 == 11 || fec1 == 11);
+        const bool ws_local = conv && p.vit_local && max_steps <= p.vit_local_steps;
+        const bool need_ws = conv && !ws_local;
+        const size_t ws_cap = ws_local ? p.vit_local_steps : vit_ws_stride;
+        if (ws_local) ws = p.vit_local + (size_t)blockIdx.x * p.vit_local_steps;
         if (need_ws) {
             if (tid == 0) {
                 unsigned int sl = blockIdx.x % vit_slots;
@@ -338,7 +377,7 @@ __global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketP
             __syncthreads();
             if (fec1 == 6) hamming128_decode_block(A, Bf, e0, tid);
             else if (fec1 == 7) golay2412_decode_block(A, Bf, e0, tid);
-            else if (8ull * e0 + 6 <= vit_ws_stride) viterbi27_decode(A, Bf, e0, ws, stage, tid);
+            else if (8ull * e0 + 6 <= ws_cap) viterbi27_decode(A, Bf, e0, ws, stage, tid, false);
             else ok = 0;
             s1out = Bf;
             __syncthreads();
@@ -349,7 +388,7 @@ __global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketP
             __syncthreads();
             if (fec0 == 6) hamming128_decode_block(s1out, D, n0, tid);
             else if (fec0 == 7) golay2412_decode_block(s1out, D, n0, tid);
-            else if (8ull * n0 + 6 <= vit_ws_stride) viterbi27_decode(s1out, D, n0, ws, stage, tid);
+            else if (8ull * n0 + 6 <= ws_cap) viterbi27_decode(s1out, D, n0, ws, stage, tid, false);
             else ok = 0;
         } else {
             for (unsigned int i = tid; i < n0; i += PK_THREADS) D[i] = s1out[i];
@@ -643,7 +682,9 @@ cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t 
         w = g;
     }
     packet_plain_kernel<<<grid, PKF_WARPS * 32, 0, st>>>(p);
-    packet_decode_kernel<<<grid, PK_THREADS, 0, st>>>(p, w.ws, w.stride, w.locks, w.slots);
+    // the general kernel keeps one warp per CTA busy in the Viterbi recursion: many small CTAs per SM
+    const int ggrid = p.vit_local ? (int)p.vit_local_ctas : grid;
+    packet_decode_kernel<<<ggrid, PK_THREADS, 0, st>>>(p, w.ws, w.stride, w.locks, w.slots);
     return cudaGetLastError();
 }
 
