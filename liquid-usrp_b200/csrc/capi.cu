@@ -72,7 +72,9 @@ struct SyncCore {
     float last_ms[4] = {0, 0, 0, 0};
     SyncParams sp;
     // a batch = one collect(); its chunks run sync on `stream` and decode on `dstream`
-    cudaStream_t dstream = nullptr;
+    cudaStream_t dstream = nullptr;      // = dstreams[0]
+    static const unsigned int NDS = 3;   // decode launches of successive chunks rotate over NDS streams (a conv-coded
+    cudaStream_t dstreams[3] = {nullptr, nullptr, nullptr};   // frame is a long serial recursion: chunks must overlap)
     DevBuf d_range;                      // [chunks+1] record count after each chunk's synchroniser
     unsigned int range_cap = 0, chunk = 0, launches = 0;
     struct ChunkEv { cudaEvent_t s0, s1, d0, d1, x; };
@@ -80,7 +82,7 @@ struct SyncCore {
     bool timing = true;
 
     int init(unsigned int M, unsigned int cp, unsigned int taper, const unsigned char * p, unsigned int streams_,
-             size_t tmax_, int device_, cudaStream_t st, cudaStream_t decode_st = nullptr);
+             size_t tmax_, int device_, cudaStream_t st, const cudaStream_t * decode_st = nullptr);
     void destroy();
     int reset_state();                   // fresh object: everything zero
     int reset_streams();                 // ofdmflexframesync_reset on every stream
@@ -99,7 +101,7 @@ struct SyncCore {
 };
 
 int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const unsigned char * p, unsigned int streams_,
-                   size_t tmax_, int device_, cudaStream_t st, cudaStream_t decode_st)
+                   size_t tmax_, int device_, cudaStream_t st, const cudaStream_t * decode_st)
 {
     device = device_; stream = st; streams = streams_; tmax = tmax_;
     if (M < 8 || (M & 1) || cp < 1 || cp > M || taper > cp) return b2_fail(B2_ERR_ARG, "invalid OFDM configuration (M=%u cp=%u taper=%u)", M, cp, taper);
@@ -157,8 +159,11 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     B2_CUDA(cudaMallocHost(&h_recs, sizeof(FrameRec) * recs_cap));
     B2_CUDA(cudaMallocHost(&h_payload, arena_cap));
     for (int i = 0; i < 5; i++) B2_CUDA(cudaEventCreate(&ev[i]));
-    if (decode_st) dstream = decode_st;
-    else B2_CUDA(cudaStreamCreateWithFlags(&dstream, cudaStreamNonBlocking));
+    for (unsigned int i = 0; i < NDS; i++) {
+        if (decode_st) dstreams[i] = decode_st[i];
+        else B2_CUDA(cudaStreamCreateWithFlags(&dstreams[i], cudaStreamNonBlocking));
+    }
+    dstream = dstreams[0];
     B2_CUDA(cudaStreamCreateWithFlags(&xstream, cudaStreamNonBlocking));
     range_cap = 4096;
     B2_TRY(d_range.alloc(sizeof(RangeMark) * (range_cap + 1)));
@@ -201,7 +206,7 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     decode_grid = sms * 2;
-    vit_ctas = (unsigned int)sms * 6;
+    vit_ctas = (unsigned int)sms * 12;
     B2_TRY(d_vit.alloc(sizeof(uint2) * (size_t)vit_ctas * vit_steps));
     return reset_state();
 }
@@ -217,7 +222,8 @@ void SyncCore::destroy()
     for (int i = 0; i < 5; i++) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; }
     for (auto & e : cev) { cudaEventDestroy(e.s0); cudaEventDestroy(e.s1); cudaEventDestroy(e.d0); cudaEventDestroy(e.d1); cudaEventDestroy(e.x); }
     cev.clear();
-    if (dstream) { cudaStreamDestroy(dstream); dstream = nullptr; }
+    for (unsigned int i = 0; i < NDS; i++) if (dstreams[i]) { cudaStreamDestroy(dstreams[i]); dstreams[i] = nullptr; }
+    dstream = nullptr;
 }
 
 int SyncCore::reset_state()
@@ -329,14 +335,17 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
     B2_CUDA(cudaMemcpyAsync(h_range + chunk + 1, range + 1, sizeof(RangeMark), cudaMemcpyDeviceToHost, stream));
     B2_CUDA(cudaEventRecord(e.s1, stream));
     // decode of this chunk runs beside the synchroniser of the next one
-    B2_CUDA(cudaStreamWaitEvent(dstream, e.s1, 0));
+    cudaStream_t ds = dstreams[chunk % NDS];
+    B2_CUDA(cudaStreamWaitEvent(ds, e.s1, 0));
     PacketParams pp;
     pp.recs = d_recs.as<FrameRec>(); pp.aux = d_aux.as<FrameAux>(); pp.range = range;
     pp.arena = d_arena.as<uint8_t>(); pp.scratch = d_scratch.as<uint8_t>(); pp.decoded = d_decoded.as<uint8_t>();
-    pp.vit_local = d_vit.as<uint2>(); pp.vit_local_steps = vit_steps; pp.vit_local_ctas = vit_ctas;
-    if (timing) B2_CUDA(cudaEventRecord(e.d0, dstream));
-    B2_CUDA(packet_decode_launch(pp, decode_grid, dstream));
-    B2_CUDA(cudaEventRecord(e.d1, dstream));
+    // every decode stream has its own third of the Viterbi regions (launches on different streams overlap)
+    pp.vit_local_ctas = vit_ctas / NDS; pp.vit_local_steps = vit_steps;
+    pp.vit_local = d_vit.as<uint2>() + (size_t)(chunk % NDS) * pp.vit_local_ctas * vit_steps;
+    if (timing) B2_CUDA(cudaEventRecord(e.d0, ds));
+    B2_CUDA(packet_decode_launch(pp, decode_grid, ds));
+    B2_CUDA(cudaEventRecord(e.d1, ds));
     chunk++; launches += 4;                  // synchroniser, record mark, two decode kernels
     return B2_OK;
 }
@@ -520,7 +529,8 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
     int rc = B2_OK;
     do {
         // many channels: the synchroniser chains get their own SMs (smpart.cu); B2_SYNC_SMS sizes the set
-        cudaStream_t decode_stream = nullptr;
+        cudaStream_t decode_streams[3] = {nullptr, nullptr, nullptr};
+        bool have_decode_streams = false;
         if (N >= 32 && sync8_supported(M) && K >= 64) {
             unsigned int want = 72;
             if (const char * e = getenv("B2_SYNC_SMS")) { long v = atol(e); if (v >= 8 && v <= 136) want = (unsigned int)v; }
@@ -530,10 +540,10 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
             if (sm_partition_create(q->part, device, want)) {
                 q->stream = q->part.big_stream[0];
                 q->sstream = q->part.small_stream;
-                // packet decode: beside the channelizer (default) or beside the synchronisers (B2_DECODE_WITH_SYNC=1)
-                const bool with_sync = getenv("B2_DECODE_WITH_SYNC") != nullptr;
-                decode_stream = with_sync ? q->part.small_stream2 : q->part.big_stream[1];
-                q->spare_stream = with_sync ? q->part.big_stream[1] : q->part.small_stream2;
+                // packet decode runs beside the channelizer (beside the synchronisers it disturbs the chains: measured)
+                decode_streams[0] = q->part.big_stream[1]; decode_streams[1] = q->part.big_stream[2]; decode_streams[2] = q->part.big_stream[3];
+                have_decode_streams = true;
+                q->spare_stream = q->part.small_stream2;
             }
         }
         if (!q->stream && cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaStreamCreate failed"); break; }
@@ -568,7 +578,7 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
         // chunk of the pipeline: long enough to amortise launches, short enough to overlap stages
         q->chunk_blocks = std::max(64u, (1u << 25) / K);
         if (const char * e = getenv("B2_CHUNK_BLOCKS")) { long v = atol(e); if (v >= 1) q->chunk_blocks = (unsigned int)v; }
-        if ((rc = q->core.init(M, cp, taper, p, N, q->tcap, device, q->sstream, decode_stream))) break;
+        if ((rc = q->core.init(M, cp, taper, p, N, q->tcap, device, q->sstream, have_decode_streams ? decode_streams : nullptr))) break;
         B2_CUDA(cudaMemsetAsync(q->d_stage.p, 0, q->d_stage.bytes, q->stream));
         B2_CUDA(cudaStreamSynchronize(q->stream));
     } while (0);

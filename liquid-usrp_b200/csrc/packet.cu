@@ -18,7 +18,7 @@
 
 namespace b2 {
 
-constexpr int PK_THREADS = 256;
+constexpr int PK_THREADS = 128;
 constexpr unsigned int PKF_MAX = 4096;              // longest packet the uncoded fast path stages (bytes)
 constexpr int PKF_WARPS = 8;
 constexpr unsigned int PK_TB_STEPS = 2048;          // traceback staging chunk (steps)
