@@ -825,6 +825,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                 if (NW == 1) __syncthreads();
             }
             if (t == 0) { S->evm_hat += ev; S->header_sym_idx = hstart + take; }
+            PH(13);
             if (hstart + take == 288u) {
                 __syncthreads();
                 // unscramble, de-interleave (n = 36, depth 4), Golay(24,12), CRC-32, parse
@@ -888,6 +889,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
             }
         }
 
+        PH(14);
         if (emit) {
             // append a frame record (+ the payload symbols) to the output of this launch; thread 0 reserves
             // the slots, one barrier publishes them together with every thread's symbol stores

@@ -18,7 +18,7 @@ out = (C.c_ulonglong * 16)()
 L.b2_debug_sync8_prof(out, 1)
 rx.execute_device(x.data_ptr(), len(period) * reps); rx.poll()
 L.b2_debug_sync8_prof(out, 0)
-names = ["top wait", "consume+pass1", "fft rest", "eq+pilots", "fit: barrier wait", "derot+demap(+next consume)", "flex+emit", "-", "fit: atan2", "fit: unwrap", "fit: sums", "fit: p0/p1/nco", "preamble (all)", "-", "-", "launch set-up"]
+names = ["top wait", "consume+pass1", "fft rest", "eq+pilots", "fit: barrier wait", "derot+demap(+next consume)", "emit (record, copy, reset)", "-", "fit: atan2", "fit: unwrap", "fit: sums", "fit: p0/p1/nco", "preamble (all)", "header: demap+evm+bits", "header decode / payload tail", "launch set-up"]
 tot = sum(out[:16])
 print("timing", rx.last_timing())
 for i, n in enumerate(names):
