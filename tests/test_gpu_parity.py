@@ -151,6 +151,23 @@ def test_chunking_invariance_on_device():
         assert_frames_equal(fo, po, fg, pg)
 
 
+def test_chunking_invariance_of_the_production_kernels():
+    """the register-resident synchroniser (pipelined payload symbols, chunk-boundary state) and the
+    column-per-thread channelizer under ragged calls: 1 .. 30000 wideband samples at a time"""
+    for name in ("c5_shape_32ch_qam64", "c3_full_64ch_qam16_v27"):
+        case = CASES[name]
+        x = make_input(case)
+        fo, po, _ = run_oracle(case, x)
+        rng = np.random.default_rng(11)
+        chunks, left = [], len(x)
+        while left:
+            c = int(min(left, rng.integers(1, 30000)))
+            chunks.append(c)
+            left -= c
+        fg, pg, _ = run_gpu(case, x, chunks)
+        assert_frames_equal(fo, po, fg, pg)
+
+
 def test_reset_mid_stream_matches_oracle():
     case = CASES["c2_8ch_h128"]
     N, M, cp, taper = case[:4]
