@@ -405,6 +405,15 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         PH(1);
       }
       pre = false;
+        // last payload symbol of a frame: reserve the record slot and the arena space now, so that the
+        // round trip of the two atomics hides behind this symbol's FFT instead of sitting in the emit path
+        const bool last_payload = (state == ST_RX) && (fstate == FS_PAYLOAD) && (pstart + min(p.M_data, mod_len - pstart) == mod_len);
+        unsigned int pre_slot = 0;
+        unsigned long long pre_off = 0;
+        if (t == 0 && last_payload) {
+            pre_slot = atomicAdd(&p.counters[0], 1u);
+            pre_off = atomicAdd((unsigned long long *)(p.counters + 2), (unsigned long long)((mod_len + 15u) & ~15u));
+        }
         if (t == 0) {
             S->ring_head = head2;
             if (state != ST_SEEK) S->nco_theta = th + adv * dth;
@@ -559,11 +568,10 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
 #pragma unroll
                     for (unsigned int s = 0; s < 8; s++) {
                         if (rk[s] == 0xffffu) { Rr[s] = make_float2(0.f, 0.f); continue; }
-                        const double xv = (double)(fxs[s] / (float)M);
-                        const double va = (((ca[4] * xv + ca[3]) * xv + ca[2]) * xv + ca[1]) * xv + ca[0];
-                        const double vg = (((ca[9] * xv + ca[8]) * xv + ca[7]) * xv + ca[6]) * xv + ca[5];
-                        const float A = (float)va;
-                        float thv = (float)vg;
+                        // order-4 polynomials in x in [-1/2, 1/2): float Horner is good to ~1e-7 relative
+                        const float xv = fxs[s] / (float)M;
+                        const float A = fmaf(fmaf(fmaf(fmaf((float)ca[4], xv, (float)ca[3]), xv, (float)ca[2]), xv, (float)ca[1]), xv, (float)ca[0]);
+                        float thv = fmaf(fmaf(fmaf(fmaf((float)ca[9], xv, (float)ca[8]), xv, (float)ca[7]), xv, (float)ca[6]), xv, (float)ca[5]);
                         thv = fmaf(-6.28318530717958647692f, rintf(thv * 0.15915494309189533577f), thv);
                         float sn, cs;
                         __sincosf(thv, &sn, &cs);
@@ -894,12 +902,16 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
             // append a frame record (+ the payload symbols) to the output of this launch; thread 0 reserves
             // the slots, one barrier publishes them together with every thread's symbol stores
             if (t == 0) {
-                unsigned int slot = atomicAdd(&p.counters[0], 1u);
-                unsigned long long offb = 0;
                 unsigned int e2 = (emit == 2) ? S->payload_enc_len : 0u;
                 unsigned int m2 = (emit == 2) ? S->payload_mod_len : 0u;      // symbols, one byte each
-                // (both reservations are issued back to back; an overflowing frame is flagged, not stored)
-                if (m2) offb = atomicAdd((unsigned long long *)(p.counters + 2), (unsigned long long)((m2 + 15u) & ~15u));
+                // reserved at the start of this symbol when it is the last payload symbol (emit == 2);
+                // a frame dropped for an invalid header (emit == 1) reserves its record slot here
+                unsigned int slot = pre_slot;
+                unsigned long long offb = pre_off;
+                if (!last_payload) {
+                    slot = atomicAdd(&p.counters[0], 1u);
+                    offb = m2 ? atomicAdd((unsigned long long *)(p.counters + 2), (unsigned long long)((m2 + 15u) & ~15u)) : 0ull;
+                }
                 int ok = slot < p.recs_cap;
                 if (m2 && offb + ((m2 + 15u) & ~15u) > p.arena_cap) ok = 0;
                 if (!ok) { atomicExch(&p.counters[1], 1u); red[115] = -1.f; }
