@@ -189,3 +189,44 @@ def test_msresamp_matches_oracle_and_chunks():
     with pytest.raises(pkg.B2Error) as e:
         pkg.MsResamp(np.float32(3.0))
     assert e.value.code == -2
+
+
+def test_config4_single_link_through_the_resampler():
+    """BASELINE configs[3] composed on the GPU: ofdmflexframegen (M = 512, cp 64, 256-QAM, no FEC) ->
+    msresamp_crcf(1.07) -> msresamp_crcf(1/1.07) -> ofdmflexframesync, the way src/flexframe_tx.cc:170,237 /
+    src/flexframe_rx.cc:179,240 put the resampler either side of a framer.  Every frame must come back
+    with its exact payload, and the resampled waveform must match the oracle resampler."""
+    from b2 import pkg
+    M, cp, taper, plen, nframes = 512, 64, 16, 1200, 24
+    rng = np.random.default_rng(4)
+    g = pkg.OfdmGen(M, cp, taper)
+    sent, wave = [], []
+    for f in range(nframes):
+        header = rng.integers(0, 256, 8, dtype=np.uint8)
+        payload = rng.integers(0, 256, plen, dtype=np.uint8)
+        nsym = g.assemble(header, payload, CRC_32, FEC_NONE, FEC_NONE, MOD_QAM256)
+        out, last = g.write(nsym)
+        assert last == 1
+        wave.append(out)
+        wave.append(np.zeros(3 * (M + cp), np.complex64))          # idle gap between packets
+        sent.append((header, payload))
+    g.close()
+    x = np.concatenate(wave)
+    up = pkg.MsResamp(np.float32(1.07))
+    y = up.execute(x)
+    up.close()
+    ref = orc.msresamp(x, np.float32(1.07))
+    assert len(y) == len(ref) and np.abs(y - ref).max() / np.abs(ref).max() < 2e-6
+    down = pkg.MsResamp(np.float32(1.0 / 1.07))
+    z = down.execute(y)
+    down.close()
+    rx = pkg.OfdmSync(M, cp, taper, streams=1, max_batch=len(z))
+    rx.execute(z.reshape(1, -1))
+    fr, pl = rx.poll()
+    rx.close()
+    assert len(fr) == nframes, len(fr)
+    assert int(fr["header_valid"].min()) == 1 and int(fr["payload_valid"].min()) == 1
+    for i, (header, payload) in enumerate(sent):
+        assert np.array_equal(fr["header"][i], header)
+        o = int(fr["payload_offset"][i])
+        assert np.array_equal(pl[o:o + plen], payload)
