@@ -76,6 +76,11 @@ int b2_mcrx_reset(b2_mcrx * q);
 int b2_mcrx_execute(b2_mcrx * q, const float * x_host, size_t n);
 /* same, samples already resident in device memory (16-byte aligned) */
 int b2_mcrx_execute_device(b2_mcrx * q, const float * x_dev, size_t n);
+/* rate-matching stage ahead of the receiver: every later execute call resamples its input by `rate`
+ * (msresamp_crcf, stop-band As dB) on the device before the NCO / channelizer -- the step the
+ * reference's programs compute (src/multichannel_rx.cc:137-138: usrp rate / wanted rate) but leave
+ * as a TODO on this path (lib/multichanneltxrx.cc:605).  rate = 0 removes the stage. */
+int b2_mcrx_set_resampler(b2_mcrx * q, float rate, float As);
 /* frames completed by the execute calls since the last poll, in the reference's callback order
  * (ascending completion block, then channel).  Pass recs = NULL to get the counts only. */
 int b2_mcrx_poll(b2_mcrx * q, b2_frame_rec * recs, size_t recs_cap, size_t * n_recs,
@@ -181,6 +186,8 @@ int b2_msresamp_destroy(b2_msresamp * q);
 int b2_msresamp_reset(b2_msresamp * q);
 int b2_msresamp_execute(b2_msresamp * q, const float * x_host, size_t nx, float * y_host, size_t y_cap, size_t * ny);
 int b2_msresamp_execute_device(b2_msresamp * q, const float * x_dev, size_t nx, float * y_dev, size_t y_cap, size_t * ny);
+/* host samples in, device samples out (feeds b2_mcrx_execute_device / b2_ofdmsync_execute_device) */
+int b2_msresamp_execute_to_device(b2_msresamp * q, const float * x_host, size_t nx, float * y_dev, size_t y_cap, size_t * ny);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,11 @@
 //   transmit: samples are appended to $B2_UHD_TX_FILE when set, otherwise dropped.  With
 //             $B2_UHD_TX_MAX_SAMPLES=n the "radio" is switched off after n samples: the file is
 //             closed and the process exits (the reference's transmit programs loop forever).
+//             Next to the samples a SigMF-style sidecar "<file>.sigmf-meta" is written when the
+//             stream is closed (datatype cf32_le, sample rate, centre frequency, gain, sample
+//             count, and the free-text $B2_UHD_NOTE, e.g. "N=4 M=64 cp=16 taper=4"), so a
+//             capture can be replayed later; the receive side reads the sidecar of
+//             $B2_UHD_RX_FILE when there is one and warns if its rate differs from set_rx_rate.
 // All rate/frequency/gain setters just remember their value.
 #ifndef B2_UHD_STUB_MULTI_USRP_HPP
 #define B2_UHD_STUB_MULTI_USRP_HPP
@@ -89,21 +94,53 @@ public:
     enum send_mode_t { SEND_MODE_FULL_BUFF = 0, SEND_MODE_ONE_PACKET = 1 };
     enum recv_mode_t { RECV_MODE_FULL_BUFF = 0, RECV_MODE_ONE_PACKET = 1 };
 
-    device() : rx_(NULL), tx_(NULL), streaming_(false), tx_sent_(0), tx_max_(0)
+    device() : rx_(NULL), tx_(NULL), streaming_(false), tx_sent_(0), tx_max_(0),
+               tx_rate_(0), tx_freq_(0), tx_gain_(0), capture_rate_(0)
     {
         const char * mx = getenv("B2_UHD_TX_MAX_SAMPLES");
         if (mx && *mx) tx_max_ = strtoull(mx, NULL, 10);
         const char * r = getenv("B2_UHD_RX_FILE");
         const char * t = getenv("B2_UHD_TX_FILE");
         const char * l = getenv("B2_UHD_RX_LOOP");
-        if (r && *r) rx_ = fopen(r, "rb");
-        if (t && *t) tx_ = fopen(t, "ab");
+        if (r && *r) {
+            rx_ = fopen(r, "rb");
+            // sidecar of the capture: only the sample rate is needed on this side
+            FILE * m = fopen((std::string(r) + ".sigmf-meta").c_str(), "r");
+            if (m) {
+                char line[512];
+                while (fgets(line, sizeof(line), m)) {
+                    const char * k = strstr(line, "\"core:sample_rate\"");
+                    if (k && (k = strchr(k, ':')) && (k = strchr(k + 1, ':'))) capture_rate_ = strtod(k + 1, NULL);
+                }
+                fclose(m);
+            }
+        }
+        if (t && *t) { tx_ = fopen(t, "ab"); tx_path_ = t; }
         loop_ = l && *l == '1';
     }
     ~device()
     {
         if (rx_) fclose(rx_);
-        if (tx_) fclose(tx_);
+        close_tx();
+    }
+    // transmit settings recorded in the sidecar; capture_rate() = rate found in the receive sidecar (0: none)
+    void note_tx(double rate, double freq, double gain) { tx_rate_ = rate; tx_freq_ = freq; tx_gain_ = gain; }
+    double capture_rate() const { return capture_rate_; }
+    void close_tx()
+    {
+        if (!tx_) return;
+        long long bytes = ftell(tx_);
+        fclose(tx_);
+        tx_ = NULL;
+        FILE * m = fopen((tx_path_ + ".sigmf-meta").c_str(), "w");
+        if (!m) return;
+        const char * note = getenv("B2_UHD_NOTE");
+        fprintf(m, "{\n  \"global\": {\n    \"core:datatype\": \"cf32_le\",\n    \"core:version\": \"1.0.0\",\n"
+                   "    \"core:sample_rate\": %.17g,\n    \"core:description\": \"%s\",\n    \"b2:tx_gain_db\": %.17g,\n"
+                   "    \"b2:samples\": %lld\n  },\n  \"captures\": [ { \"core:sample_start\": 0, \"core:frequency\": %.17g } ],\n"
+                   "  \"annotations\": []\n}\n",
+                tx_rate_, note ? note : "", tx_gain_, bytes >= 0 ? bytes / 8 : 0LL, tx_freq_);
+        fclose(m);
     }
     size_t get_max_send_samps_per_packet() const { return 362; }     // what a USRP1/N2x0 reports at MTU 1500
     size_t get_max_recv_samps_per_packet() const { return 362; }
@@ -118,7 +155,7 @@ public:
         }
         tx_sent_ += nsamps;
         if (tx_max_ && tx_sent_ >= tx_max_) {
-            if (tx_) fclose(tx_);
+            close_tx();
             printf("uhd stub: %llu samples sent, transmitter off\n", tx_sent_);
             exit(0);
         }
@@ -148,6 +185,8 @@ private:
     bool loop_;
     bool streaming_;
     unsigned long long tx_sent_, tx_max_;
+    std::string tx_path_;
+    double tx_rate_, tx_freq_, tx_gain_, capture_rate_;
 };
 
 namespace usrp {
@@ -164,16 +203,22 @@ public:
     device::sptr get_device() { return dev_; }
     std::string get_pp_string() { return "offline cf32 stream (UHD stub)\n"; }
 
-    void set_rx_rate(double rate, size_t chan = 0) { (void)chan; rx_rate_ = rate; }
+    void set_rx_rate(double rate, size_t chan = 0)
+    {
+        (void)chan; rx_rate_ = rate;
+        double c = dev_->capture_rate();
+        if (c > 0 && (c > rate * 1.000001 || c < rate * 0.999999))
+            fprintf(stderr, "uhd stub: capture was taken at %g S/s, receiver set to %g S/s (resample by %g)\n", c, rate, rate / c);
+    }
     double get_rx_rate(size_t chan = 0) { (void)chan; return rx_rate_; }
-    void set_tx_rate(double rate, size_t chan = 0) { (void)chan; tx_rate_ = rate; }
+    void set_tx_rate(double rate, size_t chan = 0) { (void)chan; tx_rate_ = rate; dev_->note_tx(tx_rate_, tx_freq_, tx_gain_); }
     double get_tx_rate(size_t chan = 0) { (void)chan; return tx_rate_; }
     void set_rx_freq(double f, size_t chan = 0) { (void)chan; rx_freq_ = f; }
     double get_rx_freq(size_t chan = 0) { (void)chan; return rx_freq_; }
-    void set_tx_freq(double f, size_t chan = 0) { (void)chan; tx_freq_ = f; }
+    void set_tx_freq(double f, size_t chan = 0) { (void)chan; tx_freq_ = f; dev_->note_tx(tx_rate_, tx_freq_, tx_gain_); }
     double get_tx_freq(size_t chan = 0) { (void)chan; return tx_freq_; }
     void set_rx_gain(double g, size_t chan = 0) { (void)chan; rx_gain_ = g; }
-    void set_tx_gain(double g, size_t chan = 0) { (void)chan; tx_gain_ = g; }
+    void set_tx_gain(double g, size_t chan = 0) { (void)chan; tx_gain_ = g; dev_->note_tx(tx_rate_, tx_freq_, tx_gain_); }
     void set_rx_antenna(const std::string & a, size_t chan = 0) { (void)chan; rx_ant_ = a; }
     void set_tx_antenna(const std::string & a, size_t chan = 0) { (void)chan; tx_ant_ = a; }
     void set_rx_bandwidth(double bw, size_t chan = 0) { (void)bw; (void)chan; }

@@ -10,3 +10,4 @@ The directory name carries a hyphen (it mirrors the reference's name), so import
 """
 from .capi import (B2Error, FRAME_DTYPE, MsResamp, MultichannelRx, MultichannelTx, OfdmGen, OfdmSync,  # noqa: F401
                    lib, lib_path)
+from . import capture  # noqa: F401

@@ -79,6 +79,8 @@ _PROTOS = {
     "b2_msresamp_reset": (C.c_int, [_vp]),
     "b2_msresamp_execute": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "b2_msresamp_execute_device": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
+    "b2_msresamp_execute_to_device": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
+    "b2_mcrx_set_resampler": (C.c_int, [_vp, C.c_float, C.c_float]),
 }
 
 
@@ -181,6 +183,10 @@ class MultichannelRx(_FrameSource):
 
     def execute_device(self, dev_ptr, n):
         _check(lib().b2_mcrx_execute_device(self.h, _ptr(dev_ptr), n))
+
+    def set_resampler(self, rate, As=60.0):
+        """msresamp_crcf ahead of the NCO / channelizer (rate = 0 removes it)"""
+        _check(lib().b2_mcrx_set_resampler(self.h, float(rate), float(As)))
 
     def tap_symbols(self, enable=True, max_symbols=1 << 16):
         _check(lib().b2_mcrx_tap_symbols(self.h, int(enable), max_symbols))
@@ -340,3 +346,16 @@ class MsResamp(_Handle):
         ny = _sz(0)
         _check(lib().b2_msresamp_execute(self.h, x.ctypes.data, len(x), y.ctypes.data, len(y), C.byref(ny)))
         return y[:ny.value]
+
+    def execute_device(self, x_ptr, nx, y_ptr, y_cap):
+        """device pointers in and out; returns the number of output samples"""
+        ny = _sz(0)
+        _check(lib().b2_msresamp_execute_device(self.h, _vp(x_ptr), nx, _vp(y_ptr), y_cap, C.byref(ny)))
+        return ny.value
+
+    def execute_to_device(self, x, y_ptr, y_cap):
+        """host samples in, device pointer out"""
+        x = np.ascontiguousarray(x, np.complex64)
+        ny = _sz(0)
+        _check(lib().b2_msresamp_execute_to_device(self.h, x.ctypes.data, len(x), _vp(y_ptr), y_cap, C.byref(ny)))
+        return ny.value

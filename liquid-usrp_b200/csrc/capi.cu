@@ -151,7 +151,10 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     B2_TRY(d_penc.alloc(penc_cap * streams));
     // outputs: a frame needs at least 4 OFDM symbols; payload bits <= 8 per sample
     recs_cap = (unsigned int)(streams * (tmax / (2 * W) + 4));
-    arena_cap = (unsigned long long)streams * (tmax + 64) + 16ull * recs_cap;
+    // arena of a batch: the symbols demapped inside the batch (<= one byte per sample) plus, per stream, one
+    // frame that began in earlier batches and completes in this one (bounded here to 32 KB of symbol bytes;
+    // B2_ERR_OVERFLOW reports a frame that does not fit)
+    arena_cap = (unsigned long long)streams * (tmax + 64 + std::min<size_t>(penc_cap, 32768)) + 16ull * recs_cap;
     B2_TRY(d_recs.alloc(sizeof(FrameRec) * recs_cap)); B2_TRY(d_aux.alloc(sizeof(FrameAux) * recs_cap));
     B2_TRY(d_arena.alloc(arena_cap)); B2_TRY(d_scratch.alloc(arena_cap)); B2_TRY(d_decoded.alloc(arena_cap));
     B2_TRY(d_counters.alloc(8 * sizeof(unsigned int)));
@@ -414,7 +417,7 @@ void SyncCore::fetch_timing()
 int SyncCore::collect()
 {
     // the overflow flag came back with the last chunk's mark; only the debug tap needs another trip
-    if (h_range[chunk].pad) return b2_fail(B2_ERR_OVERFLOW, "internal: frame output arena overflow");
+    if (h_range[chunk].pad) return b2_fail(B2_ERR_OVERFLOW, "frame output arena overflow: a frame larger than the per-call buffers completed; create the handle with a larger max_batch");
     if (!tap_cap) return B2_OK;
     B2_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     B2_CUDA(cudaStreamSynchronize(stream));
@@ -483,6 +486,10 @@ struct b2_mcrx_s {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     unsigned int timed_chunks = 0;       // chunks of the last call whose events await mcrx_fetch_timing()
     SyncCore core;
+    // optional rate-matching stage ahead of the NCO (b2_mcrx_set_resampler)
+    b2_msresamp * rs = nullptr;
+    DevBuf d_rs;
+    size_t rs_in_chunk = 0, rs_cap = 0;
 };
 
 // device times of the last call, computed from the events when somebody asks for them
@@ -595,6 +602,7 @@ extern "C" int b2_mcrx_destroy(b2_mcrx * q)
     if (q->sstream) cudaStreamSynchronize(q->sstream);
     if (q->cstream) cudaStreamSynchronize(q->cstream);
     q->core.destroy();
+    if (q->rs) b2_msresamp_destroy(q->rs);
     for (auto & e : q->aev) { cudaEventDestroy(e.copied); cudaEventDestroy(e.a0); cudaEventDestroy(e.a1); }
     if (q->ev_begin) cudaEventDestroy(q->ev_begin);
     if (q->ev_end) cudaEventDestroy(q->ev_end);
@@ -615,7 +623,28 @@ extern "C" int b2_mcrx_reset(b2_mcrx * q)
     B2_CUDA(cudaMemsetAsync(q->d_stage.p, 0, sizeof(cf) * (q->hist_len + q->K), q->stream));
     B2_CUDA(cudaStreamSynchronize(q->stream));
     q->carry = 0;
+    if (q->rs) B2_TRY(b2_msresamp_reset(q->rs));
     return q->core.reset_streams();
+}
+
+// msresamp_crcf ahead of multichannelrx::Execute: the rate-matching step the reference's programs
+// compute but never apply on this path (src/multichannel_rx.cc:137-138, TODO at lib/multichanneltxrx.cc:605)
+extern "C" int b2_mcrx_set_resampler(b2_mcrx * q, float rate, float As)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    B2_CUDA(cudaSetDevice(q->device));
+    if (q->rs) { b2_msresamp_destroy(q->rs); q->rs = nullptr; }
+    if (rate == 0.0f) return B2_OK;
+    B2_TRY(b2_msresamp_create(rate, As, q->device, &q->rs));
+    // one resampler call fills at most one receiver batch
+    q->rs_cap = q->max_batch;
+    q->rs_in_chunk = std::max<size_t>(1, (size_t)((double)q->max_batch / ((double)rate * 1.001))) ;
+    if (q->rs_in_chunk > 8) q->rs_in_chunk -= 4;
+    if (q->d_rs.bytes < sizeof(cf) * q->rs_cap) {
+        int rc = q->d_rs.alloc(sizeof(cf) * q->rs_cap);
+        if (rc) { b2_msresamp_destroy(q->rs); q->rs = nullptr; return rc; }
+    }
+    return B2_OK;
 }
 
 static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device)
@@ -747,6 +776,17 @@ static int mcrx_execute_any(b2_mcrx * q, const float * x, size_t n, bool on_devi
     B2_CUDA(cudaSetDevice(q->device));
     size_t done = 0;
     while (done < n) {
+        if (q->rs) {
+            // resample a piece into device memory, then run the receiver on it in place
+            size_t c = std::min(n - done, q->rs_in_chunk), ny = 0;
+            float * y = q->d_rs.as<float>();
+            B2_TRY(on_device ? b2_msresamp_execute_device(q->rs, x + 2 * done, c, y, q->rs_cap, &ny)
+                             : b2_msresamp_execute_to_device(q->rs, x + 2 * done, c, y, q->rs_cap, &ny));
+            if (ny) B2_TRY(mcrx_process(q, y, ny, true));
+            B2_CUDA(cudaStreamSynchronize(q->stream));      // d_rs is rewritten by the next piece
+            done += c;
+            continue;
+        }
         size_t c = std::min(n - done, q->max_batch);
         int rc = mcrx_process(q, x + 2 * done, c, on_device);
         if (rc) return rc;

@@ -480,7 +480,7 @@ struct b2_msresamp_s {
     cudaStream_t stream = nullptr;
     float rate = 1.0f;
     unsigned int m = 7, npfb_bits = 6;
-    DevBuf t_h, d_x, d_y;
+    DevBuf t_h, d_x, d_y, d_hist;       // d_x / d_y stage host buffers; d_hist = the 2m-1 samples before the next call
     size_t x_cap = 0, y_cap = 0;
     unsigned long long tau = 0, step = 0;
 };
@@ -504,8 +504,8 @@ extern "C" int b2_msresamp_create(float rate, float As, int device, b2_msresamp 
         q->step = (unsigned long long)llrint(4294967296.0 / (double)rate);
         q->x_cap = ((size_t)1 << 20);
         q->y_cap = (size_t)(q->x_cap * 2.1) + 64;
-        if ((rc = q->d_x.alloc(sizeof(cf) * (q->x_cap + 2 * q->m))) || (rc = q->d_y.alloc(sizeof(cf) * q->y_cap))) break;
-        cudaMemsetAsync(q->d_x.p, 0, q->d_x.bytes, q->stream);
+        if ((rc = q->d_x.alloc(sizeof(cf) * q->x_cap)) || (rc = q->d_y.alloc(sizeof(cf) * q->y_cap)) || (rc = q->d_hist.alloc(sizeof(cf) * 32))) break;
+        cudaMemsetAsync(q->d_hist.p, 0, q->d_hist.bytes, q->stream);
         cudaStreamSynchronize(q->stream);
     } while (0);
     if (rc) { b2_msresamp_destroy(q); return rc; }
@@ -524,40 +524,41 @@ extern "C" int b2_msresamp_reset(b2_msresamp * q)
 {
     if (!q) return b2_fail(B2_ERR_ARG, "null handle");
     B2_CUDA(cudaSetDevice(q->device));
-    B2_CUDA(cudaMemsetAsync(q->d_x.p, 0, sizeof(cf) * 2 * q->m, q->stream));
+    B2_CUDA(cudaMemsetAsync(q->d_hist.p, 0, q->d_hist.bytes, q->stream));
     q->tau = 0;
     B2_CUDA(cudaStreamSynchronize(q->stream));
     return B2_OK;
 }
-static int msresamp_any(b2_msresamp * q, const float * x, size_t nx, float * y, size_t y_cap, size_t * ny_out, bool on_device)
+static int msresamp_any(b2_msresamp * q, const float * x, size_t nx, float * y, size_t y_cap, size_t * ny_out, bool x_dev, bool y_dev)
 {
     if (!q || !ny_out) return b2_fail(B2_ERR_ARG, "null argument");
     *ny_out = 0;
     if (nx == 0) return B2_OK;
     if (!x || !y) return b2_fail(B2_ERR_ARG, "null sample pointer");
+    if (nx >> 31) return b2_fail(B2_ERR_ARG, "at most 2^31 samples per call");
     B2_CUDA(cudaSetDevice(q->device));
-    const unsigned int hist = 2 * q->m - 1;
+    ResampParams rp;
+    rp.hist_buf = q->d_hist.as<cf>(); rp.hist = 2 * q->m - 1;
+    rp.h = q->t_h.as<float>(); rp.npfb_bits = q->npfb_bits; rp.m2 = 2 * q->m;
+    rp.step = q->step;
+    // device input: one launch over the caller's memory; host buffers are staged by chunks of x_cap samples
     size_t done = 0, produced = 0;
     while (done < nx) {
-        size_t c = std::min(nx - done, q->x_cap);
+        size_t c = x_dev ? nx : std::min(nx - done, q->x_cap);
         // outputs k with tau + k*step < c * 2^32
         unsigned long long span = (unsigned long long)c << 32;
         unsigned long long ny = (q->tau < span) ? (span - q->tau + q->step - 1) / q->step : 0;
         if (produced + ny > y_cap) return b2_fail(B2_ERR_OVERFLOW, "output buffer too small (%zu needed)", (size_t)(produced + ny));
-        cf * dx = q->d_x.as<cf>();
-        B2_CUDA(cudaMemcpyAsync(dx + hist, x + 2 * done, sizeof(cf) * c, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, q->stream));
-        ResampParams rp;
-        rp.x = dx; rp.hist = hist; rp.nx = (unsigned int)c;
-        rp.h = q->t_h.as<float>(); rp.npfb_bits = q->npfb_bits; rp.m2 = 2 * q->m;
-        rp.tau0 = q->tau; rp.step = q->step; rp.ny = ny;
-        rp.y = on_device ? (cf *)y + produced : q->d_y.as<cf>();
+        if (x_dev) rp.x = (const cf *)x;
+        else {
+            B2_CUDA(cudaMemcpyAsync(q->d_x.p, x + 2 * done, sizeof(cf) * c, cudaMemcpyHostToDevice, q->stream));
+            rp.x = q->d_x.as<cf>();
+        }
+        rp.y = y_dev ? (cf *)y + produced : q->d_y.as<cf>();
+        rp.nx = c; rp.tau0 = q->tau; rp.ny = ny;
         B2_CUDA(resamp_launch(rp, q->stream));
-        if (!on_device && ny)
+        if (!y_dev && ny)
             B2_CUDA(cudaMemcpyAsync(y + 2 * produced, q->d_y.p, sizeof(cf) * ny, cudaMemcpyDeviceToHost, q->stream));
-        // the last 2m-1 samples become the history of the next call (via the tail of the stage)
-        B2_CUDA(cudaMemcpyAsync(q->d_y.as<cf>() + q->y_cap - hist, dx + c, sizeof(cf) * hist, cudaMemcpyDeviceToDevice, q->stream));
-        B2_CUDA(cudaStreamSynchronize(q->stream));
-        B2_CUDA(cudaMemcpyAsync(dx, q->d_y.as<cf>() + q->y_cap - hist, sizeof(cf) * hist, cudaMemcpyDeviceToDevice, q->stream));
         q->tau = q->tau + ny * q->step - span;
         produced += ny;
         done += c;
@@ -567,6 +568,8 @@ static int msresamp_any(b2_msresamp * q, const float * x, size_t nx, float * y, 
     return B2_OK;
 }
 extern "C" int b2_msresamp_execute(b2_msresamp * q, const float * x_host, size_t nx, float * y_host, size_t y_cap, size_t * ny)
-{ return msresamp_any(q, x_host, nx, y_host, y_cap, ny, false); }
+{ return msresamp_any(q, x_host, nx, y_host, y_cap, ny, false, false); }
 extern "C" int b2_msresamp_execute_device(b2_msresamp * q, const float * x_dev, size_t nx, float * y_dev, size_t y_cap, size_t * ny)
-{ return msresamp_any(q, x_dev, nx, y_dev, y_cap, ny, true); }
+{ return msresamp_any(q, x_dev, nx, y_dev, y_cap, ny, true, true); }
+extern "C" int b2_msresamp_execute_to_device(b2_msresamp * q, const float * x_host, size_t nx, float * y_dev, size_t y_cap, size_t * ny)
+{ return msresamp_any(q, x_host, nx, y_dev, y_cap, ny, false, true); }

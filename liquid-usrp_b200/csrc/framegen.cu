@@ -174,34 +174,90 @@ cudaError_t framegen_launch(const FramegenParams & p, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------ msresamp_crcf (arbitrary stage)
-__global__ void __launch_bounds__(256) resamp_kernel(const ResampParams p)
+// One CTA produces RS_OUT consecutive outputs.  Their input window (RS_OUT*step/2^32 + 2m samples,
+// at most 2*RS_OUT + 2m for rates >= 0.5) and the prototype, regrouped as (h[b + n*npfb], h[b + 1 + n*npfb])
+// pairs, are staged in shared memory with coalesced loads; samples older than x[0] come from the
+// 2m-1 sample history of the previous call.  Arithmetic per output is the oracle's: two
+// accumulations over n ascending (newest sample first), then the linear blend.
+#define RS_THREADS 256
+#define RS_PER     4
+#define RS_OUT     (RS_THREADS * RS_PER)
+#define RS_MAXTAPS 16
+__global__ void __launch_bounds__(RS_THREADS) resamp_kernel(const ResampParams p)
 {
-    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= p.ny) return;
-    const unsigned long long t = p.tau0 + k * p.step;
-    const unsigned int i = (unsigned int)(t >> 32);                 // newest input sample used
-    const unsigned int f = (unsigned int)t;
-    const unsigned int fb = 32 - p.npfb_bits;
-    const unsigned int b = f >> fb;
-    const float mu = (float)(f & ((1u << fb) - 1u)) * (1.0f / (float)(1u << fb));
+    extern __shared__ __align__(16) unsigned char rs_smem[];
     const unsigned int npfb = 1u << p.npfb_bits;
-    const cf * x = p.x + p.hist + i;                                 // x[-n] = sample i-n
-    float y0r = 0.f, y0i = 0.f, y1r = 0.f, y1i = 0.f;
-    // oldest sample first, as the oracle's loop (n ascending reads r[2m-1-n] = newest first)
-    for (unsigned int n = 0; n < p.m2; n++) {
-        cf s = x[-(int)n];
-        float h0 = __ldg(p.h + b + n * npfb), h1 = __ldg(p.h + b + 1 + n * npfb);
-        y0r = fmaf(h0, s.x, y0r); y0i = fmaf(h0, s.y, y0i);
-        y1r = fmaf(h1, s.x, y1r); y1i = fmaf(h1, s.y, y1i);
+    float2 * hp = reinterpret_cast<float2 *>(rs_smem);               // [m2][npfb] pairs
+    cf * xs = reinterpret_cast<cf *>(hp + p.m2 * npfb);              // input window
+    const unsigned long long k0 = (unsigned long long)blockIdx.x * RS_OUT;
+    const unsigned long long kn = (p.ny - k0 < RS_OUT) ? p.ny - k0 : RS_OUT;
+    const long long i_lo = (long long)((p.tau0 + k0 * p.step) >> 32) - (long long)(p.m2 - 1);
+    const long long i_hi = (long long)((p.tau0 + (k0 + kn - 1) * p.step) >> 32);
+    const unsigned int nwin = (unsigned int)(i_hi - i_lo + 1);
+    for (unsigned int j = threadIdx.x; j < p.m2 * npfb; j += RS_THREADS)
+        hp[j] = make_float2(__ldg(p.h + j), __ldg(p.h + j + 1));
+    for (unsigned int j = threadIdx.x; j < nwin; j += RS_THREADS) {
+        long long i = i_lo + j;
+        xs[j] = (i >= 0) ? __ldg(p.x + i) : p.hist_buf[(long long)p.hist + i];
     }
-    p.y[k] = make_float2((1.0f - mu) * y0r + mu * y1r, (1.0f - mu) * y0i + mu * y1i);
+    __syncthreads();
+    const unsigned int fb = 32 - p.npfb_bits;
+    const float inv = 1.0f / (float)(1u << fb);
+#pragma unroll
+    for (unsigned int r = 0; r < RS_PER; r++) {
+        const unsigned int kk = threadIdx.x + r * RS_THREADS;
+        if (kk >= kn) break;
+        const unsigned long long t = p.tau0 + (k0 + kk) * p.step;
+        const unsigned int f = (unsigned int)t;
+        const unsigned int bnk = f >> fb;
+        const float mu = (float)(f & ((1u << fb) - 1u)) * inv;
+        const cf * x = xs + ((long long)(t >> 32) - i_lo);          // x[-n] = sample i-n
+        const float2 * h = hp + bnk;
+        float y0r = 0.f, y0i = 0.f, y1r = 0.f, y1i = 0.f;
+        for (unsigned int n = 0; n < p.m2; n++) {
+            const cf s = x[-(int)n];
+            const float2 c = h[n * npfb];
+            y0r = fmaf(c.x, s.x, y0r); y0i = fmaf(c.x, s.y, y0i);
+            y1r = fmaf(c.y, s.x, y1r); y1i = fmaf(c.y, s.y, y1i);
+        }
+        p.y[k0 + kk] = make_float2((1.0f - mu) * y0r + mu * y1r, (1.0f - mu) * y0i + mu * y1i);
+    }
+}
+
+// history of the next call: the last `hist` samples of (previous history ++ x[0..nx))
+__global__ void resamp_hist_kernel(cf * hist_buf, unsigned int hist, const cf * x, unsigned long long nx)
+{
+    const unsigned int j = threadIdx.x;
+    cf v = make_float2(0.f, 0.f);
+    if (j < hist) {
+        long long i = (long long)nx - (long long)hist + j;           // index into x; negative = old history
+        v = (i >= 0) ? x[i] : hist_buf[(long long)hist + i];
+    }
+    __syncthreads();
+    if (j < hist) hist_buf[j] = v;
+}
+
+size_t resamp_smem_bytes(const ResampParams & p)
+{
+    // window: ceil(RS_OUT * step / 2^32) + m2 + 1 samples
+    unsigned long long span = ((unsigned long long)RS_OUT * p.step >> 32) + p.m2 + 2;
+    return sizeof(float2) * p.m2 * ((size_t)1 << p.npfb_bits) + sizeof(cf) * span;
 }
 
 cudaError_t resamp_launch(const ResampParams & p, cudaStream_t st)
 {
-    if (p.ny == 0) return cudaSuccess;
-    unsigned long long blocks = (p.ny + 255) / 256;
-    resamp_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p);
+    if (p.ny) {
+        const size_t smem = resamp_smem_bytes(p);
+        static size_t configured = 48 * 1024;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(resamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+        unsigned long long blocks = (p.ny + RS_OUT - 1) / RS_OUT;
+        resamp_kernel<<<(unsigned int)blocks, RS_THREADS, smem, st>>>(p);
+    }
+    resamp_hist_kernel<<<1, 32, 0, st>>>(p.hist_buf, p.hist, p.x, p.nx);
     return cudaGetLastError();
 }
 

@@ -218,8 +218,10 @@ cudaError_t synth_launch(const SynthParams & p, int grid, size_t smem_bytes, cud
 // msresamp_crcf (arbitrary stage, rate in [0.5, 2]); output k is a closed-form function of k:
 // t_k = tau0 + k*step (Q32), input index t_k >> 32 (relative to x[0] = first new sample)
 struct ResampParams {
-    const cf * x;               // [hist + nx] : hist = 2m-1 previous samples, then the new ones
-    unsigned int hist, nx;
+    const cf * x;               // [nx] new samples
+    cf * hist_buf;              // [hist] the 2m-1 samples before x[0]; replaced by the launch with the last 2m-1 of this call
+    unsigned int hist;          // 2m-1 (<= 31)
+    unsigned long long nx;
     const float * h;            // prototype taps [2*m*npfb + 1]
     unsigned int npfb_bits, m2; // log2(npfb), 2m
     unsigned long long tau0, step;

@@ -87,6 +87,11 @@ def test_reference_programs_run_end_to_end(tmp_path):
                         "-m", "qpsk", "-c", "h128", "-k", "none", "-g", "-6"], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
     assert f.stat().st_size >= 400000 * 8
+    # the stand-in leaves a SigMF-style sidecar next to the samples (liquid-usrp_b200/capture.py reads it)
+    import json
+    meta = json.load(open(str(f) + ".sigmf-meta"))
+    assert meta["global"]["core:datatype"] == "cf32_le" and meta["global"]["b2:samples"] == f.stat().st_size // 8
+    assert meta["global"]["core:sample_rate"] > 0
     env = dict(os.environ, B2_UHD_RX_FILE=str(f))
     r = subprocess.run([os.path.join(BIN, "multichannel_rx"), "-n", "4", "-M", "64", "-C", "16", "-T", "4", "-t", "30", "-v"],
                        env=env, capture_output=True, text=True, timeout=300)

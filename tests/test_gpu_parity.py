@@ -166,6 +166,9 @@ def test_chunking_invariance_of_the_production_kernels():
             left -= c
         fg, pg, _ = run_gpu(case, x, chunks)
         assert_frames_equal(fo, po, fg, pg)
+        # batches far shorter than a frame: every frame completes in a batch it did not begin in
+        fg, pg, _ = run_gpu(case, x, None, max_batch=5000)
+        assert_frames_equal(fo, po, fg, pg)
 
 
 def test_reset_mid_stream_matches_oracle():
@@ -376,3 +379,43 @@ def test_full_size_north_star_shape_properties():
     for name in EXACT:
         assert np.array_equal(fr[name], fr2[name]), name
     assert np.array_equal(pl, pl2)
+
+
+def test_resampler_ahead_of_the_receiver():
+    """msresamp_crcf in front of multichannelrx (the ratio src/multichannel_rx.cc:137-138
+    computes).  A capture taken at 1.07x the receiver's rate is brought back by b2_mcrx_set_resampler; the
+    frames must equal the oracle receiver run on the resampled stream, whatever the call sizes, from host or
+    device memory, and every frame must survive the two rate changes."""
+    import torch
+    import orc
+    from b2 import pkg
+    for name in ("c2_8ch_h128", "c5_shape_32ch_qam64"):
+        case = CASES[name]
+        N, M, cp, taper = case[:4]
+        x = make_input(case)
+        xr = orc.msresamp(x, np.float32(1.07))                    # what a radio at 1.07x would have captured
+        rate = np.float32(1.0 / 1.07)
+        rs = pkg.MsResamp(rate)
+        y = rs.execute(xr)
+        rs.close()
+        fo, po, _ = run_oracle(case, y)
+        assert len(fo) == N * case[8] and int(fo["payload_valid"].sum()) == len(fo)
+        rng = np.random.default_rng(12)
+        for mode in ("one_call", "ragged", "device", "small_batch"):
+            g = pkg.MultichannelRx(N, M, cp, taper, max_batch=5000 if mode == "small_batch" else 0)
+            g.set_resampler(rate)
+            if mode == "ragged":
+                i = 0
+                while i < len(xr):
+                    c = int(rng.integers(1, 20000))
+                    g.execute(xr[i:i + c])
+                    i += c
+            elif mode == "device":
+                d = torch.from_numpy(xr.view(np.float32)).cuda()
+                g.execute_device(d.data_ptr(), len(xr))
+            else:
+                g.execute(xr)
+            fg, pg = g.poll()
+            g.set_resampler(0.0)                                   # removing the stage leaves a plain receiver
+            g.close()
+            assert_frames_equal(fo, po, fg, pg)

@@ -230,3 +230,32 @@ def test_config4_single_link_through_the_resampler():
         assert np.array_equal(fr["header"][i], header)
         o = int(fr["payload_offset"][i])
         assert np.array_equal(pl[o:o + plen], payload)
+
+
+def test_msresamp_device_paths_equal_host_path():
+    """one launch over device memory (any length, history carried on the device) == the staged host path"""
+    import torch
+    from b2 import pkg
+    rng = np.random.default_rng(10)
+    n = 300001
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    for rate in (1.07, 0.5, 2.0):
+        g = pkg.MsResamp(np.float32(rate))
+        ref = g.execute(x)
+        d_x = torch.from_numpy(x.view(np.float32)).cuda()
+        cap = int(n * rate * 1.01) + 64
+        d_y = torch.zeros(2 * cap, dtype=torch.float32, device="cuda")
+        for cuts in ([n], [1, 5, 13, 14, 1000, 77777]):
+            g.reset()
+            d_y.zero_()
+            i = o = 0
+            for c in cuts + [n - sum(cuts)] if sum(cuts) < n else cuts:
+                o += g.execute_device(d_x.data_ptr() + 8 * i, c, d_y.data_ptr() + 8 * o, cap - o)
+                i += c
+            assert i == n and o == len(ref), (rate, i, o, len(ref))
+            assert np.array_equal(d_y[:2 * o].cpu().numpy().view(np.complex64), ref), (rate, cuts)
+        g.reset()
+        o = g.execute_to_device(x[:1234], d_y.data_ptr(), cap)
+        o += g.execute_to_device(x[1234:], d_y.data_ptr() + 8 * o, cap - o)
+        assert o == len(ref) and np.array_equal(d_y[:2 * o].cpu().numpy().view(np.complex64), ref)
+        g.close()
