@@ -163,7 +163,10 @@ cudaError_t framegen_launch(const FramegenParams & p, cudaStream_t st)
 {
     if (p.nchan == 0 || p.nper == 0) return cudaSuccess;
     size_t smem = framegen_smem_bytes(p);
-    static size_t configured = 0;
+    static size_t configured_dev[64] = {0};              // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t & configured = configured_dev[(unsigned int)dev & 63u];
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(framegen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -248,8 +251,11 @@ cudaError_t resamp_launch(const ResampParams & p, cudaStream_t st)
 {
     if (p.ny) {
         const size_t smem = resamp_smem_bytes(p);
-        static size_t configured = 48 * 1024;
-        if (smem > configured) {
+        static size_t configured_dev[64] = {0};          // the attribute is per device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        size_t & configured = configured_dev[(unsigned int)dev & 63u];
+        if (smem > 48 * 1024 && smem > configured) {
             cudaError_t e = cudaFuncSetAttribute(resamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             configured = smem;

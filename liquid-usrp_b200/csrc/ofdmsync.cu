@@ -688,7 +688,10 @@ cudaError_t sync_reset_launch(SyncState * st, unsigned int streams, cudaStream_t
 template <unsigned int MT, unsigned int NT>
 static cudaError_t sync_launch_t(const SyncParams & p, int threads, size_t smem_bytes, cudaStream_t st)
 {
-    static size_t configured = 0;
+    static size_t configured_dev[64] = {0};              // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t & configured = configured_dev[(unsigned int)dev & 63u];
     if (smem_bytes > configured) {
         cudaError_t e = cudaFuncSetAttribute(sync_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;

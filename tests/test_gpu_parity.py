@@ -419,3 +419,30 @@ def test_resampler_ahead_of_the_receiver():
             g.set_resampler(0.0)                                   # removing the stage leaves a plain receiver
             g.close()
             assert_frames_equal(fo, po, fg, pg)
+
+
+def test_two_devices_in_one_process():
+    """handles on different devices of one process (the C ABI takes a device ordinal): per-device kernel
+    attributes, SM partitions and streams must not leak from one device to the other"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from b2 import pkg
+    case = CASES["c5_shape_32ch_qam64"]
+    N, M, cp, taper = case[:4]
+    x = make_input(case)
+    fo, po, _ = run_oracle(case, x)
+    rxs = [pkg.MultichannelRx(N, M, cp, taper, device=d) for d in (1, 0)]
+    half = len(x) // 2 + 7
+    for rx in rxs:
+        rx.execute(x[:half])
+    for rx in reversed(rxs):
+        rx.execute(x[half:])
+    for rx in rxs:
+        fg, pg = rx.poll()
+        assert_frames_equal(fo, po, fg, pg)
+        rx.close()
+    # the transmit side and the resampler on the second device
+    rs0, rs1 = pkg.MsResamp(np.float32(1.07), device=0), pkg.MsResamp(np.float32(1.07), device=1)
+    assert np.array_equal(rs0.execute(x[:100000]), rs1.execute(x[:100000]))
+    rs0.close(); rs1.close()
