@@ -33,7 +33,11 @@ struct SyncCore {
     // tables
     DevBuf t_sctype, t_S0, t_S1, t_data, t_pilot, t_pilotx, t_active, t_seq, t_walk, t_B, t_perm, t_tw, t_rank, t_P, t_arank;
     // state
-    DevBuf d_st, d_ring, d_G0, d_R, d_penc;
+    DevBuf d_st, d_ring, d_G0, d_R, d_penc, d_ctl;
+    unsigned int workers = 1;            // 2: frame-pipelined worker pairs (ofdmsync8.cu)
+    unsigned int sm_budget = 0;          // SMs the synchroniser kernel may use (0: the whole device); set before init()
+    unsigned int launch_id = 0;
+    unsigned long long stream_pos = 0;   // samples per stream given to the synchroniser so far
     size_t penc_cap = 0;
     // outputs
     DevBuf d_recs, d_aux, d_arena, d_scratch, d_decoded, d_counters, d_vit;
@@ -146,9 +150,30 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
         if (v >= 1 && v <= 65535) max_payload = (unsigned int)v;
     }
     penc_cap = (8 * (size_t)fec_enc_len(FEC_HAMMING128, fec_enc_len(FEC_CONV_V27, max_payload + 4)) + 64 + 15) & ~(size_t)15;
-    B2_TRY(d_st.alloc(sizeof(SyncState) * streams)); B2_TRY(d_ring.alloc(sizeof(cf) * W * streams));
-    B2_TRY(d_G0.alloc(sizeof(cf) * M * streams)); B2_TRY(d_R.alloc(sizeof(cf) * M * streams));
-    B2_TRY(d_penc.alloc(penc_cap * streams));
+    // frame-pipelined worker pairs: two CTAs per stream take alternate frames (the second starts its frame
+    // search as soon as the first has decoded a header and therefore knows where its frame ends).  Both must be
+    // resident at once, so the pair is used only where the SMs given to the synchroniser hold 2 * streams CTAs.
+    workers = 1;
+    {
+        const bool fast = sync8_supported(M) && plan.M_pilot + plan.M_data >= 5 && getenv("B2_SYNC_GENERIC") == nullptr;
+        int want = 2;
+        if (const char * e = getenv("B2_SYNC_WORKERS")) want = atoi(e);
+        if (fast && want == 2) {
+            SyncParams probe;
+            memset(&probe, 0, sizeof(probe));
+            probe.M = M; probe.cp = cp; probe.M_pilot = plan.M_pilot; probe.M_data = plan.M_data;
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+            if (sm_budget && (int)sm_budget < sms) sms = (int)sm_budget;
+            const long long cap = (long long)sync8_ctas_per_sm(probe) * sms;
+            if (2ll * streams <= cap) workers = 2;
+        }
+    }
+    const size_t vstreams = (size_t)streams * workers;
+    B2_TRY(d_st.alloc(sizeof(SyncState) * vstreams)); B2_TRY(d_ring.alloc(sizeof(cf) * W * vstreams));
+    B2_TRY(d_G0.alloc(sizeof(cf) * M * vstreams)); B2_TRY(d_R.alloc(sizeof(cf) * M * vstreams));
+    B2_TRY(d_penc.alloc(penc_cap * vstreams));
+    B2_TRY(d_ctl.alloc(sizeof(SyncCtl) * streams));
     // outputs: a frame needs at least 4 OFDM symbols; payload bits <= 8 per sample
     recs_cap = (unsigned int)(streams * (tmax / (2 * W) + 4));
     // arena of a batch: the symbols demapped inside the batch (<= one byte per sample) plus, per stream, one
@@ -186,6 +211,7 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     sp.qam_alpha[2] = 1.0f / sqrtf(2.0f); sp.qam_alpha[4] = 1.0f / sqrtf(10.0f);
     sp.qam_alpha[6] = 1.0f / sqrtf(42.0f); sp.qam_alpha[8] = 1.0f / sqrtf(170.0f);
     sp.streams = streams;
+    sp.workers = workers; sp.ctl = d_ctl.as<SyncCtl>();
     sp.st = d_st.as<SyncState>(); sp.ring = d_ring.as<cf>(); sp.G0 = d_G0.as<cf>(); sp.R = d_R.as<cf>();
     sp.penc = d_penc.as<uint8_t>(); sp.penc_cap = penc_cap;
     sp.recs = d_recs.as<FrameRec>(); sp.aux = d_aux.as<FrameAux>(); sp.recs_cap = recs_cap;
@@ -233,9 +259,14 @@ int SyncCore::reset_state()
 {
     // ofdmflexframesync_reset on every stream; the sample window is NOT cleared by liquid's
     // reset, but a freshly created object starts from zeros -- reset_state() is also create
-    std::vector<SyncState> st(streams);
-    for (auto & s : st) sync_state_init(s, plan.M, plan.cp);
-    B2_CUDA(cudaMemcpyAsync(d_st.p, st.data(), sizeof(SyncState) * streams, cudaMemcpyHostToDevice, stream));
+    std::vector<SyncState> st((size_t)streams * workers);
+    for (size_t i = 0; i < st.size(); i++) {
+        sync_state_init(st[i], plan.M, plan.cp);
+        st[i].role = (workers == 2 && (i & 1)) ? SW_WAIT : SW_OWNER;
+    }
+    stream_pos = 0;
+    B2_CUDA(cudaMemcpyAsync(d_st.p, st.data(), sizeof(SyncState) * st.size(), cudaMemcpyHostToDevice, stream));
+    B2_CUDA(cudaMemsetAsync(d_ctl.p, 0, d_ctl.bytes, stream));
     B2_CUDA(cudaMemsetAsync(d_ring.p, 0, d_ring.bytes, stream));
     B2_CUDA(cudaMemsetAsync(d_G0.p, 0, d_G0.bytes, stream));
     B2_CUDA(cudaMemsetAsync(d_R.p, 0, d_R.bytes, stream));
@@ -278,7 +309,7 @@ int SyncCore::poll_view(const b2_frame_rec ** recs, size_t * n_recs, const uint8
 
 int SyncCore::reset_streams()
 {
-    B2_CUDA(sync_reset_launch(d_st.as<SyncState>(), streams, stream));
+    B2_CUDA(sync_reset_launch(d_st.as<SyncState>(), streams, workers, d_ctl.as<SyncCtl>(), stream_pos, stream));
     B2_CUDA(cudaStreamSynchronize(stream));
     return B2_OK;
 }
@@ -329,6 +360,8 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
     if (after) B2_CUDA(cudaStreamWaitEvent(stream, after, 0));
     SyncParams q = sp;
     q.in = in; q.in_stride = in_stride; q.nsamples = nsamples;
+    q.sample_base = stream_pos; q.launch_id = ++launch_id;
+    stream_pos += nsamples;
     q.tap_cap = tap_cap;
     q.tap_X = d_tapX.as<cf>(); q.tap_chan = d_tapc.as<uint32_t>(); q.tap_index = d_tapi.as<unsigned long long>();
     if (timing) B2_CUDA(cudaEventRecord(e.s0, stream));
@@ -417,7 +450,8 @@ void SyncCore::fetch_timing()
 int SyncCore::collect()
 {
     // the overflow flag came back with the last chunk's mark; only the debug tap needs another trip
-    if (h_range[chunk].pad) return b2_fail(B2_ERR_OVERFLOW, "frame output arena overflow: a frame larger than the per-call buffers completed; create the handle with a larger max_batch");
+    if (h_range[chunk].pad) return b2_fail(B2_ERR_OVERFLOW, (h_range[chunk].pad & 2u) ? "internal: synchroniser worker hand-off timed out"
+                                       : "frame output arena overflow: a frame larger than the per-call buffers completed; create the handle with a larger max_batch");
     if (!tap_cap) return B2_OK;
     B2_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     B2_CUDA(cudaStreamSynchronize(stream));
@@ -585,6 +619,7 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
         // chunk of the pipeline: long enough to amortise launches, short enough to overlap stages
         q->chunk_blocks = std::max(64u, (1u << 25) / K);
         if (const char * e = getenv("B2_CHUNK_BLOCKS")) { long v = atol(e); if (v >= 1) q->chunk_blocks = (unsigned int)v; }
+        if (q->part.ok) q->core.sm_budget = (unsigned int)q->part.small_sms;
         if ((rc = q->core.init(M, cp, taper, p, N, q->tcap, device, q->sstream, have_decode_streams ? decode_streams : nullptr))) break;
         B2_CUDA(cudaMemsetAsync(q->d_stage.p, 0, q->d_stage.bytes, q->stream));
         B2_CUDA(cudaStreamSynchronize(q->stream));

@@ -56,6 +56,22 @@ struct SyncState {              // persistent per stream, lives in global memory
     uint64_t detect_index;
     uint8_t  header_bits[36];
     uint8_t  header_dec[20];
+    // frame-pipelined workers (ofdmsync8.cu, SyncParams::workers == 2; unused otherwise)
+    uint32_t role;              // SW_OWNER / SW_SPEC / SW_WAIT
+    uint32_t my_seq;            // hand-off this worker's frame began with (role SW_SPEC)
+    uint32_t sent_seq;          // hand-off this worker published for the frame it is in (0: none)
+    uint32_t verify;            // frame over, hand-off published: the next seek event settles it
+    uint32_t pub_pending, pad0; // header decoded while speculative: publish pub_start once confirmed
+    uint64_t pub_start;
+};
+enum { SW_OWNER = 0, SW_SPEC = 1, SW_WAIT = 2 };
+// hand-off word of a chain: (sequence number << 2) | state
+enum { HS_NONE = 0, HS_SENT = 1, HS_ACCEPTED = 2, HS_ABORTED = 3 };
+struct SyncCtl {                // per chain, global memory
+    unsigned long long start;   // absolute index of the first sample of the frame search handed off
+    unsigned int hs;            // hand-off word
+    unsigned int done[2];       // launch id in which worker 0 / 1 last left the kernel
+    unsigned int pad;
 };
 
 struct FrameRec {               // same layout as b2_frame_rec (include/b200_ofdm.h)
@@ -98,6 +114,11 @@ struct SyncParams {
     float b_cos, b_sin;         // e^{j 2 pi backoff / M}: rotation of the S1 metric (ofdmframesync_execute_S1)
     float qam_alpha[9];         // 1/sqrt(2,10,42,170) at index bps = 2,4,6,8
     unsigned int streams;
+    // workers == 2 (ofdmsync8.cu only): two CTAs per stream take alternate frames; st / ring / G0 / R / penc
+    // then hold 2*streams entries (index 2*stream + worker)
+    unsigned int workers, launch_id;
+    unsigned long long sample_base;   // absolute index of in[..][0] (samples given to earlier launches)
+    SyncCtl * ctl;              // [streams]
     const cf * in;              // in[s*in_stride + t], t < nsamples
     size_t in_stride;
     unsigned int nsamples;
@@ -120,11 +141,14 @@ size_t sync_smem_bytes(const SyncParams & p);
 cudaError_t sync_configure(size_t smem_bytes);
 cudaError_t sync_launch(const SyncParams & p, int threads, size_t smem_bytes, cudaStream_t st);
 void sync_state_init(SyncState & s, unsigned int M, unsigned int cp);
-cudaError_t sync_reset_launch(SyncState * st, unsigned int streams, cudaStream_t stream);
+cudaError_t sync_reset_launch(SyncState * st, unsigned int streams, unsigned int workers, SyncCtl * ctl,
+                              unsigned long long sample_base, cudaStream_t stream);
 // register-resident fast path (ofdmsync8.cu), M/8 threads per stream; sync_launch() picks it
 bool sync8_supported(unsigned int M);
 size_t sync8_smem_bytes(const SyncParams & p);
 cudaError_t sync8_launch(const SyncParams & p, cudaStream_t st);
+// CTAs of the kernel that fit one SM (both workers of every stream must be resident at once)
+int sync8_ctas_per_sm(const SyncParams & p);
 
 // ------------------------------------------------------------------ packet decode
 // de-interleave + FEC decode + CRC of every completed frame (liquid packetizer_decode, called

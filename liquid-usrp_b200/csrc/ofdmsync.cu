@@ -661,10 +661,10 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
 // ofdmflexframesync_reset on every stream: state machine, NCO, pilot generator and header/payload
 // progress go back to their initial values; liquid leaves the sample window alone, and the
 // sample counter (our side channel) keeps counting.
-__global__ void sync_reset_kernel(SyncState * st, unsigned int streams)
+__global__ void sync_reset_kernel(SyncState * st, unsigned int streams, unsigned int workers, SyncCtl * ctl, unsigned long long sample_base)
 {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= streams) return;
+    if (i >= streams * workers) return;
     SyncState * S = st + i;
     S->fstate = FS_HEADER;
     S->header_sym_idx = 0;
@@ -678,10 +678,18 @@ __global__ void sync_reset_kernel(SyncState * st, unsigned int streams)
     S->phi_prime = 0.f; S->p1_prime = 0.f;
     S->state = ST_SEEK;
     for (int k = 0; k < 36; k++) S->header_bits[k] = 0;      // ofdmsync8.cu ORs the header bits in
+    if (workers == 2) {
+        // worker 0 carries on alone from the current stream position, worker 1 waits for a hand-off
+        S->role = (i & 1u) ? SW_WAIT : SW_OWNER;
+        S->my_seq = 0; S->sent_seq = 0; S->verify = 0; S->pub_pending = 0;
+        S->sample_index = sample_base;
+        if ((i & 1u) == 0) { SyncCtl * c = ctl + (i >> 1); c->hs = (c->hs & ~3u) | HS_NONE; }
+    }
 }
-cudaError_t sync_reset_launch(SyncState * st, unsigned int streams, cudaStream_t stream)
+cudaError_t sync_reset_launch(SyncState * st, unsigned int streams, unsigned int workers, SyncCtl * ctl,
+                              unsigned long long sample_base, cudaStream_t stream)
 {
-    sync_reset_kernel<<<(streams + 127) / 128, 128, 0, stream>>>(st, streams);
+    sync_reset_kernel<<<(streams * workers + 127) / 128, 128, 0, stream>>>(st, streams, workers, ctl, sample_base);
     return cudaGetLastError();
 }
 

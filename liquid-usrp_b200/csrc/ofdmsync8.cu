@@ -144,7 +144,12 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
     extern __shared__ __align__(16) unsigned char smem[];
     const unsigned int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const unsigned int cp = p.cp, W = M + cp;
-    const unsigned int sidx = blockIdx.x;
+    // frame-pipelined worker pairs (p.workers == 2): CTA 2c / 2c + 1 are the two workers of stream c; see the
+    // protocol note above sync8_gate below.  vs indexes the per-worker state, sidx the stream (channel)
+    const bool duo = (p.workers == 2);
+    const unsigned int vs = blockIdx.x;
+    const unsigned int sidx = duo ? (vs >> 1) : vs;
+    const unsigned int wk = duo ? (vs & 1u) : 0u;
     const unsigned int Na = p.M_pilot + p.M_data, Mp = p.M_pilot;
     const S8Layout L = s8_layout(M, cp, Na, Mp);
     SyncState * S = (SyncState *)(smem + L.off_st);
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
     const unsigned int NEED_MAX = W + M2;
 
     const cf * in = p.in + (size_t)sidx * p.in_stride;
-    uint8_t * penc = p.penc + (size_t)sidx * p.penc_cap;
+    uint8_t * penc = p.penc + (size_t)vs * p.penc_cap;
     const bool al16 = (((size_t)in) & 15) == 0;
 
     // ---- sample prefetch: ring slot = stream position & SZM.  Issued by the LAST warp only, at the
@@ -195,20 +200,20 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         }
         if (pf_warp) cp_async_commit();
     };
-    prefetch(min(PF, p.nsamples));
+    if (!duo) prefetch(min(PF, p.nsamples));     // a worker of a pair first has to learn where it stands
 
     // ---- persistent state and tables
     cf Rr[8];
     unsigned int rk[8];
     float ref_s0[8], ref_s1[8];              // training symbols (+-1 / 0) of own subcarriers
     {
-        const uint32_t * src = (const uint32_t *)(p.st + sidx);
+        const uint32_t * src = (const uint32_t *)(p.st + vs);
         uint32_t * dst = (uint32_t *)S;
         for (unsigned int i = t; i < sizeof(SyncState) / 4; i += T) dst[i] = src[i];
-        const cf * gr = p.ring + (size_t)sidx * W;
+        const cf * gr = p.ring + (size_t)vs * W;
         for (unsigned int i = t; i < W; i += T) hist[i] = gr[i];
-        const cf * g0 = p.G0 + (size_t)sidx * M;
-        const cf * gR = p.R + (size_t)sidx * M;
+        const cf * g0 = p.G0 + (size_t)vs * M;
+        const cf * gR = p.R + (size_t)vs * M;
 #pragma unroll
         for (unsigned int s = 0; s < 8; s++) {
             const unsigned int i = t + s * T;
@@ -248,6 +253,20 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         if ((rk[s] & 0xC000u) == 0x4000u) pilot_mask |= 1u << s;
     }
     unsigned int pos = 0;
+    // ---- worker pair: role and starting point of this worker in this launch
+    volatile SyncCtl * ctl = duo ? (volatile SyncCtl *)(p.ctl + sidx) : nullptr;
+    unsigned int role = SW_OWNER;
+    if (duo) {
+        __syncthreads();                     // state copy visible
+        role = S->role;
+        if (role != SW_WAIT) {
+            const unsigned long long rel = S->sample_index - p.sample_base;
+            pos = rel >= (unsigned long long)p.nsamples ? p.nsamples : (unsigned int)rel;
+        }
+        fetched = pos & ~1u;
+        done_frontier = fetched;
+        prefetch(min(pos + PF, p.nsamples));
+    }
 #ifdef B2_SYNC_PROF
     long long t_last = clock64();
 #endif
@@ -282,6 +301,127 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
     };
     auto bsync = [] { __syncthreads(); };
 
+    // ---- worker pair protocol (thread 0 talks to global memory; decisions reach the CTA through red[120..])
+    // One worker OWNS the stream position; when it has decoded a valid header it knows where its frame ends and
+    // hands the search for the NEXT frame to its partner (ctl->start, ctl->hs = seq|SENT), which starts from a
+    // fresh ofdmflexframesync_reset one sample past the frame end -- the state the owner itself would be in
+    // there, PROVIDED the seek event liquid runs on that first sample (timer = M + cp survives the reset) finds
+    // nothing.  The owner runs that event on its own window when its frame is over and settles the hand-off:
+    // ACCEPTED (it now waits for a hand-off itself) or ABORTED (it detected something: it simply carries on and
+    // the partner throws its speculative work away).  Until then the partner is SPECULATIVE: it computes, but
+    // neither emits records nor hands off; where it cannot wait (an invalid header wants a record, the launch
+    // runs out of samples) it waits at a resumable point or returns the hand-off (hs -> NONE) and the owner
+    // carries on serially.  Results are those of the serial chain in every case.
+    auto publish = [&](unsigned long long start) {         // thread 0
+        const unsigned int seq = (ctl->hs >> 2) + 1u;
+        ctl->start = start;
+        __threadfence();
+        ctl->hs = (seq << 2) | HS_SENT;
+        S->sent_seq = seq;
+    };
+    // loop-top gate; true: this worker leaves the launch (nothing more it can do with these samples)
+    auto gate = [&]() -> bool {
+        for (;;) {
+            if (role == SW_OWNER) {
+                if (S->verify && !(S->state == ST_SEEK && S->timer == (int)(M + cp))) {
+                    // the seek event after my frame has run: settle the hand-off I published
+                    if (t == 0) {
+                        const unsigned int w0 = (S->sent_seq << 2) | HS_SENT;
+                        unsigned int nr = SW_OWNER;
+                        if (S->state == ST_SEEK) {
+                            if (atomicCAS((unsigned int *)&ctl->hs, w0, (S->sent_seq << 2) | HS_ACCEPTED) == w0) nr = SW_WAIT;
+                        } else {
+                            atomicCAS((unsigned int *)&ctl->hs, w0, (S->sent_seq << 2) | HS_ABORTED);
+                        }
+                        S->verify = 0; S->sent_seq = 0; S->role = nr;
+                        red[120] = __uint_as_float(nr);
+                    }
+                    __syncthreads();
+                    role = __float_as_uint(red[120]);
+                    __syncthreads();
+                    if (role == SW_OWNER) return false;
+                    continue;
+                }
+                return false;
+            }
+            if (role == SW_SPEC) {
+                // may the coming event have side effects?  (last payload symbol: record + arena reservation)
+                const bool blocking = (S->state == ST_RX) && (S->fstate == FS_PAYLOAD) &&
+                                      (S->payload_sym_idx + min(p.M_data, S->payload_mod_len - S->payload_sym_idx) == S->payload_mod_len);
+                if (t == 0) {
+                    const unsigned int mine = S->my_seq << 2;
+                    unsigned int res = 0;                   // 0 pending, 1 accepted, 2 aborted, 3 leave the launch
+                    const long long t0 = clock64();
+                    for (;;) {
+                        const unsigned int hs = ctl->hs;
+                        if (hs == (mine | HS_ACCEPTED)) { res = 1; break; }
+                        if (hs != (mine | HS_SENT)) { res = 2; break; }
+                        if (!blocking) break;
+                        if (ctl->done[wk ^ 1u] == p.launch_id) {
+                            const unsigned int h2 = ctl->hs;
+                            if (h2 == (mine | HS_ACCEPTED)) res = 1; else if (h2 != (mine | HS_SENT)) res = 2; else res = 3;
+                            break;
+                        }
+                        if (clock64() - t0 > (1ll << 32)) { atomicOr(&p.counters[1], 2u); res = 3; break; }
+                    }
+                    if (res == 1) {
+                        S->role = SW_OWNER;
+                        if (S->pub_pending) { if (S->fstate == FS_PAYLOAD) publish(S->pub_start); S->pub_pending = 0; }
+                    } else if (res == 2) { S->role = SW_WAIT; S->pub_pending = 0; }
+                    red[120] = __uint_as_float(res);
+                }
+                __syncthreads();
+                const unsigned int res = __float_as_uint(red[120]);
+                __syncthreads();
+                if (res == 3) return true;
+                if (res == 1) role = SW_OWNER;
+                if (res == 2) { role = SW_WAIT; continue; }
+                return false;
+            }
+            // SW_WAIT: a hand-off, or the partner leaving the launch without one
+            if (t == 0) {
+                unsigned int res = 0;
+                const long long t0 = clock64();
+                for (;;) {
+                    unsigned int hs = ctl->hs;
+                    if ((hs & 3u) == HS_SENT) { res = hs >> 2; break; }
+                    if (ctl->done[wk ^ 1u] == p.launch_id) {
+                        hs = ctl->hs;
+                        if ((hs & 3u) == HS_SENT) res = hs >> 2;
+                        break;
+                    }
+                    if (clock64() - t0 > (1ll << 32)) { atomicOr(&p.counters[1], 2u); break; }
+                }
+                if (res) {
+                    __threadfence();
+                    const unsigned long long start = ctl->start;
+                    flex_reset();
+                    S->ring_head = 0;
+                    S->sample_index = start;
+                    S->detect_index = 0;
+                    S->role = SW_SPEC; S->my_seq = res; S->sent_seq = 0; S->verify = 0; S->pub_pending = 0;
+                    const unsigned long long rel = start - p.sample_base;
+                    red[121] = __uint_as_float(rel >= (unsigned long long)p.nsamples ? p.nsamples : (unsigned int)rel);
+                }
+                red[120] = __uint_as_float(res);
+            }
+            __syncthreads();
+            const unsigned int res = __float_as_uint(red[120]);
+            const unsigned int npos = __float_as_uint(red[121]);
+            __syncthreads();
+            if (!res) return true;
+            role = SW_SPEC;
+            pos = npos;
+            cp_async_wait_group<0>();        // restart the sample prefetch at the new position
+            fetched = pos & ~1u;
+            done_frontier = fetched;
+            prefetch(min(pos + PF, p.nsamples));
+            cp_async_wait_group<0>();
+            __syncthreads();
+            return false;
+        }
+    };
+
     // per-event registers; `pre` = this event's samples are already consumed, mixed and through the
     // first FFT pass (done by the previous payload event, see the pipelined tail of the RX path)
     bool pre = false;
@@ -300,6 +440,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         if (pos + NEED_MAX <= done_frontier) cp_async_wait_group<1>();
         else cp_async_wait_group<0>();
         __syncthreads();                     // staged samples + state of the previous event visible
+        if (duo && gate()) break;
         PH(0);
         // ---- advance to the next event (or to the end of this launch's samples)
         state = S->state;
@@ -681,7 +822,9 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         // frame goes on, a whole symbol is available, no debug tap)  Its samples must have landed.
         PH(11);
         const unsigned int take_now = (fstate == FS_PAYLOAD) ? min(p.M_data, mod_len - pstart) : 0u;
-        const bool pipe = (fstate == FS_PAYLOAD) && (pstart + take_now < mod_len) && (p.nsamples - pos >= W) && (p.tap_cap == 0);
+        // (a speculative worker must pass the loop-top gate before its last payload symbol)
+        const bool pipe = (fstate == FS_PAYLOAD) && (pstart + take_now < mod_len) && (p.nsamples - pos >= W) && (p.tap_cap == 0) &&
+                          !(role == SW_SPEC && pstart + take_now + p.M_data >= mod_len);
         if (pipe) {
             if (pos + W <= done_frontier) cp_async_wait_group<1>();
             else cp_async_wait_group<0>();
@@ -701,6 +844,9 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
             // ---- pipelined tail: the next symbol's samples are mixed and taken through the first FFT
             //      pass in the same stretch of code that derotates and demaps this symbol, so the two
             //      dependency chains interleave and the loop-top barrier + state reload disappear
+            // speculative worker: look at the hand-off word now, act on it at the end of the event
+            unsigned int hs_peek = 0;
+            if (duo && role == SW_SPEC && t == 0) hs_peek = ctl->hs;
             const uint32_t dth2 = __float_as_uint(red[116]);
             const uint32_t th2 = th + adv * dth;             // phase after this event's samples
             const unsigned int off2 = cp - p.backoff;
@@ -746,7 +892,17 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
 #undef B2_DEMAP
             }
             if (t == 0) S->payload_sym_idx = pstart + take_now;
+            if (duo && role == SW_SPEC && t == 0) {
+                unsigned int nr = SW_SPEC;
+                if (hs_peek == ((S->my_seq << 2) | HS_ACCEPTED)) {
+                    nr = SW_OWNER;
+                    S->role = SW_OWNER;
+                    if (S->pub_pending) { publish(S->pub_start); S->pub_pending = 0; }
+                }
+                red[122] = __uint_as_float(nr);
+            }
             __syncthreads();                 // first FFT exchange of the next event
+            if (duo && role == SW_SPEC) role = __float_as_uint(red[122]);
             PH(5);
             // the next event, as the loop top would have found it
 #pragma unroll
@@ -888,6 +1044,15 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
                             S->payload_enc_len = henc;
                             S->payload_mod_len = hmod;
                             S->fstate = FS_PAYLOAD;
+                            if (duo) {
+                                // the frame ends nps symbols from here; the partner's search starts one sample later
+                                const unsigned int nps = (hmod + p.M_data - 1) / p.M_data;
+                                if (nps >= 2) {
+                                    const unsigned long long start = S->sample_index + (unsigned long long)nps * W + 1ull;
+                                    if (role == SW_OWNER) publish(start);
+                                    else { S->pub_pending = 1; S->pub_start = start; }
+                                }
+                            }
                         }
                         red[114] = (float)valid;
                     }
@@ -898,6 +1063,20 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
         }
 
         PH(14);
+        if (emit && duo && role == SW_SPEC) {
+            // only an invalid header gets here (the gate settles the role before a last payload symbol): the record
+            // cannot wait, so either the hand-off has been settled by now or it is returned to the owner
+            if (t == 0) {
+                const unsigned int mine = S->my_seq << 2;
+                const unsigned int old = atomicCAS((unsigned int *)&ctl->hs, mine | HS_SENT, mine | HS_NONE);
+                const unsigned int nr = (old == (mine | HS_ACCEPTED)) ? SW_OWNER : SW_WAIT;
+                S->role = nr; S->pub_pending = 0;
+                red[123] = __uint_as_float(nr);
+            }
+            __syncthreads();
+            role = __float_as_uint(red[123]);
+            if (role == SW_WAIT) continue;   // loop top: barrier, then the gate waits for the next hand-off
+        }
         if (emit) {
             // append a frame record (+ the payload symbols) to the output of this launch; thread 0 reserves
             // the slots, one barrier publishes them together with every thread's symbol stores
@@ -951,6 +1130,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
             if (t == 0) {                    // the loop-top barrier orders this against everybody's next reads
                 flex_reset();
                 S->timer = (int)(M + cp);    // survives the reset, as in liquid
+                if (duo) { S->verify = S->sent_seq ? 1u : 0u; S->pub_pending = 0; }
             }
         }
     }
@@ -959,15 +1139,19 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync
     cp_async_wait_group<0>();
     __syncthreads();
     {
-        uint32_t * dst = (uint32_t *)(p.st + sidx);
+        uint32_t * dst = (uint32_t *)(p.st + vs);
         const uint32_t * src = (const uint32_t *)S;
         for (unsigned int i = t; i < sizeof(SyncState) / 4; i += T) dst[i] = src[i];
-        cf * gr = p.ring + (size_t)sidx * W;
+        cf * gr = p.ring + (size_t)vs * W;
         for (unsigned int i = t; i < W; i += T) gr[i] = hist[i];
-        cf * g0 = p.G0 + (size_t)sidx * M;
-        cf * gR = p.R + (size_t)sidx * M;
+        cf * g0 = p.G0 + (size_t)vs * M;
+        cf * gR = p.R + (size_t)vs * M;
 #pragma unroll
         for (unsigned int s = 0; s < 8; s++) { g0[t + s * T] = G0[t + s * T]; gR[t + s * T] = Rr[s]; }
+    }
+    if (duo && t == 0) {                     // the partner stops waiting for this worker
+        __threadfence();
+        ctl->done[wk] = p.launch_id;
     }
 }
 
@@ -983,13 +1167,34 @@ static cudaError_t sync8_launch_t(const SyncParams & p, size_t smem_bytes, cudaS
         if (e != cudaSuccess) return e;
         configured[dev] = smem_bytes;
     }
-    sync8_kernel<M><<<p.streams, M / 8, smem_bytes, st>>>(p);
+    sync8_kernel<M><<<p.streams * (p.workers == 2 ? 2u : 1u), M / 8, smem_bytes, st>>>(p);
     return cudaGetLastError();
 }
 
 size_t sync8_smem_bytes(const SyncParams & p) { return s8_layout(p.M, p.cp, p.M_pilot + p.M_data, p.M_pilot).total; }
 
 bool sync8_supported(unsigned int M) { return M == 256 || M == 512 || M == 1024 || M == 2048 || M == 4096; }
+
+template <unsigned int M>
+static int sync8_ctas_t(size_t smem)
+{
+    int nb = 0;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(sync8_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sync8_kernel<M>, (int)(M / 8), smem) != cudaSuccess) return 0;
+    return nb;
+}
+int sync8_ctas_per_sm(const SyncParams & p)
+{
+    const size_t smem = s8_layout(p.M, p.cp, p.M_pilot + p.M_data, p.M_pilot).total;
+    switch (p.M) {
+    case 256:  return sync8_ctas_t<256>(smem);
+    case 512:  return sync8_ctas_t<512>(smem);
+    case 1024: return sync8_ctas_t<1024>(smem);
+    case 2048: return sync8_ctas_t<2048>(smem);
+    case 4096: return sync8_ctas_t<4096>(smem);
+    default:   return 0;
+    }
+}
 
 cudaError_t sync8_launch(const SyncParams & p, cudaStream_t st)
 {
