@@ -78,7 +78,7 @@ struct SyncCore {
     // a batch = one collect(); its chunks run sync on `stream` and decode on `dstream`
     cudaStream_t dstream = nullptr;      // = dstreams[0]
     static const unsigned int NDS = 3;   // decode launches of successive chunks rotate over NDS streams (a conv-coded
-    cudaStream_t dstreams[3] = {nullptr, nullptr, nullptr};   // frame is a long serial recursion: chunks must overlap)
+    cudaStream_t dstreams[NDS] = {};     // frame is a long serial recursion: chunks must overlap)
     DevBuf d_range;                      // [chunks+1] record count after each chunk's synchroniser
     unsigned int range_cap = 0, chunk = 0, launches = 0;
     struct ChunkEv { cudaEvent_t s0, s1, d0, d1, x; };
@@ -376,7 +376,7 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
     PacketParams pp;
     pp.recs = d_recs.as<FrameRec>(); pp.aux = d_aux.as<FrameAux>(); pp.range = range;
     pp.arena = d_arena.as<uint8_t>(); pp.scratch = d_scratch.as<uint8_t>(); pp.decoded = d_decoded.as<uint8_t>();
-    // every decode stream has its own third of the Viterbi regions (launches on different streams overlap)
+    // every decode stream has its own share of the Viterbi regions (launches on different streams overlap)
     pp.vit_local_ctas = vit_ctas / NDS; pp.vit_local_steps = vit_steps;
     pp.vit_local = d_vit.as<uint2>() + (size_t)(chunk % NDS) * pp.vit_local_ctas * vit_steps;
     if (timing) B2_CUDA(cudaEventRecord(e.d0, ds));
@@ -570,7 +570,7 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
     int rc = B2_OK;
     do {
         // many channels: the synchroniser chains get their own SMs (smpart.cu); B2_SYNC_SMS sizes the set
-        cudaStream_t decode_streams[3] = {nullptr, nullptr, nullptr};
+        cudaStream_t decode_streams[SyncCore::NDS] = {};
         bool have_decode_streams = false;
         if (N >= 32 && sync8_supported(M) && K >= 64) {
             unsigned int want = 72;
@@ -582,7 +582,7 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
                 q->stream = q->part.big_stream[0];
                 q->sstream = q->part.small_stream;
                 // packet decode runs beside the channelizer (beside the synchronisers it disturbs the chains: measured)
-                decode_streams[0] = q->part.big_stream[1]; decode_streams[1] = q->part.big_stream[2]; decode_streams[2] = q->part.big_stream[3];
+                for (unsigned int i = 0; i < SyncCore::NDS; i++) decode_streams[i] = q->part.big_stream[1 + i];
                 have_decode_streams = true;
                 q->spare_stream = q->part.small_stream2;
             }

@@ -169,71 +169,109 @@ __device__ void golay2412_decode_block(const uint8_t * enc, uint8_t * dec, unsig
 // ------------------------------------------------------------------ conv r1/2 K=7 Viterbi (warp 0 of the CTA)
 // libfec metric (|expected - received| with hard bits as 0/255), start metrics 0 / 63,
 // predecessor with the oldest bit set wins only on strictly smaller metric, chain back from 0.
+//
+// Layout of the 64 path metrics over the warp: a lane keeps two states that differ in the newest bit
+// (slot = bit 0); the other five state bits select the lane through a rotation that advances with the
+// trellis step, lane = rotr5(state >> 1, t mod 5) after t steps.  With it the two predecessors j and
+// j + 32 of a pair of new states 2j, 2j + 1 sit in the same slot of two lanes that differ in one lane
+// bit, so a step costs ONE shuffle (the lanes swap the slot they do not work on) and the new pair stays
+// in the lane that computed it.  The traceback walks in the same rotated domain (see below).
+
 __device__ void viterbi27_decode(const uint8_t * enc, uint8_t * dec, unsigned int n, uint2 * decisions,
                                  uint2 * stage, unsigned int tid, bool in_smem)
 {
     const unsigned int nbits = 8 * n + 6;
     if (tid < 32) {
         const unsigned int L = tid;
-        // new states 2L (input bit 0) and 2L+1 (input bit 1) both come from old states L and L+32
-        // expected output pair for register value reg = (old << 1) | bit
-        unsigned int ex[4];
+        // expected output pair of branch j -> 2j of this lane's butterfly in each of the five phases, as
+        // (c1 << 1) | c0 (c0 from 0x6d, c1 from 0x4f: the order the streamed received pairs have below).  Both
+        // generators tap the newest and the oldest register bit, so the other three branches expect the
+        // complement (j -> 2j+1, j+32 -> 2j) or the same pair (j+32 -> 2j+1).
+        unsigned int exw[5];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            unsigned int old = (i & 2) ? L + 32 : L, bit = i & 1;
-            unsigned int reg = (old << 1) | bit;
-            ex[i] = ((__popc(reg & 0x6d) & 1) << 1) | (__popc(reg & 0x4f) & 1);
+        for (unsigned int tm = 0; tm < 5; tm++) {
+            const unsigned int lbv = (L >> (4u - tm)) & 1u;
+            unsigned int j = lbv;                                   // state bit 0 = the slot this lane works on
+#pragma unroll
+            for (unsigned int k = 1; k <= 4; k++) j |= ((L >> ((k - 1u + 5u - tm) % 5u)) & 1u) << k;
+            const unsigned int reg = j << 1;
+            exw[tm] = (((unsigned int)__popc(reg & 0x4f) & 1u) << 1) | ((unsigned int)__popc(reg & 0x6d) & 1u);
         }
-        unsigned int me = (L == 0) ? 0u : 63u, mo = 63u;      // metrics of states 2L, 2L+1
-        // received bit pairs come 16 per 32-bit word (the buffers are 16-byte aligned and padded), the
-        // next word is fetched while the current one is consumed: no memory latency inside the trellis
+        unsigned int me = (L == 0) ? 0u : 63u, mo = 63u;      // metrics of states 2L, 2L+1 (phase 0)
+        // received bit pairs come 16 per 32-bit word (the buffers are 16-byte aligned and padded).  A word is
+        // byte-swapped and bit-reversed once, after which pair q sits at bits 2q, 2q+1 as (r1 << 1) | r0 and the
+        // stream is consumed by shifting; the next word is fetched while the current one is consumed.
         const uint32_t * e32 = (const uint32_t *)enc;
-        uint32_t cur = e32[0];
-        for (unsigned int t0 = 0; t0 < nbits; t0 += 16) {
-            const uint32_t nxt = (t0 + 16 < nbits) ? e32[(t0 >> 4) + 1] : 0u;
-            const unsigned int kend = min(16u, nbits - t0);
-            for (unsigned int k = 0; k < kend; k++) {
-                const unsigned int byte = (cur >> (8 * (k >> 2))) & 0xffu;
-                const unsigned int r = (byte >> (6 - 2 * (k & 3))) & 3u;        // (r0 << 1) | r1
-                // old metrics of states L and L+32
-                unsigned int a_e = __shfl_sync(0xffffffffu, me, L >> 1), a_o = __shfl_sync(0xffffffffu, mo, L >> 1);
-                unsigned int b_e = __shfl_sync(0xffffffffu, me, 16 + (L >> 1)), b_o = __shfl_sync(0xffffffffu, mo, 16 + (L >> 1));
-                unsigned int m_lo = (L & 1) ? a_o : a_e;
-                unsigned int m_hi = (L & 1) ? b_o : b_e;
-                unsigned int m0 = m_lo + 255u * __popc(ex[0] ^ r), m1 = m_hi + 255u * __popc(ex[2] ^ r);
-                unsigned int d_e = m1 < m0;
-                unsigned int ne = d_e ? m1 : m0;
-                m0 = m_lo + 255u * __popc(ex[1] ^ r); m1 = m_hi + 255u * __popc(ex[3] ^ r);
-                unsigned int d_o = m1 < m0;
-                unsigned int no = d_o ? m1 : m0;
-                me = ne; mo = no;
-                unsigned int be = __ballot_sync(0xffffffffu, d_e), bo = __ballot_sync(0xffffffffu, d_o);
-                if (L == 0) decisions[t0 + k] = make_uint2(be, bo);
-            }
-            cur = nxt;
+        const unsigned int wmax = (2u * nbits + 31u) / 32u - 1u;             // last word that holds pairs
+        unsigned long long buf = __brev(__byte_perm(e32[0], 0u, 0x0123u));   // pairs not yet consumed, oldest at bit 0
+        unsigned int avail = 16, widx = 1;
+        uint32_t nxt = e32[min(1u, wmax)];
+        auto step = [&](const unsigned int tm, const unsigned int tt) {
+            const unsigned int r = (unsigned int)buf & 3u;
+            buf >>= 2;
+            const unsigned int lbv = (L >> (4u - tm)) & 1u;
+            const unsigned int recv = __shfl_xor_sync(0xffffffffu, lbv ? me : mo, 16u >> tm);
+            const unsigned int m_lo = lbv ? recv : me, m_hi = lbv ? mo : recv;
+            const unsigned int x = 255u * __popc(exw[tm] ^ r), y = 510u - x;
+            unsigned int m0 = m_lo + x, m1 = m_hi + y;
+            const unsigned int d_e = m1 < m0;
+            me = min(m0, m1);
+            m0 = m_lo + y; m1 = m_hi + x;
+            const unsigned int d_o = m1 < m0;
+            mo = min(m0, m1);
+            const unsigned int be = __ballot_sync(0xffffffffu, d_e), bo = __ballot_sync(0xffffffffu, d_o);
+            if (L == 0) decisions[tt] = make_uint2(be, bo);
+        };
+        unsigned int t0 = 0;
+        for (; t0 + 5 <= nbits; t0 += 5) {
+            // top the pair buffer up (branch-free: the trellis below is one dependent chain per warp)
+            const bool ref = avail < 5;
+            const unsigned long long add = (unsigned long long)__brev(__byte_perm(nxt, 0u, 0x0123u)) << (2u * avail);
+            buf |= ref ? add : 0ull;
+            avail += ref ? 16u : 0u;
+            widx += ref ? 1u : 0u;
+            const uint32_t ld = e32[min(widx, wmax)];
+            nxt = ref ? ld : nxt;
+            avail -= 5;
+#pragma unroll
+            for (unsigned int tm = 0; tm < 5; tm++) step(tm, t0 + tm);
+        }
+        if (t0 < nbits) {                    // fewer than five steps left
+            if (avail < 5) buf |= (unsigned long long)__brev(__byte_perm(nxt, 0u, 0x0123u)) << (2u * avail);
+#pragma unroll
+            for (unsigned int tm = 0; tm < 4; tm++)
+                if (t0 + tm < nbits) step(tm, t0 + tm);
         }
     }
     for (unsigned int i = tid; i < n; i += PK_THREADS) dec[i] = 0;
     __syncthreads();
-    // traceback in chunks staged through shared memory
-    __shared__ unsigned int tb_state;
-    if (tid == 0) tb_state = 0;
+    // traceback, in the rotated lane domain: the lane y of the current state stays in place from one step to
+    // the next except for ONE bit (position pb, advancing with the step) that is replaced by the decision bit,
+    // and the bit it replaces is the slot of the next (older) state.  Decoded bit of step t = slot.
+    // Decisions come in chunks staged through shared memory (or sit there already).
+    __shared__ unsigned int tb_state;                        // y | slot << 5 | pb << 6
+    if (tid == 0) tb_state = ((5u - nbits % 5u) % 5u) << 6;
+    auto tb_walk = [&](const uint2 * dsrc, unsigned int base, unsigned int hi_, unsigned int lo_) {
+        unsigned int y = tb_state & 31u, slot = (tb_state >> 5) & 1u, pb = tb_state >> 6, acc = 0;
+        for (unsigned int t = hi_; t-- > lo_;) {
+            acc |= slot << (7u - (t & 7u));
+            if ((t & 7u) == 0) {
+                if (t < 8 * n) dec[t >> 3] = (uint8_t)acc;
+                acc = 0;
+            }
+            const uint2 d = dsrc[t - base];
+            const unsigned int bit = ((slot ? d.y : d.x) >> y) & 1u;
+            const unsigned int old = (y >> pb) & 1u;
+            y = (y & ~(1u << pb)) | (bit << pb);
+            slot = old;
+            pb = (pb == 4u) ? 0u : pb + 1u;
+        }
+        tb_state = y | (slot << 5) | (pb << 6);
+    };
     unsigned int hi = nbits;
     if (in_smem) {
-        // the decisions already sit in shared memory: one walk, no staging
-        if (tid == 0) {
-            unsigned int s = 0, acc = 0;
-            for (unsigned int t = nbits; t-- > 0;) {
-                if (s & 1u) acc |= 0x80u >> (t & 7);
-                if ((t & 7) == 0) {
-                    if (t < 8 * n) dec[t >> 3] = (uint8_t)acc;
-                    acc = 0;
-                }
-                uint2 d = decisions[t];
-                unsigned int bit = (((s & 1u) ? d.y : d.x) >> (s >> 1)) & 1u;
-                s = (s >> 1) | (bit << 5);
-            }
-        }
+        __syncthreads();
+        if (tid == 0) tb_walk(decisions, 0, nbits, 0);       // one walk, no staging
         hi = 0;
     }
     while (hi > 0) {
@@ -241,22 +279,9 @@ __device__ void viterbi27_decode(const uint8_t * enc, uint8_t * dec, unsigned in
         __syncthreads();
         for (unsigned int i = lo + tid; i < hi; i += PK_THREADS) stage[i - lo] = decisions[i];
         __syncthreads();
-        if (tid == 0) {
-            // every `lo` is a multiple of 8, so a decoded byte never straddles two chunks; the flush bits
-            // (t >= 8n) of the first chunk carry no data
-            unsigned int s = tb_state, acc = 0;
-            for (unsigned int t = hi; t-- > lo;) {
-                if (s & 1u) acc |= 0x80u >> (t & 7);
-                if ((t & 7) == 0) {
-                    if (t < 8 * n) dec[t >> 3] = (uint8_t)acc;
-                    acc = 0;
-                }
-                uint2 d = stage[t - lo];
-                unsigned int bit = (((s & 1u) ? d.y : d.x) >> (s >> 1)) & 1u;
-                s = (s >> 1) | (bit << 5);
-            }
-            tb_state = s;
-        }
+        // every `lo` is a multiple of 8, so a decoded byte never straddles two chunks; the flush bits
+        // (t >= 8n) of the first chunk carry no data
+        if (tid == 0) tb_walk(stage, lo, hi, lo);
         hi = lo;
     }
     __syncthreads();

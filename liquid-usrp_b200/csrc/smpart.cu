@@ -70,23 +70,19 @@ bool sm_partition_create(SmPartition & sp, int device, unsigned int small_sms)
         if (getenv("B2_VERBOSE")) fprintf(stderr, "b200ofdm: SM partition %u (synchronisers) + %u (channelizer, decode)\n", gp.small_sms, gp.big_sms);
     }
     if (!gp.ok) return false;
-    CUstream s0 = nullptr, s1 = nullptr, s2 = nullptr, s3 = nullptr;
+    CUstream s0 = nullptr, s3 = nullptr;
     if (p_stream(&s0, gp.g_small, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
     if (p_stream(&s3, gp.g_small, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
-    if (p_stream(&s1, gp.g_big, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
-    if (p_stream(&s2, gp.g_big, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
-    CUstream s4 = nullptr, s5 = nullptr;
-    if (p_stream(&s4, gp.g_big, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
-    if (p_stream(&s5, gp.g_big, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
+    for (unsigned int i = 0; i < SmPartition::NBIG; i++) {
+        CUstream sb = nullptr;
+        if (p_stream(&sb, gp.g_big, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
+        sp.big_stream[i] = (cudaStream_t)sb;
+    }
     sp.ok = true;
     sp.small_sms = gp.small_sms;
     sp.big_sms = gp.big_sms;
     sp.small_stream = (cudaStream_t)s0;
     sp.small_stream2 = (cudaStream_t)s3;
-    sp.big_stream[0] = (cudaStream_t)s1;
-    sp.big_stream[1] = (cudaStream_t)s2;
-    sp.big_stream[2] = (cudaStream_t)s4;
-    sp.big_stream[3] = (cudaStream_t)s5;
     return true;
 }
 

@@ -9,7 +9,8 @@ struct SmPartition {
     unsigned int small_sms = 0, big_sms = 0;
     cudaStream_t small_stream = nullptr;         // synchroniser chains
     cudaStream_t small_stream2 = nullptr;        // a second stream on the same SM set
-    cudaStream_t big_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // channelizer, 3 x packet decode
+    static const unsigned int NBIG = 7;
+    cudaStream_t big_stream[NBIG] = {};          // channelizer, 6 x packet decode
 };
 // streams of a (cached, per device) partition with `small_sms` SMs in the small set; false when the
 // driver cannot partition (the caller then uses ordinary streams).  The caller destroys the streams.
