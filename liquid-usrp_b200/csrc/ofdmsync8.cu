@@ -50,7 +50,9 @@ __host__ __device__ static inline S8Layout s8_layout(unsigned int M, unsigned in
     L.SZ = 256;
     while (L.SZ < W + M / 2 + 64) L.SZ <<= 1;
     // two events deep where it is cheap (<= 32 KB): the newest prefetch group may then stay in flight
+#ifndef B2_S8_SHALLOW_RING
     if (L.SZ < 2 * W + M / 2 + 64 && L.SZ * 2 * sizeof(cf) <= 32768) L.SZ <<= 1;
+#endif
     size_t o = 0;
     L.off_st = o;   o += (sizeof(SyncState) + 15) & ~(size_t)15;
     L.off_red = o;  o += 160 * sizeof(float);
@@ -138,7 +140,10 @@ extern "C" int b2_debug_sync8_prof(unsigned long long * out, int reset)
 #endif
 
 template <unsigned int M>
-__global__ void __launch_bounds__(M / 8, (M <= 1024 ? 256 : 512) / (M / 8)) sync8_kernel(const SyncParams p)   // <= 255 registers at M = 512: 4 streams per SM
+#ifndef B2_S8_THREADS_PER_SM
+#define B2_S8_THREADS_PER_SM 256        // experiment knob: 448 = seven 64-thread chains per SM (<= 144 registers)
+#endif
+__global__ void __launch_bounds__(M / 8, (M <= 1024 ? B2_S8_THREADS_PER_SM : 512) / (M / 8)) sync8_kernel(const SyncParams p)   // <= 255 registers at M = 512: 4 streams per SM
 {
     constexpr unsigned int T = M / 8, NW = T / 32, M2 = M / 2;
     extern __shared__ __align__(16) unsigned char smem[];
