@@ -4,6 +4,7 @@ oracle -- the reference's lib/multichanneltx.cc / lib/multichannelrx.cc compiled
 Bars (BASELINE.json north_star): decoded payload bytes and frame detect/complete sample indices
 bit-exact; equalised symbols within 1e-5 relative (max |X_gpu - X_ref| / max |X_ref| per OFDM
 symbol); frame stats (evm/rssi in dB, cfo) to 1e-3."""
+import os
 import numpy as np
 import pytest
 
@@ -446,3 +447,43 @@ def test_two_devices_in_one_process():
     rs0, rs1 = pkg.MsResamp(np.float32(1.07), device=0), pkg.MsResamp(np.float32(1.07), device=1)
     assert np.array_equal(rs0.execute(x[:100000]), rs1.execute(x[:100000]))
     rs0.close(); rs1.close()
+
+
+def test_worker_pairs_under_corruption():
+    """frame-pipelined worker pairs of the register-resident synchroniser (two CTAs per channel on alternate
+    frames): long runs of back-to-back frames with OFDM symbols wiped at random places -- lost preambles, invalid
+    headers (the speculative worker has to return its hand-off), failed CRCs -- plus noise, fed in ragged calls.
+    Records must equal the oracle's, and the serial (one worker) configuration's."""
+    from b2 import pkg
+    rng = np.random.default_rng(21)
+    for case in ((8, 256, 32, 8, MOD_QPSK, FEC_NONE, FEC_HAMMING128, 150, 9, 0.02),
+                 (4, 512, 64, 16, MOD_QAM16, FEC_NONE, FEC_NONE, 400, 8, 0.01)):
+        N, M, cp, taper = case[:4]
+        K, W = 2 * N, M + cp
+        import orc
+        from test_oracle_loopback import frame_symbols
+        bps = {MOD_QPSK: 2, MOD_QAM16: 4}[case[4]]
+        nsym = frame_symbols(M, bps, orc.lib().orc_packetizer_enc_len(case[7], 6, case[5], case[6]))
+        x = make_input(case).copy()
+        # frame f of every channel starts near channel sample f * nsym * W: wipe parts of a header symbol, of a
+        # payload symbol, of a preamble symbol and of a last payload symbol (all channels at once)
+        for f, sym, frac in ((1, 3, 0.6), (3, 5, 0.5), (4, 1, 0.7), (6, 3, 0.9), (7, nsym - 1, 0.5)):
+            a = ((f * nsym + sym) * W + 13) * K
+            x[a:a + int(frac * W * K)] = 0
+        fo, po, _ = run_oracle(case, x)
+        assert len(fo) >= N * 3
+        assert int((fo["header_valid"] == 0).sum()) >= N and int((fo["payload_valid"] == 0).sum()) >= N
+        chunks, left = [], len(x)
+        while left:
+            c = int(min(left, rng.integers(1, 40000)))
+            chunks.append(c)
+            left -= c
+        for workers in ("2", "1"):
+            os.environ["B2_SYNC_WORKERS"] = workers
+            try:
+                fg, pg, _ = run_gpu(case, x)
+                assert_frames_equal(fo, po, fg, pg)
+                fg, pg, _ = run_gpu(case, x, chunks)
+                assert_frames_equal(fo, po, fg, pg)
+            finally:
+                os.environ.pop("B2_SYNC_WORKERS", None)
