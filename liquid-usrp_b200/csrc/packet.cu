@@ -253,18 +253,34 @@ __device__ void viterbi27_decode(const uint8_t * enc, uint8_t * dec, unsigned in
     if (tid == 0) tb_state = ((5u - nbits % 5u) % 5u) << 6;
     auto tb_walk = [&](const uint2 * dsrc, unsigned int base, unsigned int hi_, unsigned int lo_) {
         unsigned int y = tb_state & 31u, slot = (tb_state >> 5) & 1u, pb = tb_state >> 6, acc = 0;
-        for (unsigned int t = hi_; t-- > lo_;) {
-            acc |= slot << (7u - (t & 7u));
-            if ((t & 7u) == 0) {
-                if (t < 8 * n) dec[t >> 3] = (uint8_t)acc;
-                acc = 0;
-            }
-            const uint2 d = dsrc[t - base];
+        auto one = [&](const uint2 d) {
             const unsigned int bit = ((slot ? d.y : d.x) >> y) & 1u;
             const unsigned int old = (y >> pb) & 1u;
             y = (y & ~(1u << pb)) | (bit << pb);
             slot = old;
             pb = (pb == 4u) ? 0u : pb + 1u;
+        };
+        unsigned int t = hi_;
+        // down to a byte boundary (only the flush bits at the very end of a frame start off one)
+        while (t > lo_ && (t & 7u)) {
+            --t;
+            acc |= slot << (7u - (t & 7u));
+            one(dsrc[t - base]);
+        }
+        if (hi_ & 7u) { if (t < 8 * n && (t & 7u) == 0) dec[t >> 3] = (uint8_t)acc; }
+        // whole bytes: the eight decision words are fetched before the dependent walk through them
+        while (t > lo_) {
+            uint2 d[8];
+#pragma unroll
+            for (unsigned int k = 0; k < 8; k++) d[k] = dsrc[t - 1u - k - base];
+            acc = 0;
+#pragma unroll
+            for (unsigned int k = 0; k < 8; k++) {
+                acc |= slot << k;               // step t-1-k carries bit 7 - ((t-1-k) & 7) = k of its byte
+                one(d[k]);
+            }
+            t -= 8;
+            if (t < 8 * n) dec[t >> 3] = (uint8_t)acc;
         }
         tb_state = y | (slot << 5) | (pb << 6);
     };
