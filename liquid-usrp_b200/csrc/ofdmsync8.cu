@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? B2_S8_THREADS_PER_SM : 512
         }
         fetched = pos & ~1u;
         done_frontier = fetched;
-        prefetch(min(pos + PF, p.nsamples));
+        if (role != SW_WAIT) prefetch(min(pos + PF, p.nsamples));     // a waiting worker learns its position with the hand-off
     }
 #ifdef B2_SYNC_PROF
     long long t_last = clock64();
@@ -328,8 +328,10 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? B2_S8_THREADS_PER_SM : 512
     auto gate = [&]() -> bool {
         for (;;) {
             if (role == SW_OWNER) {
-                if (S->verify && !(S->state == ST_SEEK && S->timer == (int)(M + cp))) {
+                const bool settle = S->verify && !(S->state == ST_SEEK && S->timer == (int)(M + cp));
+                if (settle) {
                     // the seek event after my frame has run: settle the hand-off I published
+                    __syncthreads();         // everybody has read the flags thread 0 is about to change
                     if (t == 0) {
                         const unsigned int w0 = (S->sent_seq << 2) | HS_SENT;
                         unsigned int nr = SW_OWNER;
@@ -418,6 +420,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? B2_S8_THREADS_PER_SM : 512
             role = SW_SPEC;
             pos = npos;
             cp_async_wait_group<0>();        // restart the sample prefetch at the new position
+            __syncthreads();                 // (ring slots change hands between the lanes of the issuing warp)
             fetched = pos & ~1u;
             done_frontier = fetched;
             prefetch(min(pos + PF, p.nsamples));

@@ -20,3 +20,17 @@ rx.close()
 assert len(fg) == len(fo) == 2 * N, (len(fg), len(fo))
 assert np.array_equal(po, pg)
 print("sanitize case ok:", len(fg), "frames")
+# a conv-coded shape: Viterbi decode, worker pairs of the M = 256 synchroniser (one warp per worker)
+N, M, cp, taper, plen = 8, 256, 32, 8, 200
+tx = refmc.McTx(L, N, M, cp, taper)
+x = tx.run((M + cp) * 60, plen, refmc.MOD_QAM16, refmc.FEC_CONV_V27, refmc.FEC_NONE, max_frames=3, gain=1.0 / N)
+tx.close()
+orx = refmc.McRx(L, N, M, cp, taper); orx.execute(x); fo, po = orx.frames(); orx.close()
+rx = pkg.MultichannelRx(N, M, cp, taper, device=0)
+h = len(x) // 3 + 5
+rx.execute(x[:h]); rx.execute(x[h:])
+fg, pg = rx.poll()
+rx.close()
+assert len(fg) == len(fo) == 3 * N, (len(fg), len(fo))
+assert np.array_equal(po, pg) and int(fg["payload_valid"].min()) == 1
+print("sanitize case 2 ok:", len(fg), "frames")
