@@ -172,11 +172,15 @@ def test_chunking_invariance_of_the_production_kernels():
         assert_frames_equal(fo, po, fg, pg)
 
 
-def test_reset_mid_stream_matches_oracle():
-    case = CASES["c2_8ch_h128"]
+@pytest.mark.parametrize("name,frac", [("c2_8ch_h128", 0.34), ("c5_shape_32ch_qam64", 0.3), ("c5_shape_32ch_qam64", 0.62),
+                                       ("c3_16ch_qam16_v27", 0.45)])
+def test_reset_mid_stream_matches_oracle(name, frac):
+    """Reset() in the middle of a stream, also in the middle of a frame and with the register-resident
+    synchroniser's worker pairs in whatever roles they happen to hold (the M >= 256 cases)"""
+    case = CASES[name]
     N, M, cp, taper = case[:4]
     x = make_input(case)
-    cut = len(x) // 3 + 5
+    cut = int(len(x) * frac) + 5
     from b2 import pkg
     rx = McRx(ref_lib(), N, M, cp, taper)
     rx.execute(x[:cut]); rx.reset(); rx.execute(x[cut:])
