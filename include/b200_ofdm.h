@@ -185,6 +185,7 @@ int b2_msresamp_create(float rate, float As, int device, b2_msresamp ** out);
 int b2_msresamp_destroy(b2_msresamp * q);
 int b2_msresamp_reset(b2_msresamp * q);
 int b2_msresamp_execute(b2_msresamp * q, const float * x_host, size_t nx, float * y_host, size_t y_cap, size_t * ny);
+/* device pointers: the whole call is one kernel launch over the caller's buffers (nx < 2^31) */
 int b2_msresamp_execute_device(b2_msresamp * q, const float * x_dev, size_t nx, float * y_dev, size_t y_cap, size_t * ny);
 /* host samples in, device samples out (feeds b2_mcrx_execute_device / b2_ofdmsync_execute_device) */
 int b2_msresamp_execute_to_device(b2_msresamp * q, const float * x_host, size_t nx, float * y_dev, size_t y_cap, size_t * ny);
