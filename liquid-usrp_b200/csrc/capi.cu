@@ -573,7 +573,10 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
         cudaStream_t decode_streams[SyncCore::NDS] = {};
         bool have_decode_streams = false;
         if (N >= 32 && sync8_supported(M) && K >= 64) {
-            unsigned int want = 72;
+            // one scheduler per chain warp is all a chain can use (both workers of a pair counted); beyond that the
+            // SMs serve the channelizer and the packet decoder better.  72 = measured optimum of the 256 x 512 shape.
+            const unsigned int chain_warps = 2u * N * std::max(1u, M / 256u);
+            unsigned int want = std::min(72u, std::max(8u, ((chain_warps + 3) / 4 + 7) / 8 * 8));
             if (const char * e = getenv("B2_SYNC_SMS")) { long v = atol(e); if (v >= 8 && v <= 136) want = (unsigned int)v; }
             // every chain must be resident at once (a chain that waits for an SM stalls the pipeline):
             // the synchroniser kernel fits 4 CTAs of M/8 <= 64 threads per SM

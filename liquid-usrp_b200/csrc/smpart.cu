@@ -30,7 +30,7 @@ template <typename F> static bool entry(const char * name, F & fn)
 }
 
 struct GreenPair { bool tried = false, ok = false; unsigned int req = 0, small_sms = 0, big_sms = 0; CUgreenCtx g_small = nullptr, g_big = nullptr; };
-static GreenPair g_pairs[16];
+static GreenPair g_pairs[16][12];         // per device, one pair per requested size (sizes are multiples of 8)
 
 bool sm_partition_create(SmPartition & sp, int device, unsigned int small_sms)
 {
@@ -38,8 +38,12 @@ bool sm_partition_create(SmPartition & sp, int device, unsigned int small_sms)
     if (getenv("B2_NO_SM_PARTITION") || device < 0 || device >= 16) return false;
     CUresult (*p_stream)(CUstream *, CUgreenCtx, unsigned int, int) = nullptr;
     if (!entry("cuGreenCtxStreamCreate", p_stream)) return false;
-    GreenPair & gp = g_pairs[device];
-    if (!gp.tried || gp.req != small_sms) {
+    GreenPair * slot = nullptr;
+    for (auto & g : g_pairs[device]) if (g.tried && g.req == small_sms) { slot = &g; break; }
+    if (!slot) for (auto & g : g_pairs[device]) if (!g.tried) { slot = &g; break; }
+    if (!slot) return false;                             // more distinct sizes than this table holds: no partition
+    GreenPair & gp = *slot;
+    if (!gp.tried) {
         // (re)build the pair of green contexts of this device; they live as long as the process
         gp = GreenPair();
         gp.tried = true; gp.req = small_sms;
