@@ -35,6 +35,10 @@ struct SyncCore {
     // state
     DevBuf d_st, d_ring, d_G0, d_R, d_penc, d_ctl;
     unsigned int workers = 1;            // 2: frame-pipelined worker pairs (ofdmsync8.cu)
+    // frame-parallel warp-per-worker kernel (ofdmsyncw.cu): wslots workers (slots) per stream
+    bool use_w = false;
+    unsigned int wslots = 1, wrec_stride = 0;
+    DevBuf d_wst, d_wch, d_wRG, d_wrecs, d_waux;
     unsigned int sm_budget = 0;          // SMs the synchroniser kernel may use (0: the whole device); set before init()
     unsigned int launch_id = 0;
     unsigned long long stream_pos = 0;   // samples per stream given to the synchroniser so far
@@ -169,17 +173,39 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
             if (2ll * streams <= cap) workers = 2;
         }
     }
-    const size_t vstreams = (size_t)streams * workers;
+    // the frame-parallel kernel takes the shapes it is built for unless told otherwise (B2_SYNC_LEGACY=1: the
+    // serial-chain kernels of round 1)
+    use_w = syncw_supported(M) && plan.M_pilot + plan.M_data >= 5 && getenv("B2_SYNC_LEGACY") == nullptr && getenv("B2_SYNC_GENERIC") == nullptr;
+    if (use_w) {
+        workers = 1;
+        // enough warps to fill the machine about twice (16 per SM), at most 16 per stream
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        unsigned int k = (unsigned int)((2u * 16u * (unsigned int)sms + streams - 1) / streams);
+        k = std::max(1u, std::min(16u, k));
+        if (const char * e = getenv("B2_SYNC_K")) { int v = atoi(e); if (v >= 1 && v <= 64) k = (unsigned int)v; }
+        wslots = k;
+    }
+    const size_t vstreams = (size_t)streams * (use_w ? wslots : workers);
     B2_TRY(d_st.alloc(sizeof(SyncState) * vstreams)); B2_TRY(d_ring.alloc(sizeof(cf) * W * vstreams));
     B2_TRY(d_G0.alloc(sizeof(cf) * M * vstreams)); B2_TRY(d_R.alloc(sizeof(cf) * M * vstreams));
     B2_TRY(d_penc.alloc(penc_cap * vstreams));
     B2_TRY(d_ctl.alloc(sizeof(SyncCtl) * streams));
+    if (use_w) {
+        wrec_stride = (unsigned int)(tmax / (2 * W)) + 2 * wslots + 4;
+        B2_TRY(d_wst.alloc(sizeof(WSync) * vstreams)); B2_TRY(d_wch.alloc(sizeof(WChan) * streams));
+        B2_TRY(d_wRG.alloc(sizeof(cf) * M * vstreams));
+        B2_TRY(d_wrecs.alloc(sizeof(FrameRec) * (size_t)wrec_stride * streams)); B2_TRY(d_waux.alloc(sizeof(FrameAux) * (size_t)wrec_stride * streams));
+    }
     // outputs: a frame needs at least 4 OFDM symbols; payload bits <= 8 per sample
     recs_cap = (unsigned int)(streams * (tmax / (2 * W) + 4));
     // arena of a batch: the symbols demapped inside the batch (<= one byte per sample) plus, per stream, one
     // frame that began in earlier batches and completes in this one (bounded here to 32 KB of symbol bytes;
     // B2_ERR_OVERFLOW reports a frame that does not fit)
     arena_cap = (unsigned long long)streams * (tmax + 64 + std::min<size_t>(penc_cap, 32768)) + 16ull * recs_cap;
+    // (frame-parallel kernel: a stretch whose prediction failed is demapped twice, once speculatively and once by
+    // the stitcher, and the speculative copy's arena space is simply left unused)
+    if (use_w && wslots > 1) arena_cap *= 2;
     B2_TRY(d_recs.alloc(sizeof(FrameRec) * recs_cap)); B2_TRY(d_aux.alloc(sizeof(FrameAux) * recs_cap));
     B2_TRY(d_arena.alloc(arena_cap)); B2_TRY(d_scratch.alloc(arena_cap)); B2_TRY(d_decoded.alloc(arena_cap));
     B2_TRY(d_counters.alloc(8 * sizeof(unsigned int)));
@@ -225,6 +251,8 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     sp.fft.radices = 0;
     for (unsigned int i = 0; i < fftM.npass; i++) sp.fft.radices |= fft_radix_code(fftM.radix[i]) << (4 * i);
     sp.fft.perm = t_perm.as<uint16_t>(); sp.fft.tw = t_tw.as<cf>();
+    sp.wst = d_wst.as<WSync>(); sp.wch = d_wch.as<WChan>(); sp.wRG = d_wRG.as<cf>();
+    sp.wrecs = d_wrecs.as<FrameRec>(); sp.waux = d_waux.as<FrameAux>(); sp.wrec_stride = wrec_stride; sp.wslots = wslots;
     sync_smem = sync_smem_bytes(sp);
     const bool fast_sync = sync8_supported(M) && plan.M_pilot + plan.M_data >= 5 && getenv("B2_SYNC_GENERIC") == nullptr;
     if (fast_sync) sync_smem = sync8_smem_bytes(sp);          // the kernel sync_launch() will pick
@@ -265,6 +293,18 @@ int SyncCore::reset_state()
         st[i].role = (workers == 2 && (i & 1)) ? SW_WAIT : SW_OWNER;
     }
     stream_pos = 0;
+    if (use_w) {
+        // every slot zero (state SEEK = 0, timer 0, nothing mixed); head slot 0; prediction = the idle seek grid
+        std::vector<WChan> wc(streams);
+        memset(wc.data(), 0, sizeof(WChan) * streams);
+        for (auto & c : wc) { c.pred_next[0] = c.pred_next[1] = plan.M; c.pred_period[0] = c.pred_period[1] = plan.M; }
+        B2_CUDA(cudaMemsetAsync(d_wst.p, 0, d_wst.bytes, stream));
+        B2_CUDA(cudaMemcpyAsync(d_wch.p, wc.data(), sizeof(WChan) * streams, cudaMemcpyHostToDevice, stream));
+        B2_CUDA(cudaMemsetAsync(d_wRG.p, 0, d_wRG.bytes, stream));
+        B2_CUDA(cudaMemsetAsync(d_ring.p, 0, d_ring.bytes, stream));
+        B2_CUDA(cudaStreamSynchronize(stream));
+        return B2_OK;
+    }
     B2_CUDA(cudaMemcpyAsync(d_st.p, st.data(), sizeof(SyncState) * st.size(), cudaMemcpyHostToDevice, stream));
     B2_CUDA(cudaMemsetAsync(d_ctl.p, 0, d_ctl.bytes, stream));
     B2_CUDA(cudaMemsetAsync(d_ring.p, 0, d_ring.bytes, stream));
@@ -309,7 +349,8 @@ int SyncCore::poll_view(const b2_frame_rec ** recs, size_t * n_recs, const uint8
 
 int SyncCore::reset_streams()
 {
-    B2_CUDA(sync_reset_launch(d_st.as<SyncState>(), streams, workers, d_ctl.as<SyncCtl>(), stream_pos, stream));
+    if (use_w) B2_CUDA(syncw_reset_launch(d_wst.as<WSync>(), d_wch.as<WChan>(), streams, wslots, plan.M, stream_pos, stream));
+    else B2_CUDA(sync_reset_launch(d_st.as<SyncState>(), streams, workers, d_ctl.as<SyncCtl>(), stream_pos, stream));
     B2_CUDA(cudaStreamSynchronize(stream));
     return B2_OK;
 }
@@ -365,7 +406,13 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
     q.tap_cap = tap_cap;
     q.tap_X = d_tapX.as<cf>(); q.tap_chan = d_tapc.as<uint32_t>(); q.tap_index = d_tapi.as<unsigned long long>();
     if (timing) B2_CUDA(cudaEventRecord(e.s0, stream));
-    B2_CUDA(sync_launch(q, sync_threads, sync_smem, stream));
+    if (use_w) {
+        // workers of this launch: a stretch should hold a few OFDM symbols at least; the debug tap wants the
+        // symbols of the serial chain only (speculative workers would tap symbols that are thrown away)
+        const unsigned int W = plan.M + plan.cp;
+        q.workers = tap_cap ? 1u : std::max(1u, std::min(wslots, nsamples / (4u * W)));
+        B2_CUDA(syncw_launch(q, stream));
+    } else B2_CUDA(sync_launch(q, sync_threads, sync_smem, stream));
     RangeMark * range = d_range.as<RangeMark>() + chunk;
     B2_CUDA(record_mark_launch(d_counters.as<unsigned int>(), range + 1, stream));
     B2_CUDA(cudaMemcpyAsync(h_range + chunk + 1, range + 1, sizeof(RangeMark), cudaMemcpyDeviceToHost, stream));
@@ -572,7 +619,9 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
         // many channels: the synchroniser chains get their own SMs (smpart.cu); B2_SYNC_SMS sizes the set
         cudaStream_t decode_streams[SyncCore::NDS] = {};
         bool have_decode_streams = false;
-        if (N >= 32 && sync8_supported(M) && K >= 64) {
+        // (the frame-parallel synchroniser is a throughput kernel like the channelizer: the two simply share the machine)
+        const bool wk = syncw_supported(M) && getenv("B2_SYNC_LEGACY") == nullptr && getenv("B2_SYNC_GENERIC") == nullptr;
+        if (N >= 32 && sync8_supported(M) && K >= 64 && (!wk || getenv("B2_SM_PARTITION") != nullptr)) {
             // one scheduler per chain warp is all a chain can use (both workers of a pair counted); beyond that the
             // SMs serve the channelizer and the packet decoder better.  72 = measured optimum of the 256 x 512 shape.
             const unsigned int chain_warps = 2u * N * std::max(1u, M / 256u);

@@ -74,6 +74,51 @@ struct SyncCtl {                // per chain, global memory
     unsigned int pad;
 };
 
+// ---- frame-parallel synchroniser (ofdmsyncw.cu): one WARP per worker, `workers` workers per stream and launch.
+// Worker 0 carries the stream's true state on from the previous launch; workers 1.. start at PREDICTED positions
+// of the stream (see WChan) in the canonical state ofdmflexframesync is in right after a seek event that detected
+// nothing (state SEEK, timer 0, everything else reset).  A worker runs up to the next worker's start; if it gets
+// there in exactly that canonical state the next worker's results are the serial chain's, else the last worker of
+// the stream to finish (the "stitcher") redoes the rest serially from the true state.  Nobody waits for anybody.
+struct WSync {                  // per worker slot, global memory; the stream's carried state lives in slot WChan::head
+    int32_t  state, timer;
+    uint32_t num_symbols;
+    uint32_t nco_theta, nco_dtheta;      // phase of the next sample / step
+    float    g0;
+    float    s_hat0_re, s_hat0_im;
+    float    phi_prime, p1_prime;
+    uint32_t pilot_pos;
+    int32_t  fstate;
+    uint32_t header_sym_idx, payload_sym_idx;
+    float    evm_hat, evm_db;
+    uint32_t ms_payload, bps_payload, payload_len, check, fec0, fec1;
+    uint32_t payload_enc_len, payload_mod_len;
+    // The kernel keeps no sample window: an event's FFT window is re-read from the raw stream and re-mixed.  Samples
+    // [mix_start, mix_end) were pushed through the NCO; mix_end == ~0: the segment is open and follows the running
+    // NCO (phase of sample i = nco_theta + (i - sample_index) * nco_dtheta), else it is closed (frame over, NCO
+    // reset) and sample i had phase q_theta - (mix_end - i) * q_dtheta.  Everything else was pushed unmixed.
+    uint32_t q_theta, q_dtheta;
+    uint64_t sample_index;               // index of the next sample to be pushed
+    uint64_t detect_index;
+    uint64_t mix_start, mix_end;
+    // summary of the last launch (read by the stitcher)
+    uint64_t b_last, b_prev;             // sample_index right after the last two frame ends (+1: after the seek event
+                                         // liquid runs on the first sample behind a frame)
+    uint32_t nb;                         // frame ends seen in the launch (saturates at 2)
+    uint32_t matched;                    // reached its limit in the canonical state
+    uint32_t nrec, pad;                  // records in the worker's private list
+    uint8_t  header_bits[36];
+    uint8_t  header_dec[20];
+};
+struct WChan {                  // per stream, global memory.  [launch_id & 1] is read by a launch, the other entry
+                                // written by its stitcher (a warp that starts late must still see what its launch began with)
+    uint64_t pred_next[2];      // predicted canonical positions: pred_next + j * pred_period
+    uint32_t pred_period[2];    // 0: no prediction (one worker)
+    uint32_t head[2];           // slot holding the stream's carried state
+    uint64_t b_last, b_prev;    // last two frame-end positions of the stream (stitcher only)
+    uint32_t done, pad;         // workers of the running launch that have finished
+};
+
 struct FrameRec {               // same layout as b2_frame_rec (include/b200_ofdm.h)
     uint32_t channel;
     int32_t  header_valid, payload_valid;
@@ -136,6 +181,13 @@ struct SyncParams {
     cf * tap_X; uint32_t * tap_chan; unsigned long long * tap_index; unsigned int tap_cap;
     SyncTables tb;
     FftDev fft;                 // M-point plan
+    // frame-parallel kernel (ofdmsyncw.cu); workers = workers of this launch (<= wslots), ring = the M + cp raw
+    // samples before in[..][0], penc / wRG indexed by stream * wslots + slot
+    WSync * wst;                // [streams][wslots]
+    WChan * wch;                // [streams]
+    cf * wRG;                   // [streams][wslots][M] equaliser taps (state RX) / S0a gains (state S0B)
+    FrameRec * wrecs; FrameAux * waux;   // private record lists of the speculative workers, [streams][wrec_stride]
+    unsigned int wrec_stride, wslots;
 };
 size_t sync_smem_bytes(const SyncParams & p);
 cudaError_t sync_configure(size_t smem_bytes);
@@ -149,6 +201,12 @@ size_t sync8_smem_bytes(const SyncParams & p);
 cudaError_t sync8_launch(const SyncParams & p, cudaStream_t st);
 // CTAs of the kernel that fit one SM (both workers of every stream must be resident at once)
 int sync8_ctas_per_sm(const SyncParams & p);
+// frame-parallel warp-per-worker kernel (ofdmsyncw.cu), M in {256, 512}
+bool syncw_supported(unsigned int M);
+cudaError_t syncw_launch(const SyncParams & p, cudaStream_t st);
+// ofdmflexframesync_reset on every stream (state of slot `head`; prediction restarts from the idle seek grid)
+cudaError_t syncw_reset_launch(WSync * wst, WChan * wch, unsigned int streams, unsigned int wslots, unsigned int M,
+                               unsigned long long sample_base, cudaStream_t st);
 
 // ------------------------------------------------------------------ packet decode
 // de-interleave + FEC decode + CRC of every completed frame (liquid packetizer_decode, called

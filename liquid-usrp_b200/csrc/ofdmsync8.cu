@@ -77,54 +77,6 @@ __device__ __forceinline__ void cp_async16(void * dst_smem, const void * src_gme
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NKEEP> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(NKEEP) : "memory"); }
 
-// atan2 for the pilot phases: minimax odd polynomial on [0, 1] (|err| < 1e-7 rad), one
-// approximate division; quadrant handling as atan2f (the arguments are never both zero here)
-__device__ __forceinline__ float atan2_fast(float y, float x)
-{
-    const float ax = fabsf(x), ay = fabsf(y);
-    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float a = __fdividef(mn, mx);
-    const float s = a * a;
-    float r = fmaf(s, 0.002456609858199954f, -0.01440086867660284f);
-    r = fmaf(r, s, 0.03978036344051361f);
-    r = fmaf(r, s, -0.07234777510166168f);
-    r = fmaf(r, s, 0.10498903691768646f);
-    r = fmaf(r, s, -0.14161217212677002f);
-    r = fmaf(r, s, 0.19985905289649963f);
-    r = fmaf(r, s, -0.33332598209381104f);
-    r = fmaf(r, s, 0.9999998807907104f);
-    r *= a;
-    if (ay > ax) r = 1.57079637f - r;
-    if (x < 0.f) r = 3.14159274f - r;
-    return copysignf(r, y);
-}
-
-// nco_constrain_dev for |theta| < 2 pi (the NCO trims): p - floor(p) is p or p + 1 there
-__device__ __forceinline__ uint32_t nco_constrain_small(float theta)
-{
-    const double p = (double)theta * 0.15915494309189535;
-    const double f = p < 0.0 ? p + 1.0 : p;
-    return (uint32_t)(__double2ull_rn(f * 4294967296.0) & 0xffffffffull);
-}
-
-// hard demapper with the constellation known at compile time (same decisions as demod_symbol)
-template <int MB> __device__ __forceinline__ unsigned int demod_axis_t(float v, float alpha)
-{
-    unsigned int s = 0;
-#pragma unroll
-    for (int k = MB - 1; k >= 0; k--) {
-        const float ref = (float)(1u << k) * alpha;
-        const bool pos = v > 0;
-        s = (s << 1) | (pos ? 1u : 0u);
-        v += pos ? -ref : ref;
-    }
-    return s ^ (s >> 1);
-}
-template <int MB> __device__ __forceinline__ unsigned int demod_qam_t(cf x, float alpha)
-{
-    return (demod_axis_t<MB>(x.x, alpha) << MB) + demod_axis_t<MB>(x.y, alpha);
-}
-
 // optional phase profile (build with -DB2_SYNC_PROF): cycles spent by CTA 0 between marks
 #ifdef B2_SYNC_PROF
 __device__ unsigned long long g_sync8_prof[16];

@@ -181,6 +181,54 @@ __device__ __forceinline__ void solve5(const double * __restrict__ S, const doub
     for (int i = 0; i < 5; i++) coef[i] = p[i];
 }
 
+// atan2 for the pilot phases: minimax odd polynomial on [0, 1] (|err| < 1e-7 rad), one
+// approximate division; quadrant handling as atan2f (the arguments are never both zero here)
+__device__ __forceinline__ float atan2_fast(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = __fdividef(mn, mx);
+    const float s = a * a;
+    float r = fmaf(s, 0.002456609858199954f, -0.01440086867660284f);
+    r = fmaf(r, s, 0.03978036344051361f);
+    r = fmaf(r, s, -0.07234777510166168f);
+    r = fmaf(r, s, 0.10498903691768646f);
+    r = fmaf(r, s, -0.14161217212677002f);
+    r = fmaf(r, s, 0.19985905289649963f);
+    r = fmaf(r, s, -0.33332598209381104f);
+    r = fmaf(r, s, 0.9999998807907104f);
+    r *= a;
+    if (ay > ax) r = 1.57079637f - r;
+    if (x < 0.f) r = 3.14159274f - r;
+    return copysignf(r, y);
+}
+
+// nco_constrain_dev for |theta| < 2 pi (the NCO trims): p - floor(p) is p or p + 1 there
+__device__ __forceinline__ uint32_t nco_constrain_small(float theta)
+{
+    const double p = (double)theta * 0.15915494309189535;
+    const double f = p < 0.0 ? p + 1.0 : p;
+    return (uint32_t)(__double2ull_rn(f * 4294967296.0) & 0xffffffffull);
+}
+
+// hard demapper with the constellation known at compile time (same decisions as demod_symbol)
+template <int MB> __device__ __forceinline__ unsigned int demod_axis_t(float v, float alpha)
+{
+    unsigned int s = 0;
+#pragma unroll
+    for (int k = MB - 1; k >= 0; k--) {
+        const float ref = (float)(1u << k) * alpha;
+        const bool pos = v > 0;
+        s = (s << 1) | (pos ? 1u : 0u);
+        v += pos ? -ref : ref;
+    }
+    return s ^ (s >> 1);
+}
+template <int MB> __device__ __forceinline__ unsigned int demod_qam_t(cf x, float alpha)
+{
+    return (demod_axis_t<MB>(x.x, alpha) << MB) + demod_axis_t<MB>(x.y, alpha);
+}
+
 // CRC-32 with a 16-entry nibble table (frame header: 14 bytes)
 static __constant__ uint32_t b2_crc_nibble_table[16] = {
     0x00000000u, 0x1DB71064u, 0x3B6E20C8u, 0x26D930ACu, 0x76DC4190u, 0x6B6B51F4u, 0x4DB26158u, 0x5005713Cu,
