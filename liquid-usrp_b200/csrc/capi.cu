@@ -48,6 +48,7 @@ struct SyncCore {
     unsigned int vit_ctas = 0, vit_steps = 16384;     // per-CTA Viterbi decision regions of the general decode kernel
     unsigned int recs_cap = 0;
     unsigned long long arena_cap = 0;
+    unsigned long long out_cap = 0;      // bytes of decoded payload per batch (= arena_cap for the serial-chain kernels)
     // tap
     DevBuf d_tapX, d_tapc, d_tapi;
     unsigned int tap_cap = 0;
@@ -178,18 +179,19 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     use_w = syncw_supported(M) && plan.M_pilot + plan.M_data >= 5 && getenv("B2_SYNC_LEGACY") == nullptr && getenv("B2_SYNC_GENERIC") == nullptr;
     if (use_w) {
         workers = 1;
-        // enough warps to fill the machine about twice (16 per SM), at most 16 per stream
+        // slots for about eight waves of 16 warps per SM (a launch uses as many as its samples are worth)
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        unsigned int k = (unsigned int)((2u * 16u * (unsigned int)sms + streams - 1) / streams);
-        k = std::max(1u, std::min(16u, k));
+        unsigned int k = (unsigned int)((8u * 16u * (unsigned int)sms + streams - 1) / streams);
+        k = std::max(1u, std::min(128u, k));
         if (const char * e = getenv("B2_SYNC_K")) { int v = atoi(e); if (v >= 1 && v <= 64) k = (unsigned int)v; }
         wslots = k;
     }
     const size_t vstreams = (size_t)streams * (use_w ? wslots : workers);
     B2_TRY(d_st.alloc(sizeof(SyncState) * vstreams)); B2_TRY(d_ring.alloc(sizeof(cf) * W * vstreams));
     B2_TRY(d_G0.alloc(sizeof(cf) * M * vstreams)); B2_TRY(d_R.alloc(sizeof(cf) * M * vstreams));
-    B2_TRY(d_penc.alloc(penc_cap * vstreams));
+    // (the frame-parallel kernel demaps straight into the arena)
+    B2_TRY(d_penc.alloc(use_w ? 16 : penc_cap * vstreams));
     B2_TRY(d_ctl.alloc(sizeof(SyncCtl) * streams));
     if (use_w) {
         wrec_stride = (unsigned int)(tmax / (2 * W)) + 2 * wslots + 4;
@@ -205,13 +207,19 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     arena_cap = (unsigned long long)streams * (tmax + 64 + std::min<size_t>(penc_cap, 32768)) + 16ull * recs_cap;
     // (frame-parallel kernel: a stretch whose prediction failed is demapped twice, once speculatively and once by
     // the stitcher, and the speculative copy's arena space is simply left unused)
-    if (use_w && wslots > 1) arena_cap *= 2;
+    out_cap = arena_cap;
+    if (use_w) {
+        // the arena is a ring of demapped symbols that outlives batches: what a batch demaps (twice: see above), the
+        // frames in progress, and room for any single legal frame
+        out_cap = arena_cap * (wslots > 1 ? 2 : 1);
+        arena_cap = std::max<unsigned long long>(2 * arena_cap, 4ull * penc_cap) & ~15ull;
+    }
     B2_TRY(d_recs.alloc(sizeof(FrameRec) * recs_cap)); B2_TRY(d_aux.alloc(sizeof(FrameAux) * recs_cap));
-    B2_TRY(d_arena.alloc(arena_cap)); B2_TRY(d_scratch.alloc(arena_cap)); B2_TRY(d_decoded.alloc(arena_cap));
+    B2_TRY(d_arena.alloc(arena_cap)); B2_TRY(d_scratch.alloc(arena_cap)); B2_TRY(d_decoded.alloc(out_cap));
     B2_TRY(d_counters.alloc(8 * sizeof(unsigned int)));
     B2_CUDA(cudaMallocHost(&h_counters, 8 * sizeof(unsigned int)));
     B2_CUDA(cudaMallocHost(&h_recs, sizeof(FrameRec) * recs_cap));
-    B2_CUDA(cudaMallocHost(&h_payload, arena_cap));
+    B2_CUDA(cudaMallocHost(&h_payload, out_cap));
     for (int i = 0; i < 5; i++) B2_CUDA(cudaEventCreate(&ev[i]));
     for (unsigned int i = 0; i < NDS; i++) {
         if (decode_st) dstreams[i] = decode_st[i];
@@ -241,7 +249,7 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     sp.st = d_st.as<SyncState>(); sp.ring = d_ring.as<cf>(); sp.G0 = d_G0.as<cf>(); sp.R = d_R.as<cf>();
     sp.penc = d_penc.as<uint8_t>(); sp.penc_cap = penc_cap;
     sp.recs = d_recs.as<FrameRec>(); sp.aux = d_aux.as<FrameAux>(); sp.recs_cap = recs_cap;
-    sp.arena = d_arena.as<uint8_t>(); sp.arena_cap = arena_cap;
+    sp.arena = d_arena.as<uint8_t>(); sp.arena_cap = arena_cap; sp.decoded_cap = out_cap;
     sp.counters = d_counters.as<unsigned int>();
     sp.tb.sctype = t_sctype.as<uint8_t>(); sp.tb.S0 = t_S0.as<float>(); sp.tb.S1 = t_S1.as<float>();
     sp.tb.data_idx = t_data.as<uint16_t>(); sp.tb.pilot_idx = t_pilot.as<uint16_t>(); sp.tb.pilot_x = t_pilotx.as<float>();
@@ -298,6 +306,7 @@ int SyncCore::reset_state()
         std::vector<WChan> wc(streams);
         memset(wc.data(), 0, sizeof(WChan) * streams);
         for (auto & c : wc) { c.pred_next[0] = c.pred_next[1] = plan.M; c.pred_period[0] = c.pred_period[1] = plan.M; }
+        B2_CUDA(cudaMemsetAsync(d_counters.p, 0, d_counters.bytes, stream));      // incl. the ring's allocation counter
         B2_CUDA(cudaMemsetAsync(d_wst.p, 0, d_wst.bytes, stream));
         B2_CUDA(cudaMemcpyAsync(d_wch.p, wc.data(), sizeof(WChan) * streams, cudaMemcpyHostToDevice, stream));
         B2_CUDA(cudaMemsetAsync(d_wRG.p, 0, d_wRG.bytes, stream));
@@ -378,7 +387,11 @@ int SyncCore::run(const cf * in, size_t in_stride, unsigned int nsamples, bool r
 int SyncCore::begin_batch()
 {
     compact_pending();                       // h_payload is about to be overwritten
-    B2_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(unsigned int), stream));
+    if (use_w) {
+        // [2..3] is the allocation counter of the symbol ring: it keeps counting across batches
+        B2_CUDA(cudaMemsetAsync(d_counters.p, 0, 2 * sizeof(unsigned int), stream));
+        B2_CUDA(cudaMemsetAsync(d_counters.as<unsigned int>() + 4, 0, 4 * sizeof(unsigned int), stream));
+    } else B2_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(unsigned int), stream));
     B2_CUDA(cudaMemsetAsync(d_range.p, 0, sizeof(RangeMark), stream));
     memset(&h_range[0], 0, sizeof(RangeMark));
     chunk = 0; launches = 0;
@@ -414,7 +427,7 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
         B2_CUDA(syncw_launch(q, stream));
     } else B2_CUDA(sync_launch(q, sync_threads, sync_smem, stream));
     RangeMark * range = d_range.as<RangeMark>() + chunk;
-    B2_CUDA(record_mark_launch(d_counters.as<unsigned int>(), range + 1, stream));
+    B2_CUDA(record_mark_launch(d_counters.as<unsigned int>(), range + 1, stream, use_w ? 6 : 2));
     B2_CUDA(cudaMemcpyAsync(h_range + chunk + 1, range + 1, sizeof(RangeMark), cudaMemcpyDeviceToHost, stream));
     B2_CUDA(cudaEventRecord(e.s1, stream));
     // decode of this chunk runs beside the synchroniser of the next one
@@ -459,7 +472,7 @@ int SyncCore::end_batch()
         if (c < chunk) {
             B2_CUDA(cudaEventSynchronize(cev[c].d1));
             const unsigned int lo = std::min(h_range[c].nrec, recs_cap), hi = std::min(h_range[c + 1].nrec, recs_cap);
-            const unsigned long long ulo = std::min(h_range[c].arena_used, arena_cap), uhi = std::min(h_range[c + 1].arena_used, arena_cap);
+            const unsigned long long ulo = std::min(h_range[c].arena_used, out_cap), uhi = std::min(h_range[c + 1].arena_used, out_cap);
             if (hi > lo) B2_CUDA(cudaMemcpyAsync(h_recs + lo, d_recs.as<FrameRec>() + lo, sizeof(FrameRec) * (hi - lo), cudaMemcpyDeviceToHost, xstream));
             if (uhi > ulo) B2_CUDA(cudaMemcpyAsync(h_payload + ulo, d_decoded.as<uint8_t>() + ulo, uhi - ulo, cudaMemcpyDeviceToHost, xstream));
             B2_CUDA(cudaEventRecord(cev[c].x, xstream));
@@ -472,7 +485,7 @@ int SyncCore::end_batch()
         }
     }
 
-    last_used = std::min(h_range[chunk].arena_used, arena_cap);
+    last_used = std::min(h_range[chunk].arena_used, out_cap);
     rc = collect();
     timing_stale = true;                     // the per-kernel sums are computed when somebody asks (fetch_timing)
     return rc;

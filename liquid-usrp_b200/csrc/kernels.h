@@ -98,6 +98,10 @@ struct WSync {                  // per worker slot, global memory; the stream's 
     // NCO (phase of sample i = nco_theta + (i - sample_index) * nco_dtheta), else it is closed (frame over, NCO
     // reset) and sample i had phase q_theta - (mix_end - i) * q_dtheta.  Everything else was pushed unmixed.
     uint32_t q_theta, q_dtheta;
+    // payload symbols of the frame in progress go straight into the arena, a RING that outlives launches and
+    // batches: sym_abs = value of the allocation counter the frame got (~0: it did not fit, the frame will be
+    // reported without payload), sym_off = the same position inside the ring
+    uint64_t sym_abs, sym_off;
     uint64_t sample_index;               // index of the next sample to be pushed
     uint64_t detect_index;
     uint64_t mix_start, mix_end;
@@ -134,6 +138,7 @@ struct FrameAux {               // device-only companion of FrameRec
     uint32_t enc_len;           // encoded payload bytes
     uint32_t sym_bps;           // 0: the arena holds the enc_len packed bytes; else it holds the
                                 // ceil(8*enc_len/sym_bps) demapped symbols, one per byte
+    uint64_t sym_off;           // where in the arena (FrameRec::payload_offset is where the DECODED payload goes)
 };
 
 struct SyncTables {             // read-only, global memory
@@ -176,7 +181,10 @@ struct SyncParams {
     // outputs
     FrameRec * recs; FrameAux * aux; unsigned int recs_cap;
     uint8_t * arena; unsigned long long arena_cap;
-    unsigned int * counters;    // [0] n_recs, [1] overflow flag, [2..3] arena bytes (u64), [4] n_tap
+    unsigned long long decoded_cap;      // bytes of decoded payload a batch may produce (ofdmsyncw.cu)
+    unsigned int * counters;    // [0] n_recs, [1] overflow flag, [2..3] arena bytes (u64), [4] n_tap,
+                                // [6..7] decoded-payload bytes (u64; ofdmsyncw.cu, where [2..3] is the ring's
+                                // allocation counter and is never reset)
     // debug tap
     cf * tap_X; uint32_t * tap_chan; unsigned long long * tap_index; unsigned int tap_cap;
     SyncTables tb;
@@ -228,7 +236,7 @@ struct PacketParams {
 cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t st);
 // mark_out = {counters[0], counters[2..3]} (records / arena bytes so far), one thread; runs between
 // the synchroniser of a chunk and its decode so that chunk c decodes records [mark[c], mark[c+1])
-cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_out, cudaStream_t st);
+cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_out, cudaStream_t st, int used_at = 2);
 
 } // namespace b2
 

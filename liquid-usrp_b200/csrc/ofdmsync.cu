@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
                     r.complete_index = S->sample_index - 1;
                     r.payload_offset = offb;
                     p.recs[slot] = r;
-                    FrameAux a; a.enc_len = e2; a.sym_bps = 0;
+                    FrameAux a; a.enc_len = e2; a.sym_bps = 0; a.sym_off = offb;
                     p.aux[slot] = a;
                     red[115] = 1.f;
                     dsum[30] = __longlong_as_double((long long)offb);

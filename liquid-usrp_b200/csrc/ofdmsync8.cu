@@ -1073,7 +1073,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? B2_S8_THREADS_PER_SM : 512
                     r.complete_index = S->sample_index - 1;
                     r.payload_offset = offb;
                     p.recs[slot] = r;
-                    FrameAux a; a.enc_len = e2; a.sym_bps = (emit == 2) ? S->bps_payload : 0u;
+                    FrameAux a; a.enc_len = e2; a.sym_bps = (emit == 2) ? S->bps_payload : 0u; a.sym_off = offb;
                     p.aux[slot] = a;
                     red[115] = 1.f;
                     dsum[16 * 10 + 2] = __longlong_as_double((long long)offb);

@@ -37,6 +37,7 @@
 #include "fec.cuh"
 #include "syncdev.cuh"
 #include "fft8.cuh"
+#include <cstdlib>
 
 namespace b2 {
 
@@ -48,7 +49,7 @@ __host__ __device__ static inline SWLayout sw_layout(unsigned int M, unsigned in
     SWLayout L;
     L.twt_bytes = ((size_t)f8_twt_elems(M, 1) * sizeof(cf) + 15) & ~(size_t)15;
     size_t o = 0;
-    L.off_f = o;  o += (size_t)M * sizeof(cf);            // FFT exchange buffer; Gs / yph between transforms
+    L.off_f = o;  o += (size_t)(M + M / 8) * sizeof(cf);  // FFT exchange buffer (skewed); Gs / yph between transforms
     L.off_rg = o; o += (size_t)M * sizeof(cf);            // equaliser taps R (state RX) / S0a gains (state S0B)
     L.off_yc = o; o += ((size_t)(Mp + 4) * sizeof(cf) + 15) & ~(size_t)15;
     L.off_ws = o; o += (sizeof(WSync) + 15) & ~(size_t)15;
@@ -58,6 +59,26 @@ __host__ __device__ static inline SWLayout sw_layout(unsigned int M, unsigned in
     return L;
 }
 
+// Exchange between two radix-8 passes through a SKEWED buffer, element x at x + (x >> 3): the scattered stores of a
+// pass (element b0 + q Ns, q < 8) and the strided loads of the next one (element j + s N/8) are then both one base
+// address per virtual thread plus compile-time offsets, and both are bank-conflict free for a warp of consecutive j
+// (Ns = 1: 9 j + q; Ns = 8: 9 (j - k) + k + 9 q; loads: j + (j >> 3) + s (N/8 + N/64)).
+template <unsigned int N, unsigned int Ns>
+__device__ __forceinline__ void fw_store(const cf (&v)[8], unsigned int j, cf * __restrict__ buf)
+{
+    static_assert(Ns == 1 || Ns % 8 == 0, "radix-8 passes only");
+    const unsigned int k = j & (Ns - 1), b0 = (j - k) * 8 + k;
+    cf * dst = buf + (b0 + (b0 >> 3));
+#pragma unroll
+    for (unsigned int q = 0; q < 8; q++) dst[q * (Ns + Ns / 8)] = v[q];
+}
+template <unsigned int N>
+__device__ __forceinline__ void fw_load(cf (&v)[8], unsigned int j, const cf * __restrict__ buf)
+{
+    const cf * src = buf + (j + (j >> 3));
+#pragma unroll
+    for (unsigned int s = 0; s < 8; s++) v[s] = src[s * (N / 8 + N / 64)];
+}
 // passes of the M-point transform from Ns on, VT virtual threads (lane + 32 vt) per lane
 template <unsigned int N, unsigned int Ns, unsigned int VT>
 __device__ __forceinline__ void fw_run(cf (&v)[VT][8], unsigned int lane, cf * __restrict__ buf, const cf * __restrict__ twt)
@@ -66,11 +87,12 @@ __device__ __forceinline__ void fw_run(cf (&v)[VT][8], unsigned int lane, cf * _
 #pragma unroll
     for (unsigned int vt = 0; vt < VT; vt++) f8_pass<N, Ns, R, -1>(v[vt], lane + 32 * vt, nullptr, nullptr, twt);
     if constexpr (Ns * R < N) {
+        static_assert(R == 8, "only the last pass may have a smaller radix");
 #pragma unroll
-        for (unsigned int vt = 0; vt < VT; vt++) f8_store<N, Ns, R>(v[vt], lane + 32 * vt, buf);
+        for (unsigned int vt = 0; vt < VT; vt++) fw_store<N, Ns>(v[vt], lane + 32 * vt, buf);
         __syncwarp();
 #pragma unroll
-        for (unsigned int vt = 0; vt < VT; vt++) f8_load<N>(v[vt], lane + 32 * vt, buf);
+        for (unsigned int vt = 0; vt < VT; vt++) fw_load<N>(v[vt], lane + 32 * vt, buf);
         __syncwarp();
         fw_run<N, Ns * R, VT>(v, lane, buf, twt + (Ns > 1 ? (R - 1) * Ns : 0));
     }
@@ -84,9 +106,17 @@ __device__ __forceinline__ unsigned long long shfl0(unsigned long long v) { retu
     _Pragma("unroll") for (unsigned int vt = 0; vt < VT; vt++)             \
     _Pragma("unroll") for (unsigned int s = 0; s < 8; s++)
 #define B2W_I (lane + 32u * vt + T * s)
+// the W samples behind the current window (the next symbol's window, or the next seek window) into L1: one 128-byte
+// line per lane and instruction
+#define B2W_PREFETCH_NEXT                                                                                     \
+    if (rel0 + (long long)(2 * M + cp) <= (long long)p.nsamples) {                                            \
+        const char * pf = (const char *)(in + rel0 + M) + 128u * lane;                                        \
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));                                                   \
+        if (4096u + 128u * lane < W * 8u) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 4096));          \
+    }
 
-template <unsigned int M, unsigned int WPC>
-__global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_kernel(const SyncParams p)
+template <unsigned int M, unsigned int WPC, unsigned int MINB>
+__global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams p)
 {
     constexpr unsigned int VT = M / 256, T = M / 8, M2 = M / 2;
     constexpr unsigned long long OPEN = ~0ull;
@@ -122,7 +152,7 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
     if (p.workers > 1 && period >= 64u) {
         first = C->pred_next[par];
         if (first <= E0) first += ((E0 - first) / period + 1ull) * period;
-        if (first + M <= E1) J = (unsigned int)((E1 - M - first) / period) + 1u;
+        if (first + M <= E1) J = (unsigned int)min((E1 - M - first) / period + 1ull, (unsigned long long)(1u << 24));
     }
     const unsigned int n_act = min(p.workers, J + 1u);
     if (w >= n_act) return;
@@ -130,7 +160,7 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
     auto start_of = [&](unsigned int ww) -> unsigned long long {
         if (ww == 0) return E0;
         if (ww >= n_act) return OPEN;
-        return first + (unsigned long long)(((unsigned long long)ww * (J + 1u)) / n_act - 1ull) * period;
+        return first + (unsigned long long)((ww * (J + 1u)) / n_act - 1u) * period;      // ww < 64, J <= 2^24
     };
     auto slot_of = [&](unsigned int ww) -> unsigned int { return ch * p.wslots + (head + ww) % p.wslots; };
     // private record list of speculative worker ww: disjoint regions of the stream's list (a record needs > 2 W samples)
@@ -145,23 +175,15 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
     const cf * in = p.in + (size_t)ch * p.in_stride;
     const cf * ring = p.ring + (size_t)ch * W;
 
-    // ---- per-lane constants: role / rank of own subcarriers, packed two per register
-    unsigned int rkp[VT][4];
-#pragma unroll
-    for (unsigned int vt = 0; vt < VT; vt++)
-#pragma unroll
-        for (unsigned int s = 0; s < 8; s += 2) {
-            const unsigned int a = __ldg(&p.tb.sc_rank[lane + 32u * vt + T * s]), b = __ldg(&p.tb.sc_rank[lane + 32u * vt + T * (s + 1)]);
-            rkp[vt][s >> 1] = a | (b << 16);
-        }
-#define B2W_RK ((rkp[vt][s >> 1] >> (16u * (s & 1u))) & 0xffffu)
+    // role / rank of own subcarriers: read where they are used (64-byte rows of an L1-resident table)
+#define B2W_RK ((unsigned int)__ldg(&p.tb.sc_rank[B2W_I]))
 
     // ---- hot state in registers (identical in every lane), the rest in S
     int state = ST_SEEK, timer = 0, fstate = FS_HEADER;
     unsigned int num_symbols = 0, th = 0, dth = 0, pilot_pos = 0, hstart = 0, pstart = 0, bps = 0, ms = 0, mod_len = 0;
     unsigned int q_th = 0, q_dth = 0, nb = 0;
     float g0 = 1.f, sh0r = 0.f, sh0i = 0.f, phi_prime = 0.f, p1_prime = 0.f, evm_hat = 0.f;
-    unsigned long long sidx = 0, mix_start = 0, mix_end = 0, b_last = 0, b_prev = 0;
+    unsigned long long sidx = 0, mix_start = 0, mix_end = 0, b_last = 0, b_prev = 0, sym_abs = 0, sym_off = 0;
     unsigned int nrec_priv = 0;
 
     auto load_state = [&](unsigned int slot) {
@@ -175,7 +197,7 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
         hstart = S->header_sym_idx; pstart = S->payload_sym_idx; bps = S->bps_payload; ms = S->ms_payload; mod_len = S->payload_mod_len;
         q_th = S->q_theta; q_dth = S->q_dtheta;
         g0 = S->g0; sh0r = S->s_hat0_re; sh0i = S->s_hat0_im; phi_prime = S->phi_prime; p1_prime = S->p1_prime; evm_hat = S->evm_hat;
-        sidx = S->sample_index; mix_start = S->mix_start; mix_end = S->mix_end;
+        sidx = S->sample_index; mix_start = S->mix_start; mix_end = S->mix_end; sym_abs = S->sym_abs; sym_off = S->sym_off;
         nb = 0; b_last = 0; b_prev = 0; nrec_priv = 0;
         if (state == ST_RX || state == ST_S0B) {
             const cf * g = p.wRG + (size_t)slot * M;
@@ -191,7 +213,7 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
         state = ST_SEEK; timer = 0; fstate = FS_HEADER;
         num_symbols = 0; th = 0; dth = 0; pilot_pos = 0; hstart = 0; pstart = 0; bps = 0; ms = 0; mod_len = 0; q_th = 0; q_dth = 0;
         g0 = 1.f; sh0r = 0.f; sh0i = 0.f; phi_prime = 0.f; p1_prime = 0.f; evm_hat = 0.f;
-        sidx = at; mix_start = 0; mix_end = 0; nb = 0; b_last = 0; b_prev = 0; nrec_priv = 0;
+        sidx = at; mix_start = 0; mix_end = 0; nb = 0; b_last = 0; b_prev = 0; nrec_priv = 0; sym_abs = 0; sym_off = 0;
     };
     auto save_state = [&](unsigned int slot, unsigned int matched) {
         __syncwarp();
@@ -201,7 +223,7 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
             S->header_sym_idx = hstart; S->payload_sym_idx = pstart; S->bps_payload = bps; S->ms_payload = ms; S->payload_mod_len = mod_len;
             S->q_theta = q_th; S->q_dtheta = q_dth;
             S->g0 = g0; S->s_hat0_re = sh0r; S->s_hat0_im = sh0i; S->phi_prime = phi_prime; S->p1_prime = p1_prime; S->evm_hat = evm_hat;
-            S->sample_index = sidx; S->mix_start = mix_start; S->mix_end = mix_end;
+            S->sample_index = sidx; S->mix_start = mix_start; S->mix_end = mix_end; S->sym_abs = sym_abs; S->sym_off = sym_off;
             S->b_last = b_last; S->b_prev = b_prev; S->nb = nb; S->matched = matched; S->nrec = nrec_priv;
         }
         __syncwarp();
@@ -227,7 +249,6 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
     const unsigned int pbase_w = priv_base(w), pcap_w = priv_cap(w);
 
     for (;;) {
-        uint8_t * penc = p.penc + (size_t)slot_of(cur) * p.penc_cap;
         unsigned int matched = 0;
         // ================================================================ event loop of one stretch
         for (;;) {
@@ -255,23 +276,30 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
                 const bool all_mixed = any_mixed && ((long long)(mix_start - ws) <= 0) && (open || (long long)(mix_end - ws) >= (long long)M);
                 const unsigned int d0 = (unsigned int)(ws - (open ? sidx : mix_end));
                 if (rel0 >= 0 && all_mixed) {
-                    const cf * src = in + rel0;
+                    const cf * src = in + rel0 + lane;
+                    const unsigned int ph0 = r_th + (d0 + lane) * r_dth, ph32 = 32u * r_dth;
                     B2W_FORPTS {
-                        const unsigned int i = B2W_I;
-                        v[vt][s] = mix_down(__ldg(src + i), nco_cexp_fast(r_th + (d0 + i) * r_dth));
+                        const unsigned int q = vt + VT * s;
+                        v[vt][s] = mix_down(__ldg(src + 32u * q), nco_cexp_fast(ph0 + q * ph32));
                     }
+                    // the samples behind this window (the next symbol's, or the next seek window): into L1 now
+                    B2W_PREFETCH_NEXT
                 } else if (rel0 >= 0 && !any_mixed) {
-                    const cf * src = in + rel0;
-                    B2W_FORPTS { v[vt][s] = __ldg(src + B2W_I); }
+                    const cf * src = in + rel0 + lane;
+                    B2W_FORPTS { v[vt][s] = __ldg(src + 32u * (vt + VT * s)); }
+                    B2W_PREFETCH_NEXT
                 } else {
                     const long long m0 = (long long)(mix_start - ws), m1 = open ? (long long)M : (long long)(mix_end - ws);
-                    B2W_FORPTS {
-                        const unsigned int i = B2W_I;
+#pragma unroll 4
+                    for (unsigned int q = 0; q < 8 * VT; q++) {
+                        const unsigned int i = lane + 32u * q;
                         const long long r = rel0 + (long long)i;
                         cf x = (r >= 0) ? __ldg(in + r) : __ldcg(ring + ((long long)W + r));
                         if (any_mixed && (long long)i >= m0 && (long long)i < m1) x = mix_down(x, nco_cexp_fast(r_th + (d0 + i) * r_dth));
-                        v[vt][s] = x;
+                        fbuf[i] = x;
                     }
+                    __syncwarp();
+                    B2W_FORPTS { v[vt][s] = fbuf[B2W_I]; }
                 }
             }
             // ---- advance to the event
@@ -530,8 +558,10 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
                 int emit = 0;                      // 1: header invalid, 2: payload complete
                 if (fstate == FS_PAYLOAD) {
                     // demap; the symbols leave one per byte (packet.cu packs them into the encoded bytes)
-                    const unsigned int take = min(p.M_data, mod_len - pstart);
-                    uint8_t * dst = penc + pstart;
+                    // (a frame that did not fit the arena is walked through without storing anything: take = 0 below)
+                    const unsigned int take_all = min(p.M_data, mod_len - pstart);
+                    const unsigned int take = (sym_abs == ~0ull) ? 0u : take_all;
+                    uint8_t * dst = p.arena + sym_off + pstart;
                     const float alpha = p.qam_alpha[bps];
 #define B2W_DEMAP(EXPR)                                                                  \
                     B2W_FORPTS {                                                         \
@@ -545,7 +575,7 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
                     else if (bps == 8) { B2W_DEMAP(demod_qam_t<4>(x, alpha)) }
                     else { B2W_DEMAP(demod_qam_t<1>(x, alpha)) }
 #undef B2W_DEMAP
-                    pstart += take;
+                    pstart += take_all;
                     if (pstart == mod_len) emit = 2;
                 } else {
                     // header: BPSK, 288 symbols; EVM is measured on them (framesyncstats_s.evm)
@@ -609,7 +639,6 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
                             if (valid) {
                                 henc = dev_fec_enc_len(fec1, dev_fec_enc_len(fec0, plen + (check == 6 ? 4 : 0)));
                                 hmod = (8 * henc + hbps - 1) / hbps;
-                                if (hmod > p.penc_cap) valid = 0;         // cannot happen with penc_cap at its default
                             }
                             if (valid) {
                                 S->payload_len = plen; S->check = check; S->fec0 = fec0; S->fec1 = fec1;
@@ -621,6 +650,21 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
                         if (hres[0]) {
                             ms = hres[1]; bps = hres[2]; mod_len = hres[3];
                             fstate = FS_PAYLOAD;
+                            // room for the payload symbols in the arena ring (one byte per symbol, never across the ring's end)
+                            {
+                                const unsigned long long len = ((unsigned long long)mod_len + 15ull) & ~15ull;
+                                unsigned long long a = 0, ph = 0;
+                                if (lane == 0 && len) {
+                                    if (len > p.arena_cap / 2) { a = ~0ull; atomicOr(&p.counters[1], 8u); }
+                                    else {
+                                        do {
+                                            a = atomicAdd((unsigned long long *)(p.counters + 2), len);
+                                            ph = a % p.arena_cap;
+                                        } while (ph + len > p.arena_cap);
+                                    }
+                                }
+                                sym_abs = shfl0(a); sym_off = shfl0(ph);
+                            }
                             // a frame without payload symbols is complete with its header (liquid would wait for ever)
                             if (mod_len == 0) emit = 2;
                         } else emit = 1;
@@ -629,27 +673,35 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
                 }
 
                 if (emit) {
-                    // ---- append a frame record (+ the payload symbols)
+                    // ---- append a frame record; the payload symbols are in the arena already
                     const unsigned int m2 = (emit == 2) ? mod_len : 0u;      // symbols, one byte each
-                    unsigned int slot = 0, ok = 1;
-                    unsigned long long offb = 0;
+                    const bool stored = m2 && sym_abs != ~0ull;
                     if (lane == 0) {
-                        if (m2) offb = atomicAdd((unsigned long long *)(p.counters + 2), (unsigned long long)((m2 + 15u) & ~15u));
+                        unsigned int slot = 0, ok = 1;
+                        unsigned long long offd = 0;
+                        const unsigned int plen = (emit == 2 && (stored || !m2)) ? S->payload_len : 0u;
+                        if (stored) {
+                            // decoded payload (+ CRC) of this launch's frames: contiguous, in completion order per worker
+                            offd = atomicAdd((unsigned long long *)(p.counters + 6), (unsigned long long)((plen + 4u + 15u) & ~15u));
+                            if (offd + ((plen + 4u + 15u) & ~15u) > p.decoded_cap) ok = 0;
+                            // the ring must not have come round to this frame's symbols
+                            const unsigned long long now = *(volatile unsigned long long *)(p.counters + 2);
+                            if (now - sym_abs > p.arena_cap - (((unsigned long long)m2 + 15ull) & ~15ull)) ok = 0;
+                        }
                         if (direct) {
                             slot = atomicAdd(&p.counters[0], 1u);
-                            ok = slot < p.recs_cap;
+                            if (slot >= p.recs_cap) ok = 0;
                         } else {
                             slot = nrec_priv;
-                            ok = slot < pcap_w;
+                            if (slot >= pcap_w) ok = 0;
                         }
-                        if (m2 && offb + ((m2 + 15u) & ~15u) > p.arena_cap) ok = 0;
                         if (!ok) atomicOr(&p.counters[1], 1u);
                         else {
                             FrameRec r;
                             r.channel = ch;
                             r.header_valid = (emit == 2);
                             r.payload_valid = 0;
-                            r.payload_len = (emit == 2) ? S->payload_len : 0u;
+                            r.payload_len = plen;
                             for (int i = 0; i < 8; i++) r.header[i] = S->header_dec[i];
                             r.evm = S->evm_db;
                             r.rssi = -10.0f * log10f(g0);
@@ -661,22 +713,17 @@ __global__ void __launch_bounds__(WPC * 32, (M <= 256 ? 16 : 16) / WPC) syncw_ke
                             r.fec1 = (emit == 2) ? S->fec1 : 0u;
                             r.detect_index = S->detect_index;
                             r.complete_index = sidx - 1;
-                            r.payload_offset = offb;
-                            FrameAux a; a.enc_len = (emit == 2) ? S->payload_enc_len : 0u; a.sym_bps = (emit == 2) ? bps : 0u;
+                            r.payload_offset = offd;
+                            FrameAux a;
+                            a.enc_len = stored ? S->payload_enc_len : 0u;
+                            a.sym_bps = stored ? bps : ((emit == 2 && m2) ? 0xffffffffu : 0u);    // 0xffffffff: payload not stored (too large)
+                            a.sym_off = sym_off;
                             if (direct) { p.recs[slot] = r; p.aux[slot] = a; }
                             else { p.wrecs[pbase_w + slot] = r; p.waux[pbase_w + slot] = a; }
                         }
+                        if (!direct && ok) nrec_priv++;
                     }
-                    ok = shfl0(ok);
-                    offb = shfl0(offb);
-                    if (!direct && ok) nrec_priv++;
-                    __syncwarp();
-                    if (m2 && ok) {
-                        // (through L2: earlier symbols of the frame may have been written by another SM's warp)
-                        uint4 * dst = (uint4 *)(p.arena + offb);
-                        const uint4 * src = (const uint4 *)penc;
-                        for (unsigned int i = lane; i < (m2 + 15) / 16; i += 32) dst[i] = __ldcg(src + i);
-                    }
+                    nrec_priv = shfl0(nrec_priv);
                     // ofdmflexframesync_reset; the symbol timer survives it, as in liquid
                     __syncwarp();
                     if (lane < 9) ((uint32_t *)S->header_bits)[lane] = 0u;
@@ -828,32 +875,40 @@ cudaError_t syncw_reset_launch(WSync * wst, WChan * wch, unsigned int streams, u
 
 bool syncw_supported(unsigned int M) { return M == 256 || M == 512; }
 
-static const unsigned int SYNCW_WPC = 4;
-
-template <unsigned int M>
+template <unsigned int M, unsigned int WPC, unsigned int MINB>
 static cudaError_t syncw_launch_t(const SyncParams & p, cudaStream_t st)
 {
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
-    const size_t smem = sw_layout(M, p.M_pilot, SYNCW_WPC).total;
+    const size_t smem = sw_layout(M, p.M_pilot, WPC).total;
     size_t & conf = configured[(unsigned int)dev & 63u];
     if (smem > conf) {
-        cudaError_t e = cudaFuncSetAttribute(syncw_kernel<M, SYNCW_WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(syncw_kernel<M, WPC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         conf = smem;
     }
     const unsigned int warps = p.streams * p.workers;
-    syncw_kernel<M, SYNCW_WPC><<<(warps + SYNCW_WPC - 1) / SYNCW_WPC, SYNCW_WPC * 32, smem, st>>>(p);
+    syncw_kernel<M, WPC, MINB><<<(warps + WPC - 1) / WPC, WPC * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t syncw_launch(const SyncParams & p, cudaStream_t st)
 {
     if (p.nsamples == 0 || p.streams == 0) return cudaSuccess;
+    // (experiment knob: warps per CTA / CTAs per SM, i.e. the register budget)
+    static const int variant = getenv("B2_SYNCW_VARIANT") ? atoi(getenv("B2_SYNCW_VARIANT")) : 0;
     switch (p.M) {
-    case 256: return syncw_launch_t<256>(p, st);
-    case 512: return syncw_launch_t<512>(p, st);
+    case 256: return syncw_launch_t<256, 4, 4>(p, st);
+    case 512:
+        switch (variant) {
+        case 1:  return syncw_launch_t<512, 4, 5>(p, st);
+        case 2:  return syncw_launch_t<512, 2, 8>(p, st);
+        case 3:  return syncw_launch_t<512, 2, 10>(p, st);
+        case 4:  return syncw_launch_t<512, 1, 16>(p, st);
+        case 5:  return syncw_launch_t<512, 1, 20>(p, st);
+        default: return syncw_launch_t<512, 4, 4>(p, st);
+        }
     default:  return cudaErrorInvalidValue;
     }
 }

@@ -371,14 +371,15 @@ __global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketP
         if (!rec->header_valid) continue;
         const unsigned int plen = rec->payload_len, check = rec->check, fec0 = rec->fec0, fec1 = rec->fec1;
         if (fec0 == 1 && fec1 == 1 && plen + 4 <= PKF_MAX) continue;      // done by packet_plain_kernel
-        const unsigned long long off = rec->payload_offset;
+        if (p.aux[ri].sym_bps == 0xffffffffu) continue;                  // payload was not stored (did not fit the arena)
+        const unsigned long long off = p.aux[ri].sym_off;        // encoded payload: arena + work buffer
         const unsigned int crc_len = (check == 6) ? 4u : 0u;
         const unsigned int n0 = plen + crc_len;
         const unsigned int e0 = pk_fec_enc_len(fec0, n0);
         const unsigned int e1 = pk_fec_enc_len(fec1, e0);
         uint8_t * A = p.arena + off;
         uint8_t * Bf = p.scratch + off;
-        uint8_t * D = p.decoded + off;
+        uint8_t * D = p.decoded + rec->payload_offset;           // n0 bytes
         // The Viterbi decision workspace is shared by every handle of the device (kernels of different
         // handles may run concurrently): a CTA that needs it claims a free slot and releases it after
         // the frame.  Frames without a convolutional stage never touch it.
@@ -406,9 +407,9 @@ __global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketP
         if (sym_bps) {
             // the arena holds demapped symbols: pack them, then work in place as before
             const unsigned int mod_len = (8 * e1 + sym_bps - 1) / sym_bps;
-            pack_symbols(A, mod_len, sym_bps, (uint32_t *)D, nullptr, e1, tid, PK_THREADS);
+            pack_symbols(A, mod_len, sym_bps, (uint32_t *)Bf, nullptr, e1, tid, PK_THREADS);
             __syncthreads();
-            for (unsigned int i = tid; i < (e1 + 3) / 4; i += PK_THREADS) ((uint32_t *)A)[i] = ((const uint32_t *)D)[i];
+            for (unsigned int i = tid; i < (e1 + 3) / 4; i += PK_THREADS) ((uint32_t *)A)[i] = ((const uint32_t *)Bf)[i];
             __syncthreads();
         }
         // stage 1 (outer code)
@@ -642,16 +643,33 @@ __global__ void __launch_bounds__(PKF_WARPS * 32) packet_plain_kernel(const Pack
         for (int j = 0; j < 8; j++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
         table[tid] = c;                          // blockDim.x == 256
     }
-    __syncthreads();
+    // merge constants x^(8 per 2^l) mod P of the launch's first frame length (frames of a launch nearly always share
+    // their length; the GF(2) products that build them cost more than the CRC of a whole frame)
+    __shared__ uint32_t xps[5];
+    __shared__ unsigned int xps_per;
     const unsigned int nrec = p.range[1].nrec;
+    if (wid == 0) {
+        unsigned int per0 = 0;
+        const unsigned int r0 = p.range[0].nrec;
+        if (r0 < nrec) per0 = p.recs[r0].payload_len / 32;
+        uint32_t xp = crc_x8n(per0);
+#pragma unroll
+        for (int l = 0; l < 5; l++) {
+            if (lane == 0) xps[l] = xp;
+            xp = crc_multmodp(xp, xp);
+        }
+        if (lane == 0) xps_per = per0;
+    }
+    __syncthreads();
     for (unsigned int ri = p.range[0].nrec + blockIdx.x * PKF_WARPS + wid; ri < nrec; ri += gridDim.x * PKF_WARPS) {
         FrameRec * rec = p.recs + ri;
         if (!rec->header_valid || rec->fec0 != 1 || rec->fec1 != 1) continue;
         const unsigned int plen = rec->payload_len, crc_len = (rec->check == 6) ? 4u : 0u, n0 = plen + crc_len;
         if (n0 > PKF_MAX) continue;              // left to the general kernel
-        const unsigned long long off = rec->payload_offset;
+        if (p.aux[ri].sym_bps == 0xffffffffu) continue;                  // payload was not stored
+        const unsigned long long off = p.aux[ri].sym_off;
         const uint32_t * src = (const uint32_t *)(p.arena + off);       // offsets are 16-byte aligned
-        uint32_t * dst = (uint32_t *)(p.decoded + off);
+        uint32_t * dst = (uint32_t *)(p.decoded + rec->payload_offset);
         uint32_t * st = (uint32_t *)stage[wid];
         const unsigned int sym_bps = p.aux[ri].sym_bps;
         if (sym_bps) pack_symbols(p.arena + off, (8 * n0 + sym_bps - 1) / sym_bps, sym_bps, st, dst, n0, lane, 32);
@@ -665,12 +683,21 @@ __global__ void __launch_bounds__(PKF_WARPS * 32) packet_plain_kernel(const Pack
             uint32_t key = lane ? 0u : ~0u;
             for (unsigned int i = lo; i < hi; i++) key = (key >> 8) ^ table[(key ^ m[i]) & 0xffu];
             // tree merge; the right operand of every merge spans a multiple of `per` bytes
-            uint32_t xp = crc_x8n(per);
+            if (per == xps_per) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t right = __shfl_down_sync(0xffffffffu, key, o);
-                if ((lane & (2 * o - 1)) == 0) key = crc_multmodp(xp, key) ^ right;
-                xp = crc_multmodp(xp, xp);
+                for (int l = 0; l < 5; l++) {
+                    const int o = 1 << l;
+                    uint32_t right = __shfl_down_sync(0xffffffffu, key, o);
+                    if ((lane & (2 * o - 1)) == 0) key = crc_multmodp(xps[l], key) ^ right;
+                }
+            } else {
+                uint32_t xp = crc_x8n(per);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t right = __shfl_down_sync(0xffffffffu, key, o);
+                    if ((lane & (2 * o - 1)) == 0) key = crc_multmodp(xp, key) ^ right;
+                    xp = crc_multmodp(xp, xp);
+                }
             }
             if (lane == 0) {
                 uint32_t want = ((uint32_t)m[plen] << 24) | ((uint32_t)m[plen + 1] << 16) | ((uint32_t)m[plen + 2] << 8) | m[plen + 3];
@@ -682,16 +709,16 @@ __global__ void __launch_bounds__(PKF_WARPS * 32) packet_plain_kernel(const Pack
     }
 }
 
-__global__ void record_mark_kernel(const unsigned int * counters, RangeMark * mark_out)
+__global__ void record_mark_kernel(const unsigned int * counters, RangeMark * mark_out, int used_at)
 {
     RangeMark m;
     m.nrec = counters[0]; m.pad = counters[1];           // pad: overflow flag so far
-    m.arena_used = *(const unsigned long long *)(counters + 2);
+    m.arena_used = *(const unsigned long long *)(counters + used_at);   // bytes of decoded payload so far
     *mark_out = m;
 }
-cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_out, cudaStream_t st)
+cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_out, cudaStream_t st, int used_at)
 {
-    record_mark_kernel<<<1, 1, 0, st>>>(counters, mark_out);
+    record_mark_kernel<<<1, 1, 0, st>>>(counters, mark_out, used_at);
     return cudaGetLastError();
 }
 
