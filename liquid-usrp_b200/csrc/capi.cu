@@ -778,7 +778,8 @@ static int mcrx_process(b2_mcrx * q, const float * x, size_t n, bool on_device)
     if (T > 0) B2_TRY(q->core.begin_batch());
     // chunk schedule: short chunks first (the synchronisers start early), doubling up to chunk_blocks, and
     // halving again towards the end (the D2H + host ordering of the last chunk is the tail of the call)
-    size_t cb = q->chunk_blocks, cmin = std::max<size_t>(64, cb / 8);
+    // (the frame-parallel synchroniser wants launches of many frames per stream and has no chain to start early: equal chunks)
+    size_t cb = q->chunk_blocks, cmin = q->core.use_w ? cb : std::max<size_t>(64, cb / 8);
     if (const char * e = getenv("B2_CHUNK_MIN_BLOCKS")) { long v = atol(e); if (v >= 1) cmin = std::min<size_t>(cb, (size_t)v); }
     size_t next_tc = cmin;
     for (size_t b0 = 0, tc = 0; b0 < T; b0 += tc, nchunks++) {

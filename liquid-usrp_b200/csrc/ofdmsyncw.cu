@@ -47,7 +47,8 @@ struct SWLayout {
 __host__ __device__ static inline SWLayout sw_layout(unsigned int M, unsigned int Mp, unsigned int wpc)
 {
     SWLayout L;
-    L.twt_bytes = ((size_t)f8_twt_elems(M, 1) * sizeof(cf) + 15) & ~(size_t)15;
+    // per-pass twiddle tables of the M-point transform and, for M = 512, of the M/2-point one (S0 events)
+    L.twt_bytes = ((size_t)(f8_twt_elems(M, 1) + (M == 512 ? f8_twt_elems(M / 2, 1) : 0)) * sizeof(cf) + 15) & ~(size_t)15;
     size_t o = 0;
     L.off_f = o;  o += (size_t)(M + M / 8) * sizeof(cf);  // FFT exchange buffer (skewed); Gs / yph between transforms
     L.off_rg = o; o += (size_t)M * sizeof(cf);            // equaliser taps R (state RX) / S0a gains (state S0B)
@@ -79,6 +80,20 @@ __device__ __forceinline__ void fw_load(cf (&v)[8], unsigned int j, const cf * _
 #pragma unroll
     for (unsigned int s = 0; s < 8; s++) v[s] = src[s * (N / 8 + N / 64)];
 }
+// per-pass tables (f8_twt_build) of an N-point transform out of the twiddles of the 2N-point one: e^{-2 pi i k / N} = tw[2k]
+template <unsigned int N, unsigned int Ns>
+__device__ __forceinline__ void fw_twt_build_half(cf * twt, const cf * __restrict__ tw2, unsigned int tid, unsigned int nthreads)
+{
+    constexpr unsigned int R = f8_radix(N, Ns);
+    if constexpr (Ns > 1) {
+        for (unsigned int e = tid; e < (R - 1) * Ns; e += nthreads) {
+            const unsigned int q = e / Ns + 1, k = e % Ns;
+            twt[e] = tw2[2u * (k * q * (N / (Ns * R)))];
+        }
+    }
+    if constexpr (Ns * R < N) fw_twt_build_half<N, Ns * R>(twt + (Ns > 1 ? (R - 1) * Ns : 0), tw2, tid, nthreads);
+}
+
 // passes of the M-point transform from Ns on, VT virtual threads (lane + 32 vt) per lane
 template <unsigned int N, unsigned int Ns, unsigned int VT>
 __device__ __forceinline__ void fw_run(cf (&v)[VT][8], unsigned int lane, cf * __restrict__ buf, const cf * __restrict__ twt)
@@ -137,6 +152,8 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
     float * yph = (float *)fbuf;
 
     f8_twt_build<M, 1>(twt, p.fft.tw, threadIdx.x, WPC * 32);
+    cf * twt_h = twt + f8_twt_elems(M, 1);
+    if constexpr (M == 512) fw_twt_build_half<M / 2, 1>(twt_h, p.fft.tw, threadIdx.x, WPC * 32);
     __syncthreads();
 
     // ---- which stream, which worker, which stretch
@@ -310,35 +327,71 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
             if (state == ST_SEEK) {
                 B2W_FORPTS { en += v[vt][s].x * v[vt][s].x + v[vt][s].y * v[vt][s].y; }
             }
-            // ---- M-point forward FFT
+            // ---- M-point forward FFT.  The events on the short training symbol (seek, S0a, S0b) only look at the even
+            //      subcarriers, X[2k] = FFT_{M/2}(x[n] + x[n + M/2])[k]: half the transform, half the correlator
             __syncwarp();
-            fw_run<M, 1, VT>(v, lane, fbuf, twt);
-            __syncwarp();                          // fbuf is free again (Gs / yph)
+            float mr = 0.f, mi = 0.f, cr = 0.f, ci = 0.f;
+            if (VT == 2 && state != ST_RX && state != ST_S1) {
+                if constexpr (VT == 2) {
+                    cf wv[1][8];
+#pragma unroll
+                    for (unsigned int q = 0; q < 8; q++) wv[0][q] = cadd(v[q & 1][q >> 1], v[q & 1][(q >> 1) + 4]);
+                    fw_run<M / 2, 1, 1>(wv, lane, fbuf, twt_h);
+                    __syncwarp();
+                    // G[2k] = X[2k] ref[2k] gain, k = lane + 32 q
+                    const float gain = sqrtf((float)p.M_S0) / (float)M;
+#pragma unroll
+                    for (unsigned int q = 0; q < 8; q++) {
+                        const unsigned int k = lane + 32u * q;
+                        const float r = __ldg(p.tb.S0 + 2u * k);
+                        wv[0][q] = make_float2(wv[0][q].x * r * gain, wv[0][q].y * r * gain);
+                        Gs[k] = wv[0][q];
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (unsigned int q = 0; q < 8; q++) {
+                        const cf tt = cmulc(Gs[(lane + 32u * q + 1u) & (M2 - 1)], wv[0][q]);
+                        mr += tt.x; mi += tt.y;
+                    }
+                    if (state == ST_S0A) {
+#pragma unroll
+                        for (unsigned int q = 0; q < 8; q++) RG[lane + 32u * q] = wv[0][q];
+                    } else if (state == ST_S0B) {
+#pragma unroll
+                        for (unsigned int q = 0; q < 8; q++) { const cf tt = cmulc(wv[0][q], RG[lane + 32u * q]); cr += tt.x; ci += tt.y; }
+                    }
+                }
+            } else {
+                fw_run<M, 1, VT>(v, lane, fbuf, twt);
+                __syncwarp();                      // fbuf is free again (Gs / yph)
+                if (state != ST_RX) {
+                    // ---- G[i] = X[i]*ref[i]*gain on the training subcarriers
+                    const bool long_seq = (state == ST_S1);
+                    const unsigned int step = long_seq ? 1u : 2u;
+                    const float gain = sqrtf((float)(long_seq ? p.M_S1 : p.M_S0)) / (float)M;
+                    const float * ref = long_seq ? p.tb.S1 : p.tb.S0;
+                    B2W_FORPTS {
+                        const unsigned int i = B2W_I;
+                        const float r = __ldg(ref + i);
+                        v[vt][s] = make_float2(v[vt][s].x * r * gain, v[vt][s].y * r * gain);
+                        Gs[i] = v[vt][s];
+                    }
+                    __syncwarp();
+                    B2W_FORPTS {
+                        const unsigned int i = B2W_I;
+                        const cf tt = cmulc(Gs[(i + step) & (M - 1)], v[vt][s]);
+                        mr += tt.x; mi += tt.y;
+                    }
+                    if (state == ST_S0A) {
+                        B2W_FORPTS { RG[B2W_I] = v[vt][s]; }
+                    } else if (state == ST_S0B) {
+                        B2W_FORPTS { const cf tt = cmulc(v[vt][s], RG[B2W_I]); cr += tt.x; ci += tt.y; }
+                    }
+                }
+            }
 
             if (state != ST_RX) {
-                // ---- preamble events.  G[i] = X[i]*ref[i]*gain on the training subcarriers
-                const bool long_seq = (state == ST_S1);
-                const unsigned int step = long_seq ? 1u : 2u;
-                const float gain = sqrtf((float)(long_seq ? p.M_S1 : p.M_S0)) / (float)M;
-                const float * ref = long_seq ? p.tb.S1 : p.tb.S0;
-                B2W_FORPTS {
-                    const unsigned int i = B2W_I;
-                    const float r = __ldg(ref + i);
-                    v[vt][s] = make_float2(v[vt][s].x * r * gain, v[vt][s].y * r * gain);
-                    Gs[i] = v[vt][s];
-                }
-                __syncwarp();
-                float mr = 0.f, mi = 0.f, cr = 0.f, ci = 0.f;
-                B2W_FORPTS {
-                    const unsigned int i = B2W_I;
-                    const cf tt = cmulc(Gs[(i + step) & (M - 1)], v[vt][s]);
-                    mr += tt.x; mi += tt.y;
-                }
-                if (state == ST_S0A) {
-                    B2W_FORPTS { RG[B2W_I] = v[vt][s]; }
-                } else if (state == ST_S0B) {
-                    B2W_FORPTS { const cf tt = cmulc(v[vt][s], RG[B2W_I]); cr += tt.x; ci += tt.y; }
-                }
+                // ---- preamble events: s_hat = sum G[i+step] conj(G[i]) / cross-correlation of the two S0 halves
                 if (state == ST_SEEK) cr = en;
                 mr = warp_sum(mr); mi = warp_sum(mi); cr = warp_sum(cr); ci = warp_sum(ci);
                 __syncwarp();                      // everybody has read Gs (yph aliases it)

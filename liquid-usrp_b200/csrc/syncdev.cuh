@@ -211,18 +211,21 @@ __device__ __forceinline__ uint32_t nco_constrain_small(float theta)
     return (uint32_t)(__double2ull_rn(f * 4294967296.0) & 0xffffffffull);
 }
 
-// hard demapper with the constellation known at compile time (same decisions as demod_symbol)
+// hard demapper with the constellation known at compile time (same decisions as demod_symbol).
+// liquid walks the levels by successive approximation, v_{k+1} = v_k -+ 2^k alpha with the sign of v_k, and Gray-codes
+// the binary index.  With u_k = |v_k| the same float operations read u_{k+1} = |u_k| - 2^k alpha (v_{k+1} = +-u_{k+1},
+// negation is exact), and the Gray bits are simply [v > 0, u_1 < 0, u_2 < 0, ...]: a bit of s ^ (s >> 1) is set
+// where two consecutive decisions differ, i.e. where the magnitude fell below the level that was subtracted.
 template <int MB> __device__ __forceinline__ unsigned int demod_axis_t(float v, float alpha)
 {
-    unsigned int s = 0;
+    unsigned int g = (v > 0) ? (1u << (MB - 1)) : 0u;
+    float u = v;
 #pragma unroll
-    for (int k = MB - 1; k >= 0; k--) {
-        const float ref = (float)(1u << k) * alpha;
-        const bool pos = v > 0;
-        s = (s << 1) | (pos ? 1u : 0u);
-        v += pos ? -ref : ref;
+    for (int k = MB - 1; k >= 1; k--) {
+        u = fabsf(u) - (float)(1u << k) * alpha;
+        g |= (u < 0) ? (1u << (k - 1)) : 0u;
     }
-    return s ^ (s >> 1);
+    return g;
 }
 template <int MB> __device__ __forceinline__ unsigned int demod_qam_t(cf x, float alpha)
 {
