@@ -142,7 +142,12 @@ __global__ void __launch_bounds__(K, 1) analyzer8_kernel(const AnalyzerParams p)
         // K-point forward FFT of row g by group g
         cf v[8];
         f8_load<K>(v, j, bufA + g * BUF);
-        f8_run<K, 1, -1>(v, j, bufB + g * BUF, bufA + g * BUF, nullptr, [] { __syncthreads(); }, nullptr, tw);
+        // (the exchanges of a row concern its own K/8 threads only: a named barrier per group lets the eight groups
+        // drift apart, one in its butterflies while another waits for shared memory)
+        if constexpr (T8 >= 32 && T8 % 32 == 0)
+            f8_run<K, 1, -1>(v, j, bufB + g * BUF, bufA + g * BUF, nullptr, [g] { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(T8) : "memory"); }, nullptr, tw);
+        else
+            f8_run<K, 1, -1>(v, j, bufB + g * BUF, bufA + g * BUF, nullptr, [] { __syncthreads(); }, nullptr, tw);
 
         // channels 0..N-1 -> out[c][col0 + block], via a transposed tile
 #pragma unroll

@@ -42,7 +42,7 @@
 namespace b2 {
 
 struct SWLayout {
-    size_t twt_bytes, per_warp, off_f, off_rg, off_yc, off_ws, off_hb, total;
+    size_t twt_bytes, per_warp, off_f, off_rg, off_yc, off_ws, off_hb, off_ctl, total;
 };
 __host__ __device__ static inline SWLayout sw_layout(unsigned int M, unsigned int Mp, unsigned int wpc)
 {
@@ -55,10 +55,21 @@ __host__ __device__ static inline SWLayout sw_layout(unsigned int M, unsigned in
     L.off_yc = o; o += ((size_t)(Mp + 4) * sizeof(cf) + 15) & ~(size_t)15;
     L.off_ws = o; o += (sizeof(WSync) + 15) & ~(size_t)15;
     L.off_hb = o; o += 112;                                // 36 header bytes + 12 Golay symbols + decode results
+    L.off_ctl = o; o += 64;                               // stretch / stitch bookkeeping (see WCtl)
     L.per_warp = (o + 15) & ~(size_t)15;
     L.total = L.twt_bytes + L.per_warp * wpc;
     return L;
 }
+
+// per-worker bookkeeping that is only touched between stretches (shared memory, one per warp)
+struct WCtl {
+    unsigned long long chain_b_last, chain_b_prev;   // stitcher: last two frame ends of the verified chain
+    unsigned int n_act, J, period, head;
+    int rfirst;                                      // first predicted position, relative to the launch's first sample
+    unsigned int cur, sc, pbase, pcap;
+    unsigned int pad[3];
+};
+static_assert(sizeof(WCtl) == 64, "WCtl is 64 bytes");
 
 // Exchange between two radix-8 passes through a SKEWED buffer, element x at x + (x >> 3): the scattered stores of a
 // pass (element b0 + q Ns, q < 8) and the strided loads of the next one (element j + s N/8) are then both one base
@@ -134,7 +145,6 @@ template <unsigned int M, unsigned int WPC, unsigned int MINB>
 __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams p)
 {
     constexpr unsigned int VT = M / 256, T = M / 8, M2 = M / 2;
-    constexpr unsigned long long OPEN = ~0ull;
     extern __shared__ __align__(16) unsigned char smem[];
     const unsigned int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned int cp = p.cp, W = M + cp, Mp = p.M_pilot, Na = Mp + p.M_data;
@@ -156,38 +166,46 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
     if constexpr (M == 512) fw_twt_build_half<M / 2, 1>(twt_h, p.fft.tw, threadIdx.x, WPC * 32);
     __syncthreads();
 
-    // ---- which stream, which worker, which stretch
+    // ---- which stream, which worker, which stretch.  Positions inside the kernel are 32-bit offsets from the
+    //      launch's first sample (E0 = p.sample_base): a launch is shorter than 2^31 samples per stream
+    constexpr int RNONE = 0x7fffffff;                 // "open" / "no such position"
+    WCtl * ctl = (WCtl *)(wb + L.off_ctl);
     const unsigned int gw = blockIdx.x * WPC + wid;
     const unsigned int ch = gw % p.streams, w = gw / p.streams;
     if (w >= p.workers) return;
     WChan * C = p.wch + ch;
-    const unsigned long long E0 = p.sample_base, E1 = E0 + p.nsamples;
-    unsigned long long first = 0;
-    unsigned int J = 0;
     const unsigned int par = p.launch_id & 1u;
-    const unsigned int period = C->pred_period[par];
-    if (p.workers > 1 && period >= 64u) {
-        first = C->pred_next[par];
-        if (first <= E0) first += ((E0 - first) / period + 1ull) * period;
-        if (first + M <= E1) J = (unsigned int)min((E1 - M - first) / period + 1ull, (unsigned long long)(1u << 24));
+    {
+        const unsigned long long E0 = p.sample_base, E1 = E0 + p.nsamples;
+        unsigned long long first = 0;
+        unsigned int J = 0;
+        const unsigned int period = C->pred_period[par];
+        if (p.workers > 1 && period >= 64u) {
+            first = C->pred_next[par];
+            if (first <= E0) first += ((E0 - first) / period + 1ull) * period;
+            if (first + M <= E1) J = (unsigned int)min((E1 - M - first) / period + 1ull, (unsigned long long)(1u << 24));
+        }
+        const unsigned int n_act = min(p.workers, J + 1u);
+        if (w >= n_act) return;
+        if (lane == 0) {
+            ctl->n_act = n_act; ctl->J = J; ctl->period = period; ctl->head = C->head[par];
+            ctl->rfirst = J ? (int)(first - E0) : 0;
+        }
+        __syncwarp();
     }
-    const unsigned int n_act = min(p.workers, J + 1u);
-    if (w >= n_act) return;
-    const unsigned int head = C->head[par];
-    auto start_of = [&](unsigned int ww) -> unsigned long long {
-        if (ww == 0) return E0;
-        if (ww >= n_act) return OPEN;
-        return first + (unsigned long long)((ww * (J + 1u)) / n_act - 1u) * period;      // ww < 64, J <= 2^24
+    // start of worker ww's stretch (ww < 64, J <= 2^24)
+    auto rstart = [&](unsigned int ww) -> int {
+        if (ww == 0) return 0;
+        if (ww >= ctl->n_act) return RNONE;
+        return ctl->rfirst + (int)(((ww * (ctl->J + 1u)) / ctl->n_act - 1u) * ctl->period);
     };
-    auto slot_of = [&](unsigned int ww) -> unsigned int { return ch * p.wslots + (head + ww) % p.wslots; };
+    auto rend = [&](unsigned int ww) -> int { return (ww + 1 < ctl->n_act) ? rstart(ww + 1) : (int)p.nsamples; };
+    auto slot_of = [&](unsigned int ww) -> unsigned int { return ch * p.wslots + (ctl->head + ww) % p.wslots; };
     // private record list of speculative worker ww: disjoint regions of the stream's list (a record needs > 2 W samples)
     auto priv_base = [&](unsigned int ww) -> unsigned int {
-        return ch * p.wrec_stride + (unsigned int)((start_of(ww) - E0) / (2u * W)) + 2u * ww;
+        return ch * p.wrec_stride + (unsigned int)rstart(ww) / (2u * W) + 2u * ww;
     };
-    auto priv_cap = [&](unsigned int ww) -> unsigned int {
-        const unsigned long long a = start_of(ww), b = (ww + 1 < n_act) ? start_of(ww + 1) : E1;
-        return (unsigned int)((b - a) / (2u * W)) + 2u;
-    };
+    auto priv_cap = [&](unsigned int ww) -> unsigned int { return (unsigned int)(rend(ww) - rstart(ww)) / (2u * W) + 2u; };
 
     const cf * in = p.in + (size_t)ch * p.in_stride;
     const cf * ring = p.ring + (size_t)ch * W;
@@ -195,14 +213,21 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
     // role / rank of own subcarriers: read where they are used (64-byte rows of an L1-resident table)
 #define B2W_RK ((unsigned int)__ldg(&p.tb.sc_rank[B2W_I]))
 
-    // ---- hot state in registers (identical in every lane), the rest in S
+    // ---- hot state in registers (identical in every lane); everything an event does not touch lives in S (shared
+    //      memory; every lane writes the same value, or lane 0 writes and a __syncwarp follows)
     int state = ST_SEEK, timer = 0, fstate = FS_HEADER;
-    unsigned int num_symbols = 0, th = 0, dth = 0, pilot_pos = 0, hstart = 0, pstart = 0, bps = 0, ms = 0, mod_len = 0;
-    unsigned int q_th = 0, q_dth = 0, nb = 0;
-    float g0 = 1.f, sh0r = 0.f, sh0i = 0.f, phi_prime = 0.f, p1_prime = 0.f, evm_hat = 0.f;
-    unsigned long long sidx = 0, mix_start = 0, mix_end = 0, b_last = 0, b_prev = 0, sym_abs = 0, sym_off = 0;
-    unsigned int nrec_priv = 0;
+    unsigned int num_symbols = 0, th = 0, dth = 0, pilot_pos = 0, pstart = 0;
+    float phi_prime = 0.f, p1_prime = 0.f;
+    int rs = 0;                                    // next sample to be pushed
+    int rms = 0, rme = 0;                          // mixed segment [rms, rme), rme == RNONE: open
+    unsigned long long sym_off = 0;
 
+    auto rel_of = [&](unsigned long long x) -> int {
+        const unsigned long long E0 = p.sample_base;
+        if (x == ~0ull) return RNONE;
+        if (x >= E0) return (int)min(x - E0, (unsigned long long)(1u << 30));
+        return -(int)min(E0 - x, (unsigned long long)(1u << 30));
+    };
     auto load_state = [&](unsigned int slot) {
         const uint32_t * src = (const uint32_t *)(p.wst + slot);
         uint32_t * dst = (uint32_t *)S;
@@ -211,37 +236,41 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
         __syncwarp();
         state = S->state; timer = S->timer; fstate = S->fstate;
         num_symbols = S->num_symbols; th = S->nco_theta; dth = S->nco_dtheta; pilot_pos = S->pilot_pos;
-        hstart = S->header_sym_idx; pstart = S->payload_sym_idx; bps = S->bps_payload; ms = S->ms_payload; mod_len = S->payload_mod_len;
-        q_th = S->q_theta; q_dth = S->q_dtheta;
-        g0 = S->g0; sh0r = S->s_hat0_re; sh0i = S->s_hat0_im; phi_prime = S->phi_prime; p1_prime = S->p1_prime; evm_hat = S->evm_hat;
-        sidx = S->sample_index; mix_start = S->mix_start; mix_end = S->mix_end; sym_abs = S->sym_abs; sym_off = S->sym_off;
-        nb = 0; b_last = 0; b_prev = 0; nrec_priv = 0;
+        pstart = S->payload_sym_idx;
+        phi_prime = S->phi_prime; p1_prime = S->p1_prime;
+        rs = rel_of(S->sample_index); rms = rel_of(S->mix_start); rme = rel_of(S->mix_end); sym_off = S->sym_off;
+        __syncwarp();
+        if (lane == 0) { S->nb = 0; S->b_last = 0; S->b_prev = 0; S->nrec = 0; }
         if (state == ST_RX || state == ST_S0B) {
             const cf * g = p.wRG + (size_t)slot * M;
             for (unsigned int i = lane; i < M; i += 32) RG[i] = __ldcg(g + i);
         }
         __syncwarp();
     };
-    auto fresh_state = [&](unsigned long long at) {
+    auto fresh_state = [&](int at) {      // (S all zero: S->g0 is set by the seek event that always comes first)
         uint32_t * dst = (uint32_t *)S;
         __syncwarp();
         for (unsigned int i = lane; i < sizeof(WSync) / 4; i += 32) dst[i] = 0u;
         __syncwarp();
         state = ST_SEEK; timer = 0; fstate = FS_HEADER;
-        num_symbols = 0; th = 0; dth = 0; pilot_pos = 0; hstart = 0; pstart = 0; bps = 0; ms = 0; mod_len = 0; q_th = 0; q_dth = 0;
-        g0 = 1.f; sh0r = 0.f; sh0i = 0.f; phi_prime = 0.f; p1_prime = 0.f; evm_hat = 0.f;
-        sidx = at; mix_start = 0; mix_end = 0; nb = 0; b_last = 0; b_prev = 0; nrec_priv = 0; sym_abs = 0; sym_off = 0;
+        num_symbols = 0; th = 0; dth = 0; pilot_pos = 0; pstart = 0;
+        phi_prime = 0.f; p1_prime = 0.f;
+        rs = at; rms = 0; rme = 0; sym_off = 0;
     };
     auto save_state = [&](unsigned int slot, unsigned int matched) {
         __syncwarp();
         if (lane == 0) {
+            const unsigned long long E0 = p.sample_base;
             S->state = state; S->timer = timer; S->fstate = fstate;
             S->num_symbols = num_symbols; S->nco_theta = th; S->nco_dtheta = dth; S->pilot_pos = pilot_pos;
-            S->header_sym_idx = hstart; S->payload_sym_idx = pstart; S->bps_payload = bps; S->ms_payload = ms; S->payload_mod_len = mod_len;
-            S->q_theta = q_th; S->q_dtheta = q_dth;
-            S->g0 = g0; S->s_hat0_re = sh0r; S->s_hat0_im = sh0i; S->phi_prime = phi_prime; S->p1_prime = p1_prime; S->evm_hat = evm_hat;
-            S->sample_index = sidx; S->mix_start = mix_start; S->mix_end = mix_end; S->sym_abs = sym_abs; S->sym_off = sym_off;
-            S->b_last = b_last; S->b_prev = b_prev; S->nb = nb; S->matched = matched; S->nrec = nrec_priv;
+            S->payload_sym_idx = pstart;
+            S->phi_prime = phi_prime; S->p1_prime = p1_prime;
+            S->sample_index = E0 + (unsigned long long)rs;
+            const bool none = (rme <= rms);
+            S->mix_start = none ? 0ull : E0 + (long long)rms;
+            S->mix_end = none ? 0ull : (rme == RNONE ? ~0ull : E0 + (long long)rme);
+            S->sym_off = sym_off;
+            S->matched = matched;
         }
         __syncwarp();
         uint32_t * dst = (uint32_t *)(p.wst + slot);
@@ -254,16 +283,15 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
     };
 
     // ---- stretch control
-    unsigned int cur = w;                          // the worker whose slot / payload buffer this warp is working in
+    // ctl->cur: the worker whose slot this warp is working in; ctl->sc: stitch cursor
     bool direct = (w == 0);                        // records go straight to the launch's output (known to be the serial chain's)
     bool stitching = false;
-    unsigned long long limit = (w + 1 < n_act) ? start_of(w + 1) : E1;
+    int rlimit = rend(w);
     unsigned int cand = w + 1;                     // next worker whose start may be met in the canonical state
-    unsigned long long cand_pos = start_of(cand);
-    unsigned int sc = 0;                           // stitch cursor
-    unsigned long long chain_b_last = 0, chain_b_prev = 0;
-    if (w == 0) load_state(slot_of(0)); else fresh_state(start_of(w));
-    const unsigned int pbase_w = priv_base(w), pcap_w = priv_cap(w);
+    int rcand = rstart(cand);
+    if (lane == 0) { ctl->cur = w; ctl->sc = 0; ctl->pbase = priv_base(w); ctl->pcap = priv_cap(w); }
+    if (w == 0) load_state(slot_of(0)); else fresh_state(rstart(w));
+    __syncwarp();
 
     for (;;) {
         unsigned int matched = 0;
@@ -273,25 +301,24 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
             if (state == ST_SEEK) need = (timer < (int)M) ? (unsigned int)((int)M - timer) : 1u;
             else if (state == ST_S0A || state == ST_S0B) need = (timer < (int)M2) ? (unsigned int)((int)M2 - timer) : 1u;
             else need = (timer > 1) ? (unsigned int)timer : 1u;
-            if (sidx + need > limit) {             // the event lies beyond this stretch: consume what is left
-                const unsigned int adv = (unsigned int)(limit - sidx);
+            if (rs + (int)need > rlimit) {         // the event lies beyond this stretch: consume what is left
+                const unsigned int adv = (unsigned int)(rlimit - rs);
                 if (state != ST_SEEK) th += adv * dth;
                 if (state == ST_SEEK || state == ST_S0A || state == ST_S0B) timer += (int)adv; else timer -= (int)adv;
-                sidx = limit;
+                rs = rlimit;
                 break;
             }
-            const unsigned long long e = sidx + need;
+            const int re = rs + (int)need;
             const unsigned int off = (state == ST_RX) ? cp - p.backoff : cp;
-            const unsigned long long ws = e - W + off;                  // first sample of the FFT window (mod 2^64 at the very start)
-            const long long rel0 = (long long)(ws - E0);
+            const int rel0 = re - (int)W + (int)off;                    // first sample of the FFT window (may lie before the launch)
             // ---- the window, re-mixed as liquid pushed it
             cf v[VT][8];
             {
-                const bool open = (mix_end == OPEN);
-                const unsigned int r_th = open ? th : q_th, r_dth = open ? dth : q_dth;
-                const bool any_mixed = (mix_end > mix_start) && ((long long)(mix_start - ws) < (long long)M) && ((long long)(mix_end - ws) > 0 || open) && ((r_th | r_dth) != 0u);
-                const bool all_mixed = any_mixed && ((long long)(mix_start - ws) <= 0) && (open || (long long)(mix_end - ws) >= (long long)M);
-                const unsigned int d0 = (unsigned int)(ws - (open ? sidx : mix_end));
+                const bool open = (rme == RNONE);
+                const unsigned int r_th = open ? th : S->q_theta, r_dth = open ? dth : S->q_dtheta;
+                const bool any_mixed = (rme > rms) && (rms - rel0 < (int)M) && (open || rme - rel0 > 0) && ((r_th | r_dth) != 0u);
+                const bool all_mixed = any_mixed && (rms <= rel0) && (open || rme - rel0 >= (int)M);
+                const unsigned int d0 = (unsigned int)(rel0 - (open ? rs : rme));
                 if (rel0 >= 0 && all_mixed) {
                     const cf * src = in + rel0 + lane;
                     const unsigned int ph0 = r_th + (d0 + lane) * r_dth, ph32 = 32u * r_dth;
@@ -306,13 +333,13 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                     B2W_FORPTS { v[vt][s] = __ldg(src + 32u * (vt + VT * s)); }
                     B2W_PREFETCH_NEXT
                 } else {
-                    const long long m0 = (long long)(mix_start - ws), m1 = open ? (long long)M : (long long)(mix_end - ws);
+                    const int m0 = rms - rel0, m1 = open ? (int)M : rme - rel0;
 #pragma unroll 4
                     for (unsigned int q = 0; q < 8 * VT; q++) {
                         const unsigned int i = lane + 32u * q;
-                        const long long r = rel0 + (long long)i;
-                        cf x = (r >= 0) ? __ldg(in + r) : __ldcg(ring + ((long long)W + r));
-                        if (any_mixed && (long long)i >= m0 && (long long)i < m1) x = mix_down(x, nco_cexp_fast(r_th + (d0 + i) * r_dth));
+                        const int r = rel0 + (int)i;
+                        cf x = (r >= 0) ? __ldg(in + r) : __ldcg(ring + ((int)W + r));
+                        if (any_mixed && (int)i >= m0 && (int)i < m1) x = mix_down(x, nco_cexp_fast(r_th + (d0 + i) * r_dth));
                         fbuf[i] = x;
                     }
                     __syncwarp();
@@ -322,7 +349,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
             // ---- advance to the event
             if (state != ST_SEEK) th += need * dth;
             if (state == ST_SEEK || state == ST_S0A || state == ST_S0B) timer += (int)need; else timer -= (int)need;
-            sidx = e;
+            rs = re;
             float en = 0.f;
             if (state == ST_SEEK) {
                 B2W_FORPTS { en += v[vt][s].x * v[vt][s].x + v[vt][s].y * v[vt][s].y; }
@@ -398,43 +425,43 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                 if (state == ST_SEEK) {
                     const float gg = (float)M / cr;
                     const cf s_hat = make_float2(mr / (float)p.M_S0 * gg, mi / (float)p.M_S0 * gg);
-                    g0 = gg;
+                    S->g0 = gg;
                     timer = 0;
                     if (hypotf(s_hat.x, s_hat.y) > p.thresh) {
                         const float tau_hat = atan2f(s_hat.y, s_hat.x) * (float)M2 / (2 * PI_F);
                         const int dt = (int)roundf(tau_hat);
                         timer = (int)((M + (unsigned int)dt) % M2) + (int)M;
                         state = ST_S0A;
-                        if (lane == 0) S->detect_index = sidx - 1;
+                        if (lane == 0) S->detect_index = p.sample_base + (unsigned long long)rs - 1ull;
                     } else {
-                        mix_start = 0; mix_end = 0;           // canonical: nothing behind this point matters any more
+                        rms = 0; rme = 0;                     // canonical: nothing behind this point matters any more
                     }
                 } else if (state == ST_S0A) {
                     timer = 0;
-                    sh0r = mr / (float)p.M_S0 * g0;
-                    sh0i = mi / (float)p.M_S0 * g0;
+                    S->s_hat0_re = mr / (float)p.M_S0 * S->g0;
+                    S->s_hat0_im = mi / (float)p.M_S0 * S->g0;
                     state = ST_S0B;
                 } else if (state == ST_S0B) {
-                    const float s1r = mr / (float)p.M_S0 * g0, s1i = mi / (float)p.M_S0 * g0;
-                    const float tau_hat = atan2f(sh0i + s1i, sh0r + s1r) * (float)M2 / (2 * PI_F);
+                    const float s1r = mr / (float)p.M_S0 * S->g0, s1i = mi / (float)p.M_S0 * S->g0;
+                    const float tau_hat = atan2f(S->s_hat0_im + s1i, S->s_hat0_re + s1r) * (float)M2 / (2 * PI_F);
                     timer = (int)(M + cp - p.backoff) - (int)roundf(tau_hat);
                     const float nu_hat = 2.0f * atan2f(ci, cr) / (float)M;
                     dth = nco_constrain_dev(nu_hat);
                     state = ST_S1;
-                    mix_start = sidx; mix_end = OPEN;         // from here on samples are pushed through the NCO
+                    rms = rs; rme = RNONE;                    // from here on samples are pushed through the NCO
                 } else {
                     // ---- S1: accept / retry, and on accept the equaliser
                     num_symbols++;
-                    cf s_hat = make_float2(mr / (float)p.M_S1 * g0, mi / (float)p.M_S1 * g0);
+                    cf s_hat = make_float2(mr / (float)p.M_S1 * S->g0, mi / (float)p.M_S1 * S->g0);
                     s_hat = cmul(s_hat, make_float2(p.b_cos, p.b_sin));
                     const bool accept = (s_hat.x * s_hat.x + s_hat.y * s_hat.y > p.thresh * p.thresh) &&
                                         (s_hat.x > 0.f) && (fabsf(s_hat.y) < 0.32491969623290632616f * s_hat.x);
                     if (!accept) {
                         if (num_symbols == 16) {              // ofdmframesync_reset
                             th = 0; dth = 0; pilot_pos = 0; timer = 0; num_symbols = 0;
-                            sh0r = 0.f; sh0i = 0.f; phi_prime = 0.f; p1_prime = 0.f;
+                            S->s_hat0_re = 0.f; S->s_hat0_im = 0.f; phi_prime = 0.f; p1_prime = 0.f;
                             state = ST_SEEK;
-                            mix_start = 0; mix_end = 0;
+                            rms = 0; rme = 0;
                         } else timer = (int)M2;
                     } else {
                         // G *= M/sqrt(Na) * B ; smooth |G| and arg G with an order-4 polynomial over the active
@@ -584,8 +611,8 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                 num_symbols++;
                 pilot_pos = (pilot_pos + Mp) % 255u;
                 timer = (int)W;                    // liquid sets this unconditionally (also after a reset below)
-                const unsigned long long seg_start = mix_start;
-                mix_start = sidx; mix_end = OPEN;  // the next symbol is mixed with the trimmed NCO
+                const int seg_start = rms;
+                rms = rs; rme = RNONE;             // the next symbol is mixed with the trimmed NCO
 
                 // ---- derotate own subcarriers (null subcarriers carry 0: their equaliser tap is 0)
                 B2W_FORPTS {
@@ -603,7 +630,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                     slot = shfl0(slot);
                     if (slot < p.tap_cap) {
                         B2W_FORPTS { p.tap_X[(size_t)slot * M + B2W_I] = v[vt][s]; }
-                        if (lane == 0) { p.tap_chan[slot] = ch; p.tap_index[slot] = sidx - 1; }
+                        if (lane == 0) { p.tap_chan[slot] = ch; p.tap_index[slot] = p.sample_base + (unsigned long long)rs - 1ull; }
                     }
                 }
 
@@ -612,27 +639,27 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                 if (fstate == FS_PAYLOAD) {
                     // demap; the symbols leave one per byte (packet.cu packs them into the encoded bytes)
                     // (a frame that did not fit the arena is walked through without storing anything: take = 0 below)
-                    const unsigned int take_all = min(p.M_data, mod_len - pstart);
-                    const unsigned int take = (sym_abs == ~0ull) ? 0u : take_all;
+                    const unsigned int take_all = min(p.M_data, S->payload_mod_len - pstart);
+                    const unsigned int take = (S->sym_abs == ~0ull) ? 0u : take_all;
                     uint8_t * dst = p.arena + sym_off + pstart;
-                    const float alpha = p.qam_alpha[bps];
+                    const float alpha = p.qam_alpha[S->bps_payload];
 #define B2W_DEMAP(EXPR)                                                                  \
                     B2W_FORPTS {                                                         \
                         const unsigned int r = B2W_RK;                                   \
                         if (r < take) { const cf x = v[vt][s]; dst[r] = (uint8_t)(EXPR); } \
                     }
-                    if (ms == 40) { B2W_DEMAP((x.x > 0 ? 0u : 1u) + (x.y > 0 ? 0u : 2u)) }
-                    else if (ms == 39) { B2W_DEMAP(x.x > 0 ? 0u : 1u) }
-                    else if (bps == 6) { B2W_DEMAP(demod_qam_t<3>(x, alpha)) }
-                    else if (bps == 4) { B2W_DEMAP(demod_qam_t<2>(x, alpha)) }
-                    else if (bps == 8) { B2W_DEMAP(demod_qam_t<4>(x, alpha)) }
+                    if (S->ms_payload == 40) { B2W_DEMAP((x.x > 0 ? 0u : 1u) + (x.y > 0 ? 0u : 2u)) }
+                    else if (S->ms_payload == 39) { B2W_DEMAP(x.x > 0 ? 0u : 1u) }
+                    else if (S->bps_payload == 6) { B2W_DEMAP(demod_qam_t<3>(x, alpha)) }
+                    else if (S->bps_payload == 4) { B2W_DEMAP(demod_qam_t<2>(x, alpha)) }
+                    else if (S->bps_payload == 8) { B2W_DEMAP(demod_qam_t<4>(x, alpha)) }
                     else { B2W_DEMAP(demod_qam_t<1>(x, alpha)) }
 #undef B2W_DEMAP
                     pstart += take_all;
-                    if (pstart == mod_len) emit = 2;
+                    if (pstart == S->payload_mod_len) emit = 2;
                 } else {
                     // header: BPSK, 288 symbols; EVM is measured on them (framesyncstats_s.evm)
-                    const unsigned int take = min(p.M_data, 288u - hstart);
+                    const unsigned int take = min(p.M_data, 288u - S->header_sym_idx);
                     float ev = 0.f;
                     uint32_t * hwords = (uint32_t *)S->header_bits;
                     B2W_FORPTS {
@@ -640,16 +667,19 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                         if (r < take) {
                             const cf x = v[vt][s];
                             const unsigned int b = x.x > 0 ? 0u : 1u;
-                            const unsigned int gb = hstart + r;
+                            const unsigned int gb = S->header_sym_idx + r;
                             if (b) atomicOr(&hwords[gb >> 5], 1u << (8u * ((gb >> 3) & 3u) + 7u - (gb & 7u)));
                             const float dr = x.x - (b ? -1.0f : 1.0f);
                             ev += dr * dr + x.y * x.y;
                         }
                     }
                     ev = warp_sum(ev);
-                    evm_hat += ev;
-                    hstart += take;
-                    if (hstart == 288u) {
+                    const float evm_new = S->evm_hat + ev;
+                    const unsigned int hnew = S->header_sym_idx + take;
+                    __syncwarp();
+                    S->evm_hat = evm_new;
+                    S->header_sym_idx = hnew;
+                    if (hnew == 288u) {
                         __syncwarp();
                         // unscramble, de-interleave (n = 36, depth 4), Golay(24,12), CRC-32, parse
                         const uint8_t mask[4] = {0xb4, 0x6a, 0x8b, 0x45};
@@ -682,7 +712,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                             }
                             const uint32_t key = ((uint32_t)hd[14] << 24) | ((uint32_t)hd[15] << 16) | ((uint32_t)hd[16] << 8) | hd[17];
                             int valid = crc32_nibble(hd, 14) == key;
-                            S->evm_db = 10 * log10f(evm_hat / 288.0f);
+                            S->evm_db = 10 * log10f(S->evm_hat / 288.0f);
                             if (valid && hd[8] != 105) valid = 0;          // protocol id
                             const unsigned int plen = ((unsigned int)hd[9] << 8) | hd[10];
                             const unsigned int hms = hd[11], check = (hd[12] >> 5) & 7, fec0 = hd[12] & 0x1f, fec1 = hd[13] & 0x1f;
@@ -701,11 +731,11 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                         }
                         __syncwarp();
                         if (hres[0]) {
-                            ms = hres[1]; bps = hres[2]; mod_len = hres[3];
+                            S->ms_payload = hres[1]; S->bps_payload = hres[2]; S->payload_mod_len = hres[3];
                             fstate = FS_PAYLOAD;
                             // room for the payload symbols in the arena ring (one byte per symbol, never across the ring's end)
                             {
-                                const unsigned long long len = ((unsigned long long)mod_len + 15ull) & ~15ull;
+                                const unsigned long long len = ((unsigned long long)S->payload_mod_len + 15ull) & ~15ull;
                                 unsigned long long a = 0, ph = 0;
                                 if (lane == 0 && len) {
                                     if (len > p.arena_cap / 2) { a = ~0ull; atomicOr(&p.counters[1], 8u); }
@@ -716,10 +746,11 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                                         } while (ph + len > p.arena_cap);
                                     }
                                 }
-                                sym_abs = shfl0(a); sym_off = shfl0(ph);
+                                a = shfl0(a);
+                                S->sym_abs = a; sym_off = shfl0(ph);
                             }
                             // a frame without payload symbols is complete with its header (liquid would wait for ever)
-                            if (mod_len == 0) emit = 2;
+                            if (S->payload_mod_len == 0) emit = 2;
                         } else emit = 1;
                         __syncwarp();
                     }
@@ -727,8 +758,8 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
 
                 if (emit) {
                     // ---- append a frame record; the payload symbols are in the arena already
-                    const unsigned int m2 = (emit == 2) ? mod_len : 0u;      // symbols, one byte each
-                    const bool stored = m2 && sym_abs != ~0ull;
+                    const unsigned int m2 = (emit == 2) ? S->payload_mod_len : 0u;      // symbols, one byte each
+                    const bool stored = m2 && S->sym_abs != ~0ull;
                     if (lane == 0) {
                         unsigned int slot = 0, ok = 1;
                         unsigned long long offd = 0;
@@ -739,14 +770,14 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                             if (offd + ((plen + 4u + 15u) & ~15u) > p.decoded_cap) ok = 0;
                             // the ring must not have come round to this frame's symbols
                             const unsigned long long now = *(volatile unsigned long long *)(p.counters + 2);
-                            if (now - sym_abs > p.arena_cap - (((unsigned long long)m2 + 15ull) & ~15ull)) ok = 0;
+                            if (now - S->sym_abs > p.arena_cap - (((unsigned long long)m2 + 15ull) & ~15ull)) ok = 0;
                         }
                         if (direct) {
                             slot = atomicAdd(&p.counters[0], 1u);
                             if (slot >= p.recs_cap) ok = 0;
                         } else {
-                            slot = nrec_priv;
-                            if (slot >= pcap_w) ok = 0;
+                            slot = S->nrec;
+                            if (slot >= ctl->pcap) ok = 0;
                         }
                         if (!ok) atomicOr(&p.counters[1], 1u);
                         else {
@@ -757,77 +788,87 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                             r.payload_len = plen;
                             for (int i = 0; i < 8; i++) r.header[i] = S->header_dec[i];
                             r.evm = S->evm_db;
-                            r.rssi = -10.0f * log10f(g0);
+                            r.rssi = -10.0f * log10f(S->g0);
                             r.cfo = nco_freq_dev(dth);
-                            r.mod_scheme = (emit == 2) ? ms : 0u;
-                            r.mod_bps = (emit == 2) ? bps : 0u;
+                            r.mod_scheme = (emit == 2) ? S->ms_payload : 0u;
+                            r.mod_bps = (emit == 2) ? S->bps_payload : 0u;
                             r.check = (emit == 2) ? S->check : 0u;
                             r.fec0 = (emit == 2) ? S->fec0 : 0u;
                             r.fec1 = (emit == 2) ? S->fec1 : 0u;
                             r.detect_index = S->detect_index;
-                            r.complete_index = sidx - 1;
+                            r.complete_index = p.sample_base + (unsigned long long)rs - 1ull;
                             r.payload_offset = offd;
                             FrameAux a;
                             a.enc_len = stored ? S->payload_enc_len : 0u;
-                            a.sym_bps = stored ? bps : ((emit == 2 && m2) ? 0xffffffffu : 0u);    // 0xffffffff: payload not stored (too large)
+                            a.sym_bps = stored ? S->bps_payload : ((emit == 2 && m2) ? 0xffffffffu : 0u);    // 0xffffffff: payload not stored (too large)
                             a.sym_off = sym_off;
                             if (direct) { p.recs[slot] = r; p.aux[slot] = a; }
-                            else { p.wrecs[pbase_w + slot] = r; p.waux[pbase_w + slot] = a; }
+                            else { p.wrecs[ctl->pbase + slot] = r; p.waux[ctl->pbase + slot] = a; }
                         }
-                        if (!direct && ok) nrec_priv++;
+                        if (!direct && ok) S->nrec = slot + 1u;
                     }
-                    nrec_priv = shfl0(nrec_priv);
                     // ofdmflexframesync_reset; the symbol timer survives it, as in liquid
                     __syncwarp();
                     if (lane < 9) ((uint32_t *)S->header_bits)[lane] = 0u;
                     __syncwarp();
-                    fstate = FS_HEADER; hstart = 0; pstart = 0; evm_hat = 0.f;
-                    q_th = th; q_dth = dth_old;     // phase sample `sidx` would have had under the step this symbol was mixed with
-                    mix_start = seg_start; mix_end = sidx;
+                    fstate = FS_HEADER; S->header_sym_idx = 0; pstart = 0; S->evm_hat = 0.f;
+                    S->q_theta = th; S->q_dtheta = dth_old;     // phase sample `sidx` would have had under the step this symbol was mixed with
+                    rms = seg_start; rme = rs;
                     th = 0; dth = 0; pilot_pos = 0; num_symbols = 0;
-                    sh0r = 0.f; sh0i = 0.f; phi_prime = 0.f; p1_prime = 0.f;
+                    S->s_hat0_re = 0.f; S->s_hat0_im = 0.f; phi_prime = 0.f; p1_prime = 0.f;
                     state = ST_SEEK;
                     timer = (int)W;
-                    b_prev = b_last; b_last = sidx + 1; nb = min(nb + 1u, 2u);
+                    if (lane == 0) { S->b_prev = S->b_last; S->b_last = p.sample_base + (unsigned long long)rs + 1ull; S->nb = min(S->nb + 1u, 2u); }
+                    __syncwarp();
                 }
             }
 
             // ---- canonical state on a later worker's start?  (SEEK with timer 0 is only ever left by a seek event
             //      that detected nothing: NCO, pilot generator, header / payload progress are all reset there)
-            while (cand_pos < sidx) { cand++; cand_pos = start_of(cand); }
-            if (state == ST_SEEK && timer == 0 && cand_pos == sidx) { matched = 1; break; }
+            while (rcand < rs) { cand++; rcand = rstart(cand); }
+            if (state == ST_SEEK && timer == 0 && rcand == rs) { matched = 1; break; }
         }
 
         // ================================================================ end of a stretch
+        // (the stitcher's chain bookkeeping lives in ctl: lane 0 writes, everybody reads after a __syncwarp)
         if (!stitching) {
-            save_state(slot_of(cur), matched);
+            save_state(slot_of(ctl->cur), matched);
             unsigned int last = 0;
             __syncwarp();
             if (lane == 0) {
                 __threadfence();
-                last = (atomicAdd(&C->done, 1u) == n_act - 1u);
+                last = (atomicAdd(&C->done, 1u) == ctl->n_act - 1u);
                 __threadfence();
             }
             last = shfl0(last);
             if (!last) return;
             stitching = true;
-            sc = 0;
-            chain_b_last = __ldcg(&C->b_last); chain_b_prev = __ldcg(&C->b_prev);
+            if (lane == 0) { ctl->sc = 0; ctl->chain_b_last = __ldcg(&C->b_last); ctl->chain_b_prev = __ldcg(&C->b_prev); }
+            __syncwarp();
         } else {
             // back from a serial stretch that began in worker cur's final state
-            if (nb >= 2) { chain_b_last = b_last; chain_b_prev = b_prev; }
-            else if (nb == 1) { chain_b_prev = chain_b_last; chain_b_last = b_last; }
-            if (matched) sc = cand;                 // met worker cand's start in the canonical state: its results stand
-            else { save_state(slot_of(cur), 0); sc = n_act; }
+            if (lane == 0) {
+                if (S->nb >= 2) { ctl->chain_b_last = S->b_last; ctl->chain_b_prev = S->b_prev; }
+                else if (S->nb == 1) { ctl->chain_b_prev = ctl->chain_b_last; ctl->chain_b_last = S->b_last; }
+                ctl->sc = matched ? cand : ctl->n_act;      // matched: met worker cand's start in the canonical state, its results stand
+            }
+            __syncwarp();
+            if (!matched) save_state(slot_of(ctl->cur), 0);
+            __syncwarp();
         }
         // ---- walk the workers in order
-        unsigned int final_w = cur;
+        unsigned int final_w = ctl->cur;
         bool again = false;
-        while (sc < n_act) {
+        for (;;) {
+            const unsigned int sc = ctl->sc, n_act = ctl->n_act;
+            if (sc >= n_act) break;
             const WSync * Q = p.wst + slot_of(sc);
             const unsigned int q_nb = __ldcg(&Q->nb), q_matched = __ldcg(&Q->matched), q_nrec = __ldcg(&Q->nrec);
-            if (q_nb >= 2) { chain_b_last = __ldcg(&Q->b_last); chain_b_prev = __ldcg(&Q->b_prev); }
-            else if (q_nb == 1) { chain_b_prev = chain_b_last; chain_b_last = __ldcg(&Q->b_last); }
+            __syncwarp();
+            if (lane == 0) {
+                if (q_nb >= 2) { ctl->chain_b_last = __ldcg(&Q->b_last); ctl->chain_b_prev = __ldcg(&Q->b_prev); }
+                else if (q_nb == 1) { ctl->chain_b_prev = ctl->chain_b_last; ctl->chain_b_last = __ldcg(&Q->b_last); }
+            }
             if (sc != 0 && q_nrec) {
                 // commit the private record list
                 unsigned int base = 0;
@@ -846,22 +887,31 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
             }
             final_w = sc;
             if (sc == n_act - 1) break;
-            if (q_matched) { sc++; continue; }
+            if (q_matched) {
+                __syncwarp();
+                if (lane == 0) ctl->sc = sc + 1;
+                __syncwarp();
+                continue;
+            }
             // worker sc did not arrive in the canonical state: carry on serially from its final (true) state
             load_state(slot_of(sc));
-            cur = sc; direct = true; limit = E1;
-            cand = sc + 2; cand_pos = start_of(cand);
+            if (lane == 0) ctl->cur = sc;
+            __syncwarp();
+            direct = true; rlimit = (int)p.nsamples;
+            cand = sc + 2; rcand = rstart(cand);
             again = true;
             break;
         }
         if (again) continue;
 
         // ================================================================ the stream's launch is complete
-        if (sc >= n_act) final_w = cur;
+        if (ctl->sc >= ctl->n_act) final_w = ctl->cur;
         {
             const WSync * F = p.wst + slot_of(final_w);
             __syncwarp();
             const int f_state = __ldcg(&F->state), f_timer = __ldcg(&F->timer);
+            const unsigned long long E1 = p.sample_base + p.nsamples;
+            const unsigned long long chain_b_last = ctl->chain_b_last, chain_b_prev = ctl->chain_b_prev;
             unsigned long long nx = 0;
             unsigned int per = 0;
             const bool have = chain_b_last && chain_b_prev && chain_b_last > chain_b_prev && (chain_b_last - chain_b_prev) < (1ull << 31);
@@ -885,7 +935,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
             }
             if (lane == 0) {
                 C->pred_next[par ^ 1u] = nx; C->pred_period[par ^ 1u] = per;
-                C->head[par ^ 1u] = (head + final_w) % p.wslots;
+                C->head[par ^ 1u] = (ctl->head + final_w) % p.wslots;
                 C->b_last = chain_b_last; C->b_prev = chain_b_prev;
                 C->done = 0;
             }
@@ -955,12 +1005,12 @@ cudaError_t syncw_launch(const SyncParams & p, cudaStream_t st)
     case 256: return syncw_launch_t<256, 4, 4>(p, st);
     case 512:
         switch (variant) {
-        case 1:  return syncw_launch_t<512, 4, 5>(p, st);
         case 2:  return syncw_launch_t<512, 2, 8>(p, st);
         case 3:  return syncw_launch_t<512, 2, 10>(p, st);
         case 4:  return syncw_launch_t<512, 1, 16>(p, st);
         case 5:  return syncw_launch_t<512, 1, 20>(p, st);
-        default: return syncw_launch_t<512, 4, 4>(p, st);
+        case 6:  return syncw_launch_t<512, 4, 4>(p, st);
+        default: return syncw_launch_t<512, 4, 5>(p, st);      // 96 registers, 20 workers per SM
         }
     default:  return cudaErrorInvalidValue;
     }
