@@ -247,21 +247,49 @@ def measure_config64(args, local_rank, pkg, barrier):
 METRIC = "complex Msamples/s through multichannelrx (64ch OFDM) at 1/2/4/8 GPU vs CPU"
 
 
-def run_sharded(args, rank, local_rank, world, period, expected):
-    """one wideband stream over `world` GPUs: time-sharded channelizer, all-to-all, channel-sharded
-    synchronisers (liquid-usrp_b200/sharded.py)"""
+def bind_near_gpu(index):
+    """run this rank's host threads (and therefore its pinned allocations, first touch) on the CPUs next to its GPU:
+    without it every rank of a box pins on NUMA node 0 and the host side of the PCIe copies is shared"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
+def run_sharded(args, rank, local_rank, world, period, expected, flen):
+    """ONE wideband stream over `world` GPUs (liquid-usrp_b200/sharded.py ShardedRx over b2_mcrx_shard_*): chunks of the
+    stream dealt round-robin to the ranks, channelizer storing straight into the owning GPU's memory over NVLink,
+    synchronisers sharded over channels, a one-word NCCL all-reduce per step, frame records gathered on rank 0.
+    Weak scaling: every rank channelizes `reps` frame periods per step-of-the-bench (the N = 1 workload), so the stream
+    is `world` times longer."""
     import importlib
     import torch
     import torch.distributed as dist
     sh = importlib.import_module("liquid-usrp_b200.sharded")
     w = WORKLOAD
     K = 2 * w["N"]
-    t_local = (len(period) // K) * args.reps
-    rxs = sh.ShardedMultichannelRx(w["N"], w["M"], w["cp"], w["taper"], t_local * world, rank, world, device=local_rank)
-    # the stream is periodic in `period`, every shard starts on a period boundary: halo = end of a period
-    tile = np.concatenate([period[-sh.HALO_BLOCKS * K:], np.tile(period, args.reps)])
-    d_x = torch.from_numpy(tile.view(np.float32)).cuda().view(-1, 2)
-    d_x = torch.view_as_complex(d_x)
+    # a chunk = 13 frame periods (74 880 blocks, 38 M wideband samples), 7 chunks per rank per call = 91 periods
+    per_chunk = 13
+    steps = max(1, args.reps // per_chunk)
+    tc = per_chunk * flen
+    rx = sh.ShardedRx(w["N"], w["M"], w["cp"], w["taper"], tc, steps, rank, world, device=local_rank)
+    # the stream is periodic in `period` and every chunk starts on a period boundary: [halo | chunk] is the same for all
+    tile = np.concatenate([period[-sh.HALO_BLOCKS * K:], np.tile(period, per_chunk)])
+    d_x = torch.from_numpy(tile.view(np.float32)).cuda()
+    h_x = torch.from_numpy(tile.view(np.float32)).pin_memory()
+    ptrs = [d_x.data_ptr()] * steps
+    dev = torch.device("cuda", local_rank)
 
     def barrier():
         torch.cuda.synchronize()
@@ -269,81 +297,93 @@ def run_sharded(args, rank, local_rank, world, period, expected):
             dist.barrier()
         torch.cuda.synchronize()
 
+    frames_call = w["N"] * steps * per_chunk                      # frames a rank decodes per call (its channels, all chunks of the call)
+    cap = int(1.25 * frames_call * (88 + w["payload"] + 16)) + (1 << 20)
+    pending = [None]
+    gathered = [0]
+
+    def one_call(host):
+        if host:
+            rx.execute_host([h_x] * steps)
+        else:
+            rx.execute_device(ptrs)
+        recs, pl = rx.poll_view()                                 # this rank's own frames (pinned host memory, zero copy)
+        ticket = rx.gather_async(cap)                             # NCCL gather to rank 0 + D2H there, overlapping the next call
+        if pending[0] is not None:
+            res = rx.gather_wait(pending[0])
+            if res is not None:
+                gathered[0] = sum(len(r) for r, _p in res)
+        pending[0] = ticket
+        return recs, pl, gathered[0]
+
+    def drain():
+        if pending[0] is not None:
+            res = rx.gather_wait(pending[0])
+            if res is not None:
+                gathered[0] = sum(len(r) for r, _p in res)
+                # rank 0 holds every rank's frames: spot-check one payload per source rank
+                for r, p_ in res:
+                    if len(r):
+                        c, o = int(r["channel"][-1]), int(r["payload_offset"][-1])
+                        assert int(r["payload_valid"].min()) == 1
+                        assert np.array_equal(p_[o:o + w["payload"]], expected[c][1]), "gathered payload mismatch on channel %d" % c
+            pending[0] = None
+        return gathered[0]
+
+    n_call = steps * tc * K * world                  # wideband samples of the whole stream per call
     for _ in range(args.warmup):
-        rxs.execute_device(d_x)
-        recs, pl = rxs.poll()
+        recs, pl, _n = one_call(False)
+    drain()
+    assert len(recs) >= (w["N"] // world) * (steps * per_chunk * world - 1), "frames missing: %d" % len(recs)
+    assert int(recs["payload_valid"].min()) == 1
+    for i in (0, len(recs) // 2, len(recs) - 1):
+        c, o = int(recs["channel"][i]), int(recs["payload_offset"][i])
+        assert np.array_equal(pl[o:o + w["payload"]], expected[c][1]), "payload mismatch on channel %d" % c
     clk = Clocks(local_rank)
     clk.start()
     barrier()
     t0 = time.perf_counter()
     nfr = 0
     for _ in range(args.steps):
-        rxs.execute_device(d_x)
-        recs, pl = rxs.poll()
-        allr, allp = sh.gather_frames(recs, pl, world, rank, torch.device("cuda", local_rank))
-        if rank == 0:
-            nfr += sum(len(r) for r in allr)
+        recs, pl, n = one_call(False)
+        nfr += n
+    nfr += drain() - 0
     barrier()
     dt = time.perf_counter() - t0
+    for _ in range(2):
+        one_call(True)
+    drain()
+    barrier()
+    t1 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        recs, pl, n = one_call(True)
+        d2h += recs.nbytes + len(pl)
+    drain()
+    barrier()
+    dt_e2e = time.perf_counter() - t1
     clk.stop_flag = True
     clk.join()
-    assert len(recs) >= (w["N"] // world) * (args.reps * world - 1)
-    assert int(recs["payload_valid"].min()) == 1
-    c = int(recs["channel"][0]); o = int(recs["payload_offset"][0])
-    assert np.array_equal(pl[o:o + w["payload"]], expected[c][1])
-    times = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dt = float(times[0])
-    n_step = t_local * world * K
-    if rank == 0:
-        print(json.dumps({"metric": METRIC, "value": n_step * args.steps / dt / 1e6, "unit": "Msamples/s", "n_gpus": world,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic (oracle transmitter, one frame period tiled on device)",
-                          "config": {"workload": w["name"], "samples_per_step": n_step, "frames_per_step": nfr // args.steps,
-                                     "parallelism": "one stream: time-sharded channelizer -> NCCL all-to-all -> %d channels/rank" % (w["N"] // world)},
-                          "gpu_launches": args.steps * (1 + 2 * world) * world, "clocks": clk.summary()}), flush=True)
-    rxs.close()
-    if world > 1:
-        dist.destroy_process_group()
+    rx.close()
+    peak, peak_src = peaks()
+    val = n_call * args.steps / float(times[0]) / 1e6
+    return {"value": val, "e2e": n_call * args.steps / float(times[1]) / 1e6, "ms_per_step": 1e3 * float(times[0]) / args.steps,
+            "samples_per_step": n_call, "frames_per_step": nfr // max(args.steps, 1), "steps_per_call": steps, "chunk_blocks": tc,
+            "h2d_bytes_per_step": n_call * 8 + steps * world * sh.HALO_BLOCKS * K * 8, "d2h_bytes_per_step": d2h // max(args.steps, 1) * world,
+            "launches_per_step": steps * world * (1 + 4), "clocks": clk.summary(),
+            "path_frac": val * 1e6 * B_ALG_PATH / 1e9 / (peak * world)}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours")
-    ap.add_argument("--reps", type=int, default=91, help="frame periods per step (91 -> 2^28 wideband samples, the per-GPU share "
-                    "of BASELINE configs[4]'s 2^31; 2.1 GB of input per step, far larger than L2)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"])
-    ap.add_argument("--no-config64", action="store_true", help="skip the extra 64-channel (BASELINE configs[2]) leg")
-    ap.add_argument("--receivers", type=int, default=1, help="extra leg: R independent receivers sharing this GPU (reported under "
-                    "'multi_receiver', never as the headline): shows that one receiver is bound by its 256 serial chains")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-    args.warmup = max(args.warmup, 3)
-
+def run_single(args, rank, local_rank, world, period, expected, flen, extras=True):
+    """one complete 256-channel receiver per rank (N = 1: THE receiver; N > 1: independent replicas, no data-path
+    collective) -> the JSON line as a dict"""
     import torch
     import torch.distributed as dist
     from b2 import pkg
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w = WORKLOAD
-    period, expected, flen = make_period()
-    if args.mode == "sharded":
-        run_sharded(args, rank, local_rank, world, period, expected)
-        return
     n_step = len(period) * args.reps
     # device-resident input (the "stubbed UHD source"), tiled on the device
     d_period = torch.from_numpy(period.view(np.float32)).cuda()
@@ -451,7 +491,7 @@ def main():
                          "path": {"alg_bytes_per_sample": B_ALG_PATH, "achieved": n_step * B_ALG_PATH / (kt_avg[3] * 1e-3) / 1e9,
                                   "frac": n_step * B_ALG_PATH / (kt_avg[3] * 1e-3) / 1e9 / peak}},
             "clocks": clk.summary()}
-    if not args.no_config64 and world == 1:
+    if extras and not args.no_config64 and world == 1:
         line["config64"] = measure_config64(args, local_rank, pkg, barrier)
     if args.receivers > 1:
         rxs = [rx] + [pkg.MultichannelRx(w["N"], w["M"], w["cp"], w["taper"], device=local_rank, max_batch=n_step) for _ in range(args.receivers - 1)]
@@ -474,7 +514,7 @@ def main():
                                   "note": "aggregate of independent 256-channel receivers on ONE GPU, each fed the same device-resident stream"}
         for r in rxs[1:]:
             r.close()
-    if rank == 0 and world == 1 and not args.no_cpu:       # reported baseline: rank 0 at N = 1 only
+    if extras and rank == 0 and world == 1 and not args.no_cpu:       # reported baseline: rank 0 at N = 1 only
         cores = cpu_cores()
         ncpu, tcpu, _nf, per_step = cpu_receivers(period, cores, 2, seconds=10.0)
         n1, t1, _nf1, _ = cpu_receivers(period, 1, 2, seconds=4.0)
@@ -483,9 +523,76 @@ def main():
                                 "sample": "%d wideband samples in ~10 s over %d independent receivers (one per host core; the "
                                           "reference's DSP path is single-threaded): reference lib/multichannelrx.cc compiled "
                                           "unmodified over the oracle's C restatement of liquid-dsp, gcc -O2" % (ncpu, cores)}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     rx.close()
+    return line
+
+
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--reps", type=int, default=91, help="frame periods per step (91 -> 2^28 wideband samples, the per-GPU share "
+                    "of BASELINE configs[4]'s 2^31; 2.1 GB of input per step, far larger than L2)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "sharded"], help="N > 1: auto / sharded = ONE stream split over the "
+                    "GPUs (the headline; independent replicas are reported alongside), replicas = independent receivers only")
+    ap.add_argument("--no-config64", action="store_true", help="skip the extra 64-channel (BASELINE configs[2]) leg")
+    ap.add_argument("--receivers", type=int, default=1, help="extra leg: R independent receivers sharing this GPU (reported under "
+                    "'multi_receiver', never as the headline): shows that one receiver is bound by its 256 serial chains")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from b2 import pkg
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        bind_near_gpu(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w = WORKLOAD
+    period, expected, flen = make_period()
+    if (world > 1 and args.mode != "replicas") or args.mode == "sharded":
+        sh = run_sharded(args, rank, local_rank, world, period, expected, flen)
+        steps_keep = args.steps
+        args.steps = max(3, min(args.steps, 6))
+        rep = run_single(args, rank, local_rank, world, period, expected, flen, extras=False)
+        args.steps = steps_keep
+        if rank == 0:
+            line = dict(rep)
+            line.update({"value": sh["value"], "ms_per_step": sh["ms_per_step"], "steps": args.steps,
+                         "e2e": {"value": sh["e2e"], "unit": "Msamples/s", "h2d_bytes_per_step": sh["h2d_bytes_per_step"],
+                                 "d2h_bytes_per_step": sh["d2h_bytes_per_step"]},
+                         "gpu_launches": sh["launches_per_step"] * args.steps, "clocks": sh["clocks"]})
+            line["config"] = {"workload": WORKLOAD["name"], "samples_per_step": sh["samples_per_step"],
+                              "input_bytes_per_step": sh["samples_per_step"] * 8, "l2_policy": "input per rank (%.0f MB/step) larger than L2" % (sh["samples_per_step"] * 8 / 1e6 / world),
+                              "frames_per_step": sh["frames_per_step"],
+                              "parallelism": "one stream split over %d GPUs: round-robin time chunks -> channelizer storing into the owning GPU over NVLink -> "
+                                             "%d channels/GPU synchronisers; NCCL: one-word all-reduce per step + gather of frame records" % (world, WORKLOAD["N"] // world),
+                              "steps_per_call": sh["steps_per_call"], "chunk_blocks": sh["chunk_blocks"]}
+            line["roofline"] = {"bound": "hbm", "kernel": "whole path", "achieved": sh["path_frac"] * peaks()[0], "peak": peaks()[0], "unit": "GB/s",
+                                "frac": sh["path_frac"], "traffic": None, "peak_source": peaks()[1], "alg_bytes_per_sample": B_ALG_PATH,
+                                "note": "per-GPU average over the split: %.2f B of algorithmic traffic per wideband sample" % B_ALG_PATH}
+            line["replicas"] = {"value": rep["value"], "e2e": rep["e2e"]["value"], "unit": "Msamples/s", "ms_per_step": rep["ms_per_step"],
+                                "parallelism": rep["config"]["parallelism"], "note": "independent receivers, no data-path collective (round-1 headline mode)"}
+            for k in ("kernels_ms_per_step", "host_ms_per_step"):
+                line.pop(k, None)
+            print(json.dumps(line), flush=True)
+    else:
+        line = run_single(args, rank, local_rank, world, period, expected, flen)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -115,6 +115,52 @@ int b2_mcrx_channelize_device(b2_mcrx * q, const float * x_dev, size_t n_blocks,
  * calls equals one call); frames are queued for b2_mcrx_poll. */
 int b2_mcrx_sync_device(b2_mcrx * q, const float * in_dev, size_t n, size_t in_stride);
 
+/* ------------------------------------------------------------------ one rank of a multi-GPU multichannelrx
+ * The reference runs multichannelrx::Execute (lib/multichannelrx.cc:155-195) on one core and leaves "run each
+ * channel in its own thread" as a TODO (:184, :193-194).  Here ONE wideband stream is spread over `world` GPUs of a
+ * box, one process per GPU:
+ *   stage 1  NCO + analysis bank (lib/multichannelrx.cc:163-164,188), sharded over TIME in round-robin chunks of
+ *            chunk_blocks blocks of 2N samples: the rank handles chunks rank, rank + world, rank + 2 world, ...
+ *   scatter  fused into stage 1: every channel's run is stored straight into the memory of the GPU that owns the
+ *            channel (peer mapping over NVLink, handles exchanged with _export / _connect); no staging, no repack
+ *   stage 2  ofdmflexframesync + packet decode (lib/multichannelrx.cc:193-194), sharded over CHANNELS: the rank owns
+ *            channels [rank N/world, (rank+1) N/world) for all time and runs them over `world` exchanged chunks per step
+ * The caller (one per rank, e.g. liquid-usrp_b200/sharded.py over torch.distributed) provides the two CUDA streams
+ * and the only cross-rank ordering the data path needs: after stage1(step) a barrier among the ranks on stream_stage1
+ * (a one-word NCCL all-reduce), which stage2(step) must wait for; and stage1(step + B2_SHARD_SLOTS - 1) must not
+ * start before every rank's stage2(step) is done (join that barrier only behind the own stage2(step - ...) event). */
+typedef struct b2_mcrx_shard_s b2_mcrx_shard;
+#define B2_SHARD_SLOTS 3
+#define B2_SHARD_HALO_BLOCKS 13     /* taps per branch - 1 of the receive bank (m = 7, lib/multichannelrx.cc:89) */
+/* steps_per_call: steps (of world chunks each) between _begin and _end, sizes the frame output */
+int b2_mcrx_shard_create(unsigned int num_channels, unsigned int M, unsigned int cp_len, unsigned int taper_len,
+                         const unsigned char * p, int device, unsigned int rank, unsigned int world,
+                         size_t chunk_blocks, size_t steps_per_call, void * stream_stage1, void * stream_stage2,
+                         b2_mcrx_shard ** out);
+int b2_mcrx_shard_destroy(b2_mcrx_shard * q);
+/* 64 opaque bytes naming this rank's exchange buffer (cudaIpcMemHandle_t); gather them from all ranks ... */
+int b2_mcrx_shard_export(b2_mcrx_shard * q, void * handle64);
+/* ... and hand every rank the whole list, in rank order (world x 64 bytes) */
+int b2_mcrx_shard_connect(b2_mcrx_shard * q, const void * handles, size_t n_handles);
+int b2_mcrx_shard_begin(b2_mcrx_shard * q);
+/* stage 1 + scatter of this rank's chunk of step `step` (absolute chunk index step*world + rank since the stream
+ * began): x_dev points at the 13 halo blocks before the chunk (zeros at the start of a stream) followed by
+ * chunk_blocks blocks; asynchronous on stream_stage1 */
+int b2_mcrx_shard_stage1(b2_mcrx_shard * q, const float * x_dev, uint64_t step);
+/* stage 2 over the world chunks of `step`, asynchronous on stream_stage2 (+ the handle's decode / copy streams) */
+int b2_mcrx_shard_stage2(b2_mcrx_shard * q, uint64_t step);
+/* end of the call: waits for stage 2 of every step since _begin; frames are queued for _poll (channel = global index) */
+int b2_mcrx_shard_end(b2_mcrx_shard * q);
+int b2_mcrx_shard_poll(b2_mcrx_shard * q, b2_frame_rec * recs, size_t recs_cap, size_t * n_recs,
+                       uint8_t * payloads, size_t payloads_cap, size_t * n_payload_bytes);
+int b2_mcrx_shard_poll_view(b2_mcrx_shard * q, const b2_frame_rec ** recs, size_t * n_recs,
+                            const uint8_t ** payloads, size_t * n_payload_bytes);
+/* the frames of the call that just ended, still in DEVICE memory, packed for a collective: dst_dev receives
+ * [n_recs records of sizeof(b2_frame_rec) | payload bytes], payload_offset relative to the payload part, records in
+ * completion order per synchroniser worker (not globally sorted); asynchronous on stream_stage2 */
+int b2_mcrx_shard_pack_results(b2_mcrx_shard * q, void * dst_dev, size_t cap_bytes, size_t * n_recs, size_t * n_payload_bytes);
+int b2_mcrx_shard_reset(b2_mcrx_shard * q);
+
 /* ------------------------------------------------------------------ multichanneltx
  * replaces: multichanneltx::multichanneltx        lib/multichanneltx.cc:41-100
  *           multichanneltx::IsChannelReadyForData lib/multichanneltx.cc:152-162

@@ -81,6 +81,19 @@ _PROTOS = {
     "b2_msresamp_execute_device": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "b2_msresamp_execute_to_device": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "b2_mcrx_set_resampler": (C.c_int, [_vp, C.c_float, C.c_float]),
+    "b2_mcrx_shard_create": (C.c_int, [C.c_uint, C.c_uint, C.c_uint, C.c_uint, _vp, C.c_int, C.c_uint, C.c_uint, _sz, _sz, _vp, _vp,
+                                       C.POINTER(_vp)]),
+    "b2_mcrx_shard_destroy": (C.c_int, [_vp]),
+    "b2_mcrx_shard_export": (C.c_int, [_vp, _vp]),
+    "b2_mcrx_shard_connect": (C.c_int, [_vp, _vp, _sz]),
+    "b2_mcrx_shard_begin": (C.c_int, [_vp]),
+    "b2_mcrx_shard_stage1": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "b2_mcrx_shard_stage2": (C.c_int, [_vp, C.c_uint64]),
+    "b2_mcrx_shard_end": (C.c_int, [_vp]),
+    "b2_mcrx_shard_poll": (C.c_int, [_vp, _vp, _sz, C.POINTER(_sz), _vp, _sz, C.POINTER(_sz)]),
+    "b2_mcrx_shard_reset": (C.c_int, [_vp]),
+    "b2_mcrx_shard_poll_view": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), C.POINTER(_sz)]),
+    "b2_mcrx_shard_pack_results": (C.c_int, [_vp, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz)]),
 }
 
 

@@ -971,15 +971,10 @@ extern "C" int b2_mcrx_read_channelizer(b2_mcrx * q, float * out, size_t cap_sam
 
 extern "C" void * b2_mcrx_stream(b2_mcrx * q) { return q ? (void *)q->stream : nullptr; }
 
-extern "C" int b2_mcrx_channelize_device(b2_mcrx * q, const float * x_dev, size_t n_blocks, int64_t sample_offset,
-                                         float * out_dev, size_t out_stride)
+// stage 1 alone on a time shard; `peers` != nullptr: channel c is written into peers[c / cpp] (multi-GPU split)
+static int mcrx_channelize(b2_mcrx * q, const float * x_dev, size_t n_blocks, int64_t sample_offset, float * out_dev,
+                           size_t out_stride, size_t out_col0, cf * const * peers, unsigned int n_peer, unsigned int cpp, cudaStream_t st)
 {
-    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
-    if (n_blocks == 0) return B2_OK;
-    if (!x_dev || !out_dev) return b2_fail(B2_ERR_ARG, "null pointer");
-    if (((uintptr_t)x_dev) & 15) return b2_fail(B2_ERR_ARG, "input must be 16-byte aligned");
-    if (n_blocks > 0x7fffffffu) return b2_fail(B2_ERR_ARG, "too many blocks in one call");
-    B2_CUDA(cudaSetDevice(q->device));
     AnalyzerParams ap;
     memset(&ap, 0, sizeof(ap));
     ap.seg0 = (const cf *)x_dev; ap.rows0 = 0xffffffffu; ap.seg1 = (const cf *)x_dev;
@@ -989,12 +984,28 @@ extern "C" int b2_mcrx_channelize_device(b2_mcrx * q, const float * x_dev, size_
     ap.taps = q->t_taps.as<float>();
     ap.dtheta = q->nco_dtheta;
     ap.theta0 = (uint32_t)((uint64_t)sample_offset) * q->nco_dtheta;
-    ap.out = (cf *)out_dev; ap.out_stride = out_stride; ap.out_col0 = 0;
+    ap.out = (cf *)out_dev; ap.out_stride = out_stride; ap.out_col0 = out_col0;
+    if (peers) {
+        for (unsigned int i = 0; i < n_peer && i < 8; i++) ap.out_peer[i] = peers[i];
+        ap.n_peer = n_peer; ap.chan_per_peer = cpp;
+    }
     ap.fft.n = q->K; ap.fft.npass = q->fftK.npass; ap.fft.radices = 0;
     for (unsigned int i = 0; i < q->fftK.npass; i++) ap.fft.radices |= fft_radix_code(q->fftK.radix[i]) << (4 * i);
     ap.fft.perm = q->t_perm.as<uint16_t>(); ap.fft.tw = q->t_tw.as<cf>();
-    B2_CUDA(analyzer_launch(ap, q->an_grid, q->an_smem, q->stream));
+    B2_CUDA(analyzer_launch(ap, q->an_grid, q->an_smem, st));
     return B2_OK;
+}
+
+extern "C" int b2_mcrx_channelize_device(b2_mcrx * q, const float * x_dev, size_t n_blocks, int64_t sample_offset,
+                                         float * out_dev, size_t out_stride)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    if (n_blocks == 0) return B2_OK;
+    if (!x_dev || !out_dev) return b2_fail(B2_ERR_ARG, "null pointer");
+    if (((uintptr_t)x_dev) & 15) return b2_fail(B2_ERR_ARG, "input must be 16-byte aligned");
+    if (n_blocks > 0x7fffffffu) return b2_fail(B2_ERR_ARG, "too many blocks in one call");
+    B2_CUDA(cudaSetDevice(q->device));
+    return mcrx_channelize(q, x_dev, n_blocks, sample_offset, out_dev, out_stride, 0, nullptr, 0, 0, q->stream);
 }
 
 extern "C" int b2_mcrx_sync_device(b2_mcrx * q, const float * in_dev, size_t n, size_t in_stride)
@@ -1126,4 +1137,167 @@ extern "C" int b2_ofdmsync_last_timing(b2_ofdmsync * q, float ms[4])
     q->core.fetch_timing();
     for (int i = 0; i < 4; i++) ms[i] = q->core.last_ms[i];
     return B2_OK;
+}
+
+// ================================================================== one rank of a multi-GPU multichannelrx
+struct b2_mcrx_shard_s {
+    int device = 0;
+    unsigned int N = 0, K = 0, rank = 0, world = 1, cpp = 0;
+    size_t tc = 0, steps = 0, row = 0;   // chunk blocks, steps per call, row length (world * tc) of an exchange slot
+    cudaStream_t s1 = nullptr, s2 = nullptr;
+    b2_mcrx * chan = nullptr;            // stage 1: tables and launch configuration of a full N-channel receiver
+    SyncCore core;                       // stage 2: N / world streams
+    DevBuf d_xchg;                       // [B2_SHARD_SLOTS][N / world][world * tc]
+    cf * peer[8] = {};                   // every rank's exchange buffer as seen from this device
+    bool connected = false, in_call = false;
+};
+
+extern "C" int b2_mcrx_shard_destroy(b2_mcrx_shard * q)
+{
+    if (!q) return B2_OK;
+    cudaSetDevice(q->device);
+    cudaDeviceSynchronize();
+    for (unsigned int i = 0; i < q->world && i < 8; i++)
+        if (q->connected && i != q->rank && q->peer[i]) cudaIpcCloseMemHandle(q->peer[i]);
+    q->core.destroy();
+    if (q->chan) b2_mcrx_destroy(q->chan);
+    delete q;
+    return B2_OK;
+}
+
+extern "C" int b2_mcrx_shard_create(unsigned int N, unsigned int M, unsigned int cp, unsigned int taper, const unsigned char * p,
+                                    int device, unsigned int rank, unsigned int world, size_t chunk_blocks, size_t steps_per_call,
+                                    void * stream_stage1, void * stream_stage2, b2_mcrx_shard ** out)
+{
+    if (!out) return b2_fail(B2_ERR_ARG, "null output pointer");
+    *out = nullptr;
+    if (world < 1 || world > 8 || rank >= world) return b2_fail(B2_ERR_ARG, "rank %u of %u: at most 8 ranks", rank, world);
+    if (N % world) return b2_fail(B2_ERR_ARG, "the number of channels (%u) must divide by the number of ranks (%u)", N, world);
+    if (chunk_blocks < 64 || steps_per_call < 1) return b2_fail(B2_ERR_ARG, "chunk_blocks >= 64 and steps_per_call >= 1 required");
+    if ((uint64_t)chunk_blocks * world > 0x3fffffffull) return b2_fail(B2_ERR_ARG, "chunk too long");
+    b2_mcrx_shard * q = new b2_mcrx_shard_s;
+    q->device = device; q->N = N; q->K = 2 * N; q->rank = rank; q->world = world; q->cpp = N / world;
+    q->tc = chunk_blocks; q->steps = steps_per_call; q->row = chunk_blocks * world;
+    q->s1 = (cudaStream_t)stream_stage1; q->s2 = (cudaStream_t)stream_stage2;
+    int rc = B2_OK;
+    do {
+        if ((rc = b2_mcrx_create(N, M, cp, taper, p, device, 4 * (size_t)q->K, &q->chan))) break;
+        if ((rc = q->d_xchg.alloc(sizeof(cf) * (size_t)B2_SHARD_SLOTS * q->cpp * q->row))) break;
+        B2_CUDA(cudaMemset(q->d_xchg.p, 0, q->d_xchg.bytes));
+        q->peer[rank] = q->d_xchg.as<cf>();
+        // stage 2: one batch = one call = steps_per_call launches of world * chunk_blocks samples per stream
+        if ((rc = q->core.init(M, cp, taper, p, q->cpp, q->row * steps_per_call, device, q->s2))) break;
+        q->core.sp.chan_base = rank * q->cpp;                           // records carry the global channel index
+        q->connected = (world == 1);
+    } while (0);
+    if (rc) { b2_mcrx_shard_destroy(q); return rc; }
+    *out = q;
+    return B2_OK;
+}
+
+extern "C" int b2_mcrx_shard_export(b2_mcrx_shard * q, void * handle64)
+{
+    if (!q || !handle64) return b2_fail(B2_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    B2_CUDA(cudaSetDevice(q->device));
+    cudaIpcMemHandle_t h;
+    B2_CUDA(cudaIpcGetMemHandle(&h, q->d_xchg.p));
+    memcpy(handle64, &h, 64);
+    return B2_OK;
+}
+
+extern "C" int b2_mcrx_shard_connect(b2_mcrx_shard * q, const void * handles, size_t n_handles)
+{
+    if (!q || !handles) return b2_fail(B2_ERR_ARG, "null argument");
+    if (n_handles != q->world) return b2_fail(B2_ERR_ARG, "expected %u handles, got %zu", q->world, n_handles);
+    B2_CUDA(cudaSetDevice(q->device));
+    for (unsigned int i = 0; i < q->world; i++) {
+        if (i == q->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)i, 64);
+        void * ptr = nullptr;
+        B2_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        q->peer[i] = (cf *)ptr;
+    }
+    q->connected = true;
+    return B2_OK;
+}
+
+extern "C" int b2_mcrx_shard_begin(b2_mcrx_shard * q)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    if (!q->connected) return b2_fail(B2_ERR_ARG, "b2_mcrx_shard_connect has not been called");
+    B2_CUDA(cudaSetDevice(q->device));
+    B2_TRY(q->core.begin_batch());
+    q->in_call = true;
+    return B2_OK;
+}
+
+extern "C" int b2_mcrx_shard_stage1(b2_mcrx_shard * q, const float * x_dev, uint64_t step)
+{
+    if (!q || !x_dev) return b2_fail(B2_ERR_ARG, "null argument");
+    if (!q->connected) return b2_fail(B2_ERR_ARG, "b2_mcrx_shard_connect has not been called");
+    if (((uintptr_t)x_dev) & 15) return b2_fail(B2_ERR_ARG, "input must be 16-byte aligned");
+    B2_CUDA(cudaSetDevice(q->device));
+    const uint64_t chunk = step * q->world + q->rank;                   // absolute chunk index of the stream
+    const int64_t offset = ((int64_t)(chunk * q->tc) - B2_SHARD_HALO_BLOCKS) * (int64_t)q->K;
+    // slot base of every peer; this rank's chunk lands in columns [rank * tc, (rank + 1) * tc) of the slot's rows
+    cf * dst[8];
+    const size_t slot_off = (size_t)(step % B2_SHARD_SLOTS) * q->cpp * q->row;
+    for (unsigned int i = 0; i < q->world; i++) dst[i] = q->peer[i] + slot_off;
+    return mcrx_channelize(q->chan, x_dev, q->tc, offset, nullptr, q->row, (size_t)q->rank * q->tc, dst, q->world, q->cpp, q->s1);
+}
+
+extern "C" int b2_mcrx_shard_stage2(b2_mcrx_shard * q, uint64_t step)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    if (!q->in_call) return b2_fail(B2_ERR_ARG, "b2_mcrx_shard_begin has not been called");
+    B2_CUDA(cudaSetDevice(q->device));
+    const cf * in = q->d_xchg.as<cf>() + (size_t)(step % B2_SHARD_SLOTS) * q->cpp * q->row;
+    return q->core.launch_chunk(in, q->row, (unsigned int)q->row, nullptr);
+}
+
+extern "C" int b2_mcrx_shard_end(b2_mcrx_shard * q)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    if (!q->in_call) return B2_OK;
+    B2_CUDA(cudaSetDevice(q->device));
+    q->in_call = false;
+    return q->core.end_batch();
+}
+
+extern "C" int b2_mcrx_shard_poll_view(b2_mcrx_shard * q, const b2_frame_rec ** recs, size_t * n_recs,
+                                       const uint8_t ** payloads, size_t * n_payload_bytes)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    return q->core.poll_view(recs, n_recs, payloads, n_payload_bytes);
+}
+
+extern "C" int b2_mcrx_shard_pack_results(b2_mcrx_shard * q, void * dst_dev, size_t cap_bytes, size_t * n_recs, size_t * n_payload_bytes)
+{
+    if (!q || !dst_dev) return b2_fail(B2_ERR_ARG, "null argument");
+    B2_CUDA(cudaSetDevice(q->device));
+    SyncCore & c = q->core;
+    const size_t nr = c.chunk ? std::min<size_t>(c.h_range[c.chunk].nrec, c.recs_cap) : 0;
+    const size_t nb = c.chunk ? (size_t)c.last_used : 0;
+    if (nr * sizeof(FrameRec) + nb > cap_bytes) return b2_fail(B2_ERR_OVERFLOW, "pack buffer too small (%zu records, %zu payload bytes)", nr, nb);
+    if (nr) B2_CUDA(cudaMemcpyAsync(dst_dev, c.d_recs.p, nr * sizeof(FrameRec), cudaMemcpyDeviceToDevice, q->s2));
+    if (nb) B2_CUDA(cudaMemcpyAsync((char *)dst_dev + nr * sizeof(FrameRec), c.d_decoded.p, nb, cudaMemcpyDeviceToDevice, q->s2));
+    if (n_recs) *n_recs = nr;
+    if (n_payload_bytes) *n_payload_bytes = nb;
+    return B2_OK;
+}
+
+extern "C" int b2_mcrx_shard_poll(b2_mcrx_shard * q, b2_frame_rec * recs, size_t recs_cap, size_t * n_recs,
+                                  uint8_t * payloads, size_t payloads_cap, size_t * n_payload_bytes)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    return q->core.poll(recs, recs_cap, n_recs, payloads, payloads_cap, n_payload_bytes);
+}
+
+extern "C" int b2_mcrx_shard_reset(b2_mcrx_shard * q)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    B2_CUDA(cudaSetDevice(q->device));
+    return q->core.reset_streams();
 }

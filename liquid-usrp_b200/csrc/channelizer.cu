@@ -164,11 +164,12 @@ __global__ void __launch_bounds__(AN_THREADS, 1) analyzer_kernel(const AnalyzerP
 
         // channels 0..N-1 -> out[c][col0 + b], runs of nb contiguous samples per channel
         {
-            cf * out = p.out + p.out_col0 + b_begin + tb0;
+            const size_t ocol = p.out_col0 + b_begin + tb0;
             const unsigned int total = N * nb;
             for (unsigned int e = tid; e < total; e += AN_THREADS) {
                 unsigned int c = e / nb, b = e - c * nb;
-                out[(size_t)c * p.out_stride + b] = xbuf[(size_t)b * ldx + phys<1>(c)];
+                (p.n_peer ? p.out_peer[c / p.chan_per_peer] + (size_t)(c % p.chan_per_peer) * p.out_stride
+                          : p.out + (size_t)c * p.out_stride)[ocol + b] = xbuf[(size_t)b * ldx + phys<1>(c)];
             }
         }
         __syncthreads();

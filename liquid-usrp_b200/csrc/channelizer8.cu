@@ -154,11 +154,14 @@ __global__ void __launch_bounds__(K, 1) analyzer8_kernel(const AnalyzerParams p)
         for (unsigned int s = 0; s < 4; s++) outst[(j + s * T8) * A8_OLD + g] = v[s];
         __syncthreads();
         {
-            cf * out = p.out + p.out_col0 + B0 + k * JB;
+            const size_t col = p.out_col0 + B0 + k * JB;
             for (unsigned int e = r; e < N * (JB / 2); e += K) {
                 const unsigned int c = e / (JB / 2), q2 = (e % (JB / 2)) * 2;
                 if (q2 >= nb) continue;
-                cf * dst = out + (size_t)c * p.out_stride + q2;
+                // (multi-GPU split: the run goes to the GPU that owns channel c)
+                cf * row = p.n_peer ? p.out_peer[c / p.chan_per_peer] + (size_t)(c % p.chan_per_peer) * p.out_stride
+                                    : p.out + (size_t)c * p.out_stride;
+                cf * dst = row + col + q2;
                 const cf x0 = outst[c * A8_OLD + q2], x1 = outst[c * A8_OLD + q2 + 1];
                 if (q2 + 1 < nb && ((((size_t)dst) & 15) == 0)) *(float4 *)dst = make_float4(x0.x, x0.y, x1.x, x1.y);
                 else { dst[0] = x0; if (q2 + 1 < nb) dst[1] = x1; }

@@ -23,6 +23,11 @@ struct AnalyzerParams {
     int row_alt;                // set by the launcher: K*dtheta == 0 (+1) or pi (-1) mod 2 pi, else 0
     cf * out;                   // out[c*out_stride + out_col0 + b]
     size_t out_stride, out_col0;
+    // multi-GPU split (capi_shard.cu): channel c belongs to GPU c / chan_per_peer and is written straight into that
+    // GPU's memory, out_peer[c / chan_per_peer][(c % chan_per_peer)*out_stride + out_col0 + b] (peer mapping over
+    // NVLink; n_peer == 0: `out`)
+    cf * out_peer[8];
+    unsigned int n_peer, chan_per_peer;
     FftDev fft;                 // K-point plan (perm / tw in global memory)
 };
 size_t analyzer_smem_bytes(const AnalyzerParams & p);
@@ -164,6 +169,7 @@ struct SyncParams {
     float b_cos, b_sin;         // e^{j 2 pi backoff / M}: rotation of the S1 metric (ofdmframesync_execute_S1)
     float qam_alpha[9];         // 1/sqrt(2,10,42,170) at index bps = 2,4,6,8
     unsigned int streams;
+    unsigned int chan_base;     // added to the stream index in FrameRec::channel (channel-sharded receivers)
     // workers == 2 (ofdmsync8.cu only): two CTAs per stream take alternate frames; st / ring / G0 / R / penc
     // then hold 2*streams entries (index 2*stream + worker)
     unsigned int workers, launch_id;

@@ -1056,7 +1056,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? B2_S8_THREADS_PER_SM : 512
                 if (!ok) { atomicExch(&p.counters[1], 1u); red[115] = -1.f; }
                 else {
                     FrameRec r;
-                    r.channel = sidx;
+                    r.channel = p.chan_base + sidx;
                     r.header_valid = (emit == 2);
                     r.payload_valid = 0;
                     r.payload_len = (emit == 2) ? S->payload_len : 0u;

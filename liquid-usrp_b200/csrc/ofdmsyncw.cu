@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                         if (!ok) atomicOr(&p.counters[1], 1u);
                         else {
                             FrameRec r;
-                            r.channel = ch;
+                            r.channel = p.chan_base + ch;
                             r.header_valid = (emit == 2);
                             r.payload_valid = 0;
                             r.payload_len = plen;

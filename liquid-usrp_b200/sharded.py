@@ -1,5 +1,11 @@
 """Multi-GPU multichannelrx: one process per GPU over torch.distributed.
 
+ShardedRx (bottom of this file) is the production path: round-robin time chunks, the channelizer scattering
+straight into peer GPU memory (b2_mcrx_shard_* in include/b200_ofdm.h), one one-word NCCL all-reduce per step
+as the only cross-rank synchronisation, stages of successive steps overlapping on two streams.
+ShardedMultichannelRx below is the first, unpipelined formulation (contiguous time shards, NCCL all-to-all); it
+is kept because its pure index logic (plan / exchange / gather_frames) is what the gloo tests exercise on CPU.
+
 A single wideband stream is split two ways, with ONE exchange in between:
 
   stage 1  NCO + analysis channelizer   sharded over TIME.  Rank r owns blocks
@@ -132,3 +138,217 @@ class ShardedMultichannelRx:
     def close(self):
         self.chan.close()
         self.sync.close()
+
+
+class ShardedRx:
+    """one rank of a multichannelrx spread over `world` GPUs (one process each).
+
+    The wideband stream is cut into chunks of `chunk_blocks` blocks of 2N samples; chunk g goes to rank g % world
+    (the way a front end would deal DMA buffers round), so after every STEP -- one chunk per rank -- each rank holds
+    its N/world channels for `world` consecutive chunks of time and runs its synchronisers over them while the
+    next step is being channelized.  Data plane: the stage-1 kernel stores every channel's run directly into the
+    owning GPU's exchange buffer (CUDA IPC mapping over NVLink).  Control plane: a one-word all-reduce per step on
+    the stage-1 stream (everybody's stores of the step have landed / everybody is done with the slot that comes
+    round next), torch.distributed gather of the frame records at the end of a call.
+    """
+    SLOTS = 3
+
+    def __init__(self, num_channels, M, cp_len, taper_len, chunk_blocks, steps_per_call, rank, world, device=0, group=None):
+        import ctypes as C
+        from . import capi
+        self.C, self.capi = C, capi
+        self.L = capi.lib()
+        self.N, self.K, self.rank, self.world, self.group = num_channels, 2 * num_channels, rank, world, group
+        self.tc, self.steps = chunk_blocks, steps_per_call
+        self.device = torch.device("cuda", device)
+        self.s1 = torch.cuda.Stream(device=self.device)
+        self.s2 = torch.cuda.Stream(device=self.device)
+        h = C.c_void_p()
+        capi._check(self.L.b2_mcrx_shard_create(num_channels, M, cp_len, taper_len, None, device, rank, world, chunk_blocks,
+                                                 steps_per_call, C.c_void_p(self.s1.cuda_stream), C.c_void_p(self.s2.cuda_stream),
+                                                 C.byref(h)))
+        self.h = h
+        if world > 1:
+            mine = (C.c_ubyte * 64)()
+            capi._check(self.L.b2_mcrx_shard_export(self.h, mine))
+            t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(self.device)
+            allh = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allh, t, group=group)
+            blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh)
+            buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+            capi._check(self.L.b2_mcrx_shard_connect(self.h, buf, world))
+            dist.barrier(group=group)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.step = 0                                  # steps since the stream began
+        self.ev_ready = [torch.cuda.Event() for _ in range(steps_per_call)]
+        self.ev_done = [torch.cuda.Event() for _ in range(steps_per_call)]
+
+    def execute_device(self, chunk_ptrs):
+        """one call = steps_per_call steps; chunk_ptrs[i]: device pointer to this rank's chunk of step i, preceded
+        by its 13 halo blocks ((13 + chunk_blocks) * 2N complex64 samples, 16-byte aligned)"""
+        L, C, capi = self.L, self.C, self.capi
+        assert len(chunk_ptrs) == self.steps
+        cur = torch.cuda.current_stream(self.device)
+        self.s1.wait_stream(cur)
+        self.s2.wait_stream(cur)
+        capi._check(L.b2_mcrx_shard_begin(self.h))
+        for i in range(self.steps):
+            with torch.cuda.stream(self.s1):
+                capi._check(L.b2_mcrx_shard_stage1(self.h, C.c_void_p(int(chunk_ptrs[i])), self.step))
+                if self.world > 1:
+                    # the slot that step + 1 will write must have been read by everybody: join the barrier only
+                    # behind the own stage 2 of the step that used it
+                    if i >= self.SLOTS - 1:
+                        self.s1.wait_event(self.ev_done[i - (self.SLOTS - 1)])
+                    dist.all_reduce(self.flag, group=self.group)
+                self.ev_ready[i].record(self.s1)
+            with torch.cuda.stream(self.s2):
+                self.s2.wait_event(self.ev_ready[i])
+                capi._check(L.b2_mcrx_shard_stage2(self.h, self.step))
+                self.ev_done[i].record(self.s2)
+            self.step += 1
+        capi._check(L.b2_mcrx_shard_end(self.h))       # host waits for stage 2 of every step
+        # the next call's first stage 1 may overwrite a slot only after the slowest rank's stage 2
+        if self.world > 1:
+            with torch.cuda.stream(self.s1):
+                self.s1.wait_event(self.ev_done[self.steps - 1])
+                dist.all_reduce(self.flag, group=self.group)
+        cur.wait_stream(self.s1)
+        cur.wait_stream(self.s2)
+
+    def execute_host(self, host_chunks):
+        """the same call fed from PINNED HOST memory: host_chunks[i] is a pinned uint8/float32/complex64 tensor holding
+        [13 halo blocks | chunk] of step i; the copies go through two device buffers on a copy stream, so the H2D of
+        step i + 1 overlaps stage 1 of step i"""
+        if not hasattr(self, "_hbuf"):
+            n = host_chunks[0].numel()
+            self._hbuf = [torch.empty(n, dtype=host_chunks[0].dtype, device=self.device) for _ in range(2)]
+            self._hcopy = torch.cuda.Stream(device=self.device)
+            self._hev_copied = [torch.cuda.Event() for _ in range(2)]
+            self._hev_used = [torch.cuda.Event() for _ in range(2)]
+            self._hused = [False, False]
+        L, C, capi = self.L, self.C, self.capi
+        assert len(host_chunks) == self.steps
+        cur = torch.cuda.current_stream(self.device)
+        self.s1.wait_stream(cur); self.s2.wait_stream(cur); self._hcopy.wait_stream(cur)
+        capi._check(L.b2_mcrx_shard_begin(self.h))
+        for i in range(self.steps):
+            b = i & 1
+            with torch.cuda.stream(self._hcopy):
+                if self._hused[b]:
+                    self._hcopy.wait_event(self._hev_used[b])           # stage 1 that read this buffer last
+                self._hbuf[b].copy_(host_chunks[i], non_blocking=True)
+                self._hev_copied[b].record(self._hcopy)
+            with torch.cuda.stream(self.s1):
+                self.s1.wait_event(self._hev_copied[b])
+                capi._check(L.b2_mcrx_shard_stage1(self.h, C.c_void_p(self._hbuf[b].data_ptr()), self.step))
+                self._hev_used[b].record(self.s1)
+                self._hused[b] = True
+                if self.world > 1:
+                    if i >= self.SLOTS - 1:
+                        self.s1.wait_event(self.ev_done[i - (self.SLOTS - 1)])
+                    dist.all_reduce(self.flag, group=self.group)
+                self.ev_ready[i].record(self.s1)
+            with torch.cuda.stream(self.s2):
+                self.s2.wait_event(self.ev_ready[i])
+                capi._check(L.b2_mcrx_shard_stage2(self.h, self.step))
+                self.ev_done[i].record(self.s2)
+            self.step += 1
+        capi._check(L.b2_mcrx_shard_end(self.h))
+        if self.world > 1:
+            with torch.cuda.stream(self.s1):
+                self.s1.wait_event(self.ev_done[self.steps - 1])
+                dist.all_reduce(self.flag, group=self.group)
+        cur.wait_stream(self.s1); cur.wait_stream(self.s2)
+
+    def poll(self):
+        C, capi = self.C, self.capi
+        n, nb = C.c_size_t(), C.c_size_t()
+        capi._check(self.L.b2_mcrx_shard_poll(self.h, None, 0, C.byref(n), None, 0, C.byref(nb)))
+        recs = np.zeros(n.value, dtype=capi.FRAME_DTYPE)
+        pl = np.zeros(max(nb.value, 1), dtype=np.uint8)
+        if n.value:
+            capi._check(self.L.b2_mcrx_shard_poll(self.h, C.c_void_p(recs.ctypes.data), n.value, C.byref(n),
+                                                  C.c_void_p(pl.ctypes.data), len(pl), C.byref(nb)))
+        return recs, pl[:nb.value]
+
+    def poll_view(self):
+        """zero-copy: arrays alias the library's pinned buffers, valid until the next call on this handle"""
+        C, capi = self.C, self.capi
+        pr, pp, n, nb = C.c_void_p(), C.c_void_p(), C.c_size_t(0), C.c_size_t(0)
+        capi._check(self.L.b2_mcrx_shard_poll_view(self.h, C.byref(pr), C.byref(n), C.byref(pp), C.byref(nb)))
+        if n.value == 0:
+            return np.zeros(0, capi.FRAME_DTYPE), np.zeros(0, np.uint8)
+        recs = np.frombuffer((C.c_char * (n.value * capi.FRAME_DTYPE.itemsize)).from_address(pr.value), dtype=capi.FRAME_DTYPE)
+        pl = np.frombuffer((C.c_char * max(nb.value, 1)).from_address(pp.value), dtype=np.uint8)[:nb.value] if nb.value else np.zeros(0, np.uint8)
+        return recs, pl
+
+    # ---- gather of the decoded frames on rank 0: NCCL from device memory, one D2H on rank 0 that overlaps the next call
+    def gather_async(self, cap_bytes):
+        """start gathering the frames of the call that just ended: every rank packs [records | payloads] from device
+        memory, NCCL gathers the packs on rank 0, rank 0 copies them to pinned host memory on a copy stream.
+        Returns a ticket for gather_wait()."""
+        C, capi = self.C, self.capi
+        if not hasattr(self, "_g"):
+            self._g = {"send": torch.empty(cap_bytes, dtype=torch.uint8, device=self.device),
+                       "sizes": torch.zeros(2, dtype=torch.int64, device=self.device),
+                       "copy": torch.cuda.Stream(device=self.device), "k": 0}
+            if self.rank == 0:
+                self._g["recv"] = [torch.empty((self.world, cap_bytes), dtype=torch.uint8, device=self.device) for _ in range(2)]
+                self._g["host"] = [torch.empty((self.world, cap_bytes), dtype=torch.uint8).pin_memory() for _ in range(2)]
+                self._g["ev"] = [torch.cuda.Event() for _ in range(2)]
+        g = self._g
+        nr, nb = C.c_size_t(0), C.c_size_t(0)
+        with torch.cuda.stream(self.s2):
+            capi._check(self.L.b2_mcrx_shard_pack_results(self.h, C.c_void_p(g["send"].data_ptr()), cap_bytes, C.byref(nr), C.byref(nb)))
+            g["sizes"][0] = nr.value
+            g["sizes"][1] = nb.value
+            k = g["k"] & 1
+            g["k"] += 1
+            if self.world == 1:
+                all_sizes = np.array([[nr.value, nb.value]])
+                src = g["send"].view(1, -1)
+            else:
+                sz = [torch.zeros_like(g["sizes"]) for _ in range(self.world)]
+                dist.all_gather(sz, g["sizes"], group=self.group)
+                all_sizes = torch.stack(sz).cpu().numpy()
+                used = int((all_sizes[:, 0] * capi.FRAME_DTYPE.itemsize + all_sizes[:, 1]).max())
+                used = min(cap_bytes, (used + 255) & ~255)
+                outl = [g["recv"][k][r, :used] for r in range(self.world)] if self.rank == 0 else None
+                dist.gather(g["send"][:used], outl, dst=0, group=self.group)
+                src = g["recv"][k] if self.rank == 0 else None
+            done = torch.cuda.Event()
+            done.record(self.s2)
+        if self.rank != 0:
+            return None
+        used = int((all_sizes[:, 0] * capi.FRAME_DTYPE.itemsize + all_sizes[:, 1]).max())
+        with torch.cuda.stream(g["copy"]):
+            g["copy"].wait_event(done)
+            for r in range(self.world):              # (row by row: a strided 2-D D2H copy is 30x slower)
+                g["host"][k][r, :used].copy_(src[r, :used], non_blocking=True)
+            g["ev"][k].record(g["copy"])
+        return (k, all_sizes)
+
+    def gather_wait(self, ticket):
+        """rank 0: -> list over source ranks of (records, payload bytes) numpy views into pinned memory (valid until the
+        ticket after next); other ranks: None"""
+        if ticket is None:
+            return None
+        k, all_sizes = ticket
+        self._g["ev"][k].synchronize()
+        host = self._g["host"][k].numpy()
+        out = []
+        isz = self.capi.FRAME_DTYPE.itemsize
+        for r in range(self.world):
+            nr, nb = int(all_sizes[r][0]), int(all_sizes[r][1])
+            out.append((host[r, :nr * isz].view(self.capi.FRAME_DTYPE), host[r, nr * isz:nr * isz + nb]))
+        return out
+
+    def reset(self):
+        self.capi._check(self.L.b2_mcrx_shard_reset(self.h))
+
+    def close(self):
+        if self.h:
+            torch.cuda.synchronize(self.device)
+            self.L.b2_mcrx_shard_destroy(self.h)
+            self.h = None

@@ -341,6 +341,57 @@ def test_stagewise_and_sharded_world1_equal_monolithic():
     assert_frames_equal(fo, po, fg, pg)
 
 
+def sharded_chunks(x, K, tc, steps, rank, world, halo):
+    """device tensors [halo | chunk] of the chunks rank, rank + world, ... of stream x (zeros before the stream)"""
+    import torch
+    pad = np.concatenate([np.zeros(halo * K, np.complex64), x])
+    out = []
+    for i in range(steps):
+        g = i * world + rank
+        out.append(torch.from_numpy(pad[g * tc * K:(g * tc + halo + tc) * K].copy()).cuda())
+    return out
+
+
+def test_sharded_rx_single_rank_equals_oracle():
+    """the pipelined multi-GPU receiver (b2_mcrx_shard_*: round-robin chunks, channelizer storing into the exchange
+    slots, synchronisers over the slots) with one rank, over two calls: same records as the oracle"""
+    import importlib
+    sh = importlib.import_module("liquid-usrp_b200.sharded")
+    for name in ("c5_shape_32ch_qam64", "c2_8ch_h128"):
+        case = CASES[name]
+        N, M, cp, taper = case[:4]
+        K = 2 * N
+        x = make_input(case)
+        steps, calls = 3, 2
+        tc = (len(x) // K) // (steps * calls)
+        x = x[:tc * steps * calls * K]
+        fo, po, _ = run_oracle(case, x)
+        rx = sh.ShardedRx(N, M, cp, taper, tc, steps, 0, 1, device=0)
+        bufs = sharded_chunks(x, K, tc, steps * calls, 0, 1, sh.HALO_BLOCKS)
+        frames, pls = [], []
+        for c in range(calls):
+            rx.execute_device([b.data_ptr() for b in bufs[c * steps:(c + 1) * steps]])
+            f, pl = rx.poll()
+            f = f.copy()
+            f["payload_offset"] += sum(len(q) for q in pls)
+            frames.append(f); pls.append(pl.copy())
+        rx.close()
+        assert_frames_equal(fo, po, np.concatenate(frames), np.concatenate(pls))
+
+
+def test_sharded_rx_two_gpus():
+    """two ranks under torchrun (tests/mgpu_sharded.py): the gathered records equal a single-GPU receiver's"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", os.path.join(root, "tests", "mgpu_sharded.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "sharded ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_full_size_north_star_shape_properties():
     """BASELINE configs[4] shape at full width (256 channels x 512 subcarriers, 64-QAM), too big for
     the oracle receiver to be run in a test, checked through size-independent properties: every
