@@ -283,7 +283,7 @@ def run_sharded(args, rank, local_rank, world, period, expected, flen):
     per_chunk = 13
     steps = max(1, args.reps // per_chunk)
     tc = per_chunk * flen
-    rx = sh.ShardedRx(w["N"], w["M"], w["cp"], w["taper"], tc, steps, rank, world, device=local_rank)
+    rx = sh.ShardedRx(w["N"], w["M"], w["cp"], w["taper"], tc, steps, rank, world, device=local_rank, host_results=False)
     # the stream is periodic in `period` and every chunk starts on a period boundary: [halo | chunk] is the same for all
     tile = np.concatenate([period[-sh.HALO_BLOCKS * K:], np.tile(period, per_chunk)])
     d_x = torch.from_numpy(tile.view(np.float32)).cuda()
@@ -298,7 +298,7 @@ def run_sharded(args, rank, local_rank, world, period, expected, flen):
         torch.cuda.synchronize()
 
     frames_call = w["N"] * steps * per_chunk                      # frames a rank decodes per call (its channels, all chunks of the call)
-    cap = int(1.25 * frames_call * (88 + w["payload"] + 16)) + (1 << 20)
+    cap = int(1.03 * frames_call * (88 + w["payload"] + 16)) + (1 << 20)
     pending = [None]
     gathered = [0]
 
@@ -307,8 +307,8 @@ def run_sharded(args, rank, local_rank, world, period, expected, flen):
             rx.execute_host([h_x] * steps)
         else:
             rx.execute_device(ptrs)
-        recs, pl = rx.poll_view()                                 # this rank's own frames (pinned host memory, zero copy)
-        ticket = rx.gather_async(cap)                             # NCCL gather to rank 0 + D2H there, overlapping the next call
+        recs, pl = rx.poll_view()                                 # (empty: the frames are taken from device memory below)
+        ticket = rx.gather_async(cap, via=args.gather)                             # device-side ordering, NCCL gather to rank 0, D2H there: overlaps the next call
         if pending[0] is not None:
             res = rx.gather_wait(pending[0])
             if res is not None:
@@ -325,7 +325,9 @@ def run_sharded(args, rank, local_rank, world, period, expected, flen):
                 for r, p_ in res:
                     if len(r):
                         c, o = int(r["channel"][-1]), int(r["payload_offset"][-1])
-                        assert int(r["payload_valid"].min()) == 1
+                        assert int(r["payload_valid"].min()) == 1 and int(r["header_valid"].min()) == 1
+                        key = (r["complete_index"].astype(np.uint64) << np.uint64(16)) | r["channel"].astype(np.uint64)
+                        assert bool(np.all(key[1:] >= key[:-1])), "records of a rank are not in callback order"
                         assert np.array_equal(p_[o:o + w["payload"]], expected[c][1]), "gathered payload mismatch on channel %d" % c
             pending[0] = None
         return gathered[0]
@@ -333,12 +335,9 @@ def run_sharded(args, rank, local_rank, world, period, expected, flen):
     n_call = steps * tc * K * world                  # wideband samples of the whole stream per call
     for _ in range(args.warmup):
         recs, pl, _n = one_call(False)
-    drain()
-    assert len(recs) >= (w["N"] // world) * (steps * per_chunk * world - 1), "frames missing: %d" % len(recs)
-    assert int(recs["payload_valid"].min()) == 1
-    for i in (0, len(recs) // 2, len(recs) - 1):
-        c, o = int(recs["channel"][i]), int(recs["payload_offset"][i])
-        assert np.array_equal(pl[o:o + w["payload"]], expected[c][1]), "payload mismatch on channel %d" % c
+    n_got = drain()
+    if rank == 0:
+        assert n_got >= w["N"] * (steps * per_chunk * world - 1), "frames missing: %d" % n_got
     clk = Clocks(local_rank)
     clk.start()
     barrier()
@@ -358,7 +357,7 @@ def run_sharded(args, rank, local_rank, world, period, expected, flen):
     d2h = 0
     for _ in range(args.steps):
         recs, pl, n = one_call(True)
-        d2h += recs.nbytes + len(pl)
+        d2h += cap
     drain()
     barrier()
     dt_e2e = time.perf_counter() - t1
@@ -540,6 +539,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "sharded"], help="N > 1: auto / sharded = ONE stream split over the "
                     "GPUs (the headline; independent replicas are reported alongside), replicas = independent receivers only")
+    ap.add_argument("--gather", default="shm", choices=["shm", "nccl"], help="N > 1: how the decoded frames reach rank 0's host memory: shm = every rank "
+                    "over its own PCIe link into shared host memory, nccl = NCCL gather over NVLink to rank 0's GPU, then rank 0's PCIe link")
     ap.add_argument("--no-config64", action="store_true", help="skip the extra 64-channel (BASELINE configs[2]) leg")
     ap.add_argument("--receivers", type=int, default=1, help="extra leg: R independent receivers sharing this GPU (reported under "
                     "'multi_receiver', never as the headline): shows that one receiver is bound by its 256 serial chains")

@@ -89,6 +89,7 @@ struct SyncCore {
     struct ChunkEv { cudaEvent_t s0, s1, d0, d1, x; };
     std::vector<ChunkEv> cev;            // sync begin/end, decode begin/end of each chunk
     bool timing = true;
+    bool host_results = true;            // end_batch brings records + payloads to pinned host memory and orders them
 
     int init(unsigned int M, unsigned int cp, unsigned int taper, const unsigned char * p, unsigned int streams_,
              size_t tmax_, int device_, cudaStream_t st, const cudaStream_t * decode_st = nullptr);
@@ -467,6 +468,13 @@ int SyncCore::end_batch()
     // chunk by chunk, as soon as its decode is done: records + decoded payloads -> pinned host memory on
     // the copy stream, and the host orders chunk c-1 while chunk c is in flight
     int rc = B2_OK;
+    if (!host_results) {
+        // the frames stay in device memory (b2_mcrx_shard_pack_results): wait for the last decode, keep the counts
+        for (unsigned int i = 0; i < NDS && i < chunk; i++) B2_CUDA(cudaEventSynchronize(cev[chunk - 1 - i].d1));
+        last_used = std::min(h_range[chunk].arena_used, out_cap);
+        timing_stale = true;
+        return collect();
+    }
     ready.reserve(ready.size() + 1024);
     for (unsigned int c = 0; c <= chunk; c++) {
         if (c < chunk) {
@@ -1148,6 +1156,12 @@ struct b2_mcrx_shard_s {
     b2_mcrx * chan = nullptr;            // stage 1: tables and launch configuration of a full N-channel receiver
     SyncCore core;                       // stage 2: N / world streams
     DevBuf d_xchg;                       // [B2_SHARD_SLOTS][N / world][world * tc]
+    // B2_SHARD_COPY=1: stage 1 writes a local tile and the copy engines carry the slabs to their owners (instead of the
+    // channelizer storing into peer memory itself)
+    bool copy_mode = false;
+    DevBuf d_tile;                       // [N][tc]
+    cudaStream_t cpy = nullptr;
+    cudaEvent_t ev_tile = nullptr, ev_copied = nullptr;
     cf * peer[8] = {};                   // every rank's exchange buffer as seen from this device
     bool connected = false, in_call = false;
 };
@@ -1161,6 +1175,9 @@ extern "C" int b2_mcrx_shard_destroy(b2_mcrx_shard * q)
         if (q->connected && i != q->rank && q->peer[i]) cudaIpcCloseMemHandle(q->peer[i]);
     q->core.destroy();
     if (q->chan) b2_mcrx_destroy(q->chan);
+    if (q->cpy) cudaStreamDestroy(q->cpy);
+    if (q->ev_tile) cudaEventDestroy(q->ev_tile);
+    if (q->ev_copied) cudaEventDestroy(q->ev_copied);
     delete q;
     return B2_OK;
 }
@@ -1188,6 +1205,13 @@ extern "C" int b2_mcrx_shard_create(unsigned int N, unsigned int M, unsigned int
         // stage 2: one batch = one call = steps_per_call launches of world * chunk_blocks samples per stream
         if ((rc = q->core.init(M, cp, taper, p, q->cpp, q->row * steps_per_call, device, q->s2))) break;
         q->core.sp.chan_base = rank * q->cpp;                           // records carry the global channel index
+        if (const char * e = getenv("B2_SHARD_COPY")) q->copy_mode = atoi(e) != 0;
+        if (q->copy_mode) {
+            if ((rc = q->d_tile.alloc(sizeof(cf) * (size_t)N * q->tc))) break;
+            B2_CUDA(cudaStreamCreateWithFlags(&q->cpy, cudaStreamNonBlocking));
+            B2_CUDA(cudaEventCreateWithFlags(&q->ev_tile, cudaEventDisableTiming));
+            B2_CUDA(cudaEventCreateWithFlags(&q->ev_copied, cudaEventDisableTiming));
+        }
         q->connected = (world == 1);
     } while (0);
     if (rc) { b2_mcrx_shard_destroy(q); return rc; }
@@ -1245,6 +1269,22 @@ extern "C" int b2_mcrx_shard_stage1(b2_mcrx_shard * q, const float * x_dev, uint
     cf * dst[8];
     const size_t slot_off = (size_t)(step % B2_SHARD_SLOTS) * q->cpp * q->row;
     for (unsigned int i = 0; i < q->world; i++) dst[i] = q->peer[i] + slot_off;
+    if (q->copy_mode) {
+        // local tile, then one strided copy per owner on the copy stream; stream_stage1 continues behind the copies
+        B2_CUDA(cudaStreamWaitEvent(q->s1, q->ev_copied, 0));            // the previous step's copies have read the tile
+        B2_TRY(mcrx_channelize(q->chan, x_dev, q->tc, offset, q->d_tile.as<float>(), q->tc, 0, nullptr, 0, 0, q->s1));
+        B2_CUDA(cudaEventRecord(q->ev_tile, q->s1));
+        B2_CUDA(cudaStreamWaitEvent(q->cpy, q->ev_tile, 0));
+        for (unsigned int k = 0; k < q->world; k++) {
+            const unsigned int i = (q->rank + k) % q->world;             // everybody starts with a different owner
+            B2_CUDA(cudaMemcpy2DAsync(dst[i] + (size_t)q->rank * q->tc, sizeof(cf) * q->row,
+                                      q->d_tile.as<cf>() + (size_t)i * q->cpp * q->tc, sizeof(cf) * q->tc,
+                                      sizeof(cf) * q->tc, q->cpp, cudaMemcpyDeviceToDevice, q->cpy));
+        }
+        B2_CUDA(cudaEventRecord(q->ev_copied, q->cpy));
+        B2_CUDA(cudaStreamWaitEvent(q->s1, q->ev_copied, 0));
+        return B2_OK;
+    }
     return mcrx_channelize(q->chan, x_dev, q->tc, offset, nullptr, q->row, (size_t)q->rank * q->tc, dst, q->world, q->cpp, q->s1);
 }
 
@@ -1280,9 +1320,14 @@ extern "C" int b2_mcrx_shard_pack_results(b2_mcrx_shard * q, void * dst_dev, siz
     SyncCore & c = q->core;
     const size_t nr = c.chunk ? std::min<size_t>(c.h_range[c.chunk].nrec, c.recs_cap) : 0;
     const size_t nb = c.chunk ? (size_t)c.last_used : 0;
-    if (nr * sizeof(FrameRec) + nb > cap_bytes) return b2_fail(B2_ERR_OVERFLOW, "pack buffer too small (%zu records, %zu payload bytes)", nr, nb);
-    if (nr) B2_CUDA(cudaMemcpyAsync(dst_dev, c.d_recs.p, nr * sizeof(FrameRec), cudaMemcpyDeviceToDevice, q->s2));
-    if (nb) B2_CUDA(cudaMemcpyAsync((char *)dst_dev + nr * sizeof(FrameRec), c.d_decoded.p, nb, cudaMemcpyDeviceToDevice, q->s2));
+    if (16 + nr * sizeof(FrameRec) + nb > cap_bytes) return b2_fail(B2_ERR_OVERFLOW, "pack buffer too small (%zu records, %zu payload bytes)", nr, nb);
+    // header: the sizes travel with the data (no separate size exchange); h_counters is pinned
+    unsigned long long * hdr = (unsigned long long *)(c.h_counters + 4) ;
+    B2_CUDA(cudaStreamSynchronize(q->s2));                               // the previous header copy has been consumed
+    hdr[0] = nr; hdr[1] = nb;
+    B2_CUDA(cudaMemcpyAsync(dst_dev, hdr, 16, cudaMemcpyHostToDevice, q->s2));
+    if (nr) B2_CUDA(pack_sorted_launch(c.d_recs.as<FrameRec>(), (unsigned int)nr, (FrameRec *)((char *)dst_dev + 16), q->s2));
+    if (nb) B2_CUDA(cudaMemcpyAsync((char *)dst_dev + 16 + nr * sizeof(FrameRec), c.d_decoded.p, nb, cudaMemcpyDeviceToDevice, q->s2));
     if (n_recs) *n_recs = nr;
     if (n_payload_bytes) *n_payload_bytes = nb;
     return B2_OK;
@@ -1293,6 +1338,13 @@ extern "C" int b2_mcrx_shard_poll(b2_mcrx_shard * q, b2_frame_rec * recs, size_t
 {
     if (!q) return b2_fail(B2_ERR_ARG, "null handle");
     return q->core.poll(recs, recs_cap, n_recs, payloads, payloads_cap, n_payload_bytes);
+}
+
+extern "C" int b2_mcrx_shard_host_results(b2_mcrx_shard * q, int on)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    q->core.host_results = (on != 0);
+    return B2_OK;
 }
 
 extern "C" int b2_mcrx_shard_reset(b2_mcrx_shard * q)

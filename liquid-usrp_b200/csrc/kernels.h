@@ -242,6 +242,8 @@ struct PacketParams {
 cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t st);
 // mark_out = {counters[0], counters[2..3]} (records / arena bytes so far), one thread; runs between
 // the synchroniser of a chunk and its decode so that chunk c decodes records [mark[c], mark[c+1])
+// records of a batch in callback order (completion index, then channel): device sort + permuting copy into dst
+cudaError_t pack_sorted_launch(const FrameRec * recs, unsigned int n, FrameRec * dst, cudaStream_t st);
 cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_out, cudaStream_t st, int used_at = 2);
 
 } // namespace b2

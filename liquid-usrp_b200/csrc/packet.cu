@@ -13,6 +13,8 @@
 //                 frame: lane L owns states 2L, 2L+1; decisions ballot-packed, 64 bit per step).
 //   CRC-32      : 32 lanes x bytewise CRC of a slice, slices merged with x^(8n) mod P products.
 #include <mutex>
+#include <thrust/sort.h>
+#include <thrust/execution_policy.h>
 #include "kernels.h"
 #include "fec.cuh"
 
@@ -719,6 +721,46 @@ __global__ void record_mark_kernel(const unsigned int * counters, RangeMark * ma
 cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_out, cudaStream_t st, int used_at)
 {
     record_mark_kernel<<<1, 1, 0, st>>>(counters, mark_out, used_at);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ records in callback order, on the device
+__global__ void rec_keys_kernel(const FrameRec * recs, unsigned int n, unsigned long long * keys, unsigned int * idx)
+{
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = (recs[i].complete_index << 16) | (unsigned long long)(recs[i].channel & 0xffffu);
+    idx[i] = i;
+}
+__global__ void rec_permute_kernel(const FrameRec * recs, const unsigned int * idx, unsigned int n, FrameRec * dst)
+{
+    // 22 words per record, one thread per word
+    const unsigned int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int r = e / (sizeof(FrameRec) / 4), wd = e % (sizeof(FrameRec) / 4);
+    if (r >= n) return;
+    ((uint32_t *)(dst + r))[wd] = ((const uint32_t *)(recs + idx[r]))[wd];
+}
+cudaError_t pack_sorted_launch(const FrameRec * recs, unsigned int n, FrameRec * dst, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    static thread_local unsigned long long * keys = nullptr;
+    static thread_local unsigned int * idx = nullptr;
+    static thread_local unsigned int cap = 0;
+    static thread_local int cap_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (n > cap || dev != cap_dev) {
+        if (keys) cudaFree(keys);
+        if (idx) cudaFree(idx);
+        cap = n + n / 4 + 1024; cap_dev = dev;
+        cudaError_t e = cudaMalloc(&keys, sizeof(unsigned long long) * cap);
+        if (e == cudaSuccess) e = cudaMalloc(&idx, sizeof(unsigned int) * cap);
+        if (e != cudaSuccess) { keys = nullptr; idx = nullptr; cap = 0; return e; }
+    }
+    rec_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(recs, n, keys, idx);
+    thrust::sort_by_key(thrust::cuda::par_nosync.on(st), keys, keys + n, idx);
+    const unsigned int words = n * (unsigned int)(sizeof(FrameRec) / 4);
+    rec_permute_kernel<<<(words + 255) / 256, 256, 0, st>>>(recs, idx, n, dst);
     return cudaGetLastError();
 }
 

@@ -153,7 +153,8 @@ class ShardedRx:
     """
     SLOTS = 3
 
-    def __init__(self, num_channels, M, cp_len, taper_len, chunk_blocks, steps_per_call, rank, world, device=0, group=None):
+    def __init__(self, num_channels, M, cp_len, taper_len, chunk_blocks, steps_per_call, rank, world, device=0, group=None,
+                 host_results=True):
         import ctypes as C
         from . import capi
         self.C, self.capi = C, capi
@@ -168,6 +169,8 @@ class ShardedRx:
                                                  steps_per_call, C.c_void_p(self.s1.cuda_stream), C.c_void_p(self.s2.cuda_stream),
                                                  C.byref(h)))
         self.h = h
+        if not host_results:                           # frames are collected with gather_async / gather_wait only
+            capi._check(self.L.b2_mcrx_shard_host_results(self.h, 0))
         if world > 1:
             mine = (C.c_ubyte * 64)()
             capi._check(self.L.b2_mcrx_shard_export(self.h, mine))
@@ -284,64 +287,113 @@ class ShardedRx:
         return recs, pl
 
     # ---- gather of the decoded frames on rank 0: NCCL from device memory, one D2H on rank 0 that overlaps the next call
-    def gather_async(self, cap_bytes):
-        """start gathering the frames of the call that just ended: every rank packs [records | payloads] from device
-        memory, NCCL gathers the packs on rank 0, rank 0 copies them to pinned host memory on a copy stream.
-        Returns a ticket for gather_wait()."""
+    def gather_async(self, cap_bytes, via="nccl"):
+        """start collecting the frames of the call that just ended on rank 0.  Every rank packs
+        [sizes | records in callback order | payloads] from device memory (cap_bytes, the same on every rank; the sizes
+        travel inside the pack, so there is no size exchange and no host synchronisation), then
+          via="nccl": NCCL gathers the packs on rank 0 over NVLink and rank 0 copies them to pinned host memory -- every
+                      byte crosses rank 0's PCIe link;
+          via="shm":  every rank copies its pack over ITS OWN PCIe link into a host buffer that rank 0 has mapped too
+                      (POSIX shared memory registered with CUDA): nothing funnels through one link.
+        Returns a ticket for gather_wait(); the copies overlap the next call."""
         C, capi = self.C, self.capi
-        if not hasattr(self, "_g"):
-            self._g = {"send": torch.empty(cap_bytes, dtype=torch.uint8, device=self.device),
-                       "sizes": torch.zeros(2, dtype=torch.int64, device=self.device),
-                       "copy": torch.cuda.Stream(device=self.device), "k": 0}
-            if self.rank == 0:
+        if getattr(self, "_g", None) is None or self._g["cap"] != cap_bytes or self._g["via"] != via:
+            self._gather_release()
+            self._g = {"cap": cap_bytes, "via": via, "send": torch.empty(cap_bytes, dtype=torch.uint8, device=self.device),
+                       "copy": torch.cuda.Stream(device=self.device), "k": 0, "ev": [torch.cuda.Event() for _ in range(2)]}
+            if via == "shm":
+                self._shm_setup(cap_bytes)
+            elif self.rank == 0:
                 self._g["recv"] = [torch.empty((self.world, cap_bytes), dtype=torch.uint8, device=self.device) for _ in range(2)]
                 self._g["host"] = [torch.empty((self.world, cap_bytes), dtype=torch.uint8).pin_memory() for _ in range(2)]
-                self._g["ev"] = [torch.cuda.Event() for _ in range(2)]
         g = self._g
         nr, nb = C.c_size_t(0), C.c_size_t(0)
+        k = g["k"] & 1
+        g["k"] += 1
         with torch.cuda.stream(self.s2):
             capi._check(self.L.b2_mcrx_shard_pack_results(self.h, C.c_void_p(g["send"].data_ptr()), cap_bytes, C.byref(nr), C.byref(nb)))
-            g["sizes"][0] = nr.value
-            g["sizes"][1] = nb.value
-            k = g["k"] & 1
-            g["k"] += 1
-            if self.world == 1:
-                all_sizes = np.array([[nr.value, nb.value]])
-                src = g["send"].view(1, -1)
-            else:
-                sz = [torch.zeros_like(g["sizes"]) for _ in range(self.world)]
-                dist.all_gather(sz, g["sizes"], group=self.group)
-                all_sizes = torch.stack(sz).cpu().numpy()
-                used = int((all_sizes[:, 0] * capi.FRAME_DTYPE.itemsize + all_sizes[:, 1]).max())
-                used = min(cap_bytes, (used + 255) & ~255)
-                outl = [g["recv"][k][r, :used] for r in range(self.world)] if self.rank == 0 else None
-                dist.gather(g["send"][:used], outl, dst=0, group=self.group)
-                src = g["recv"][k] if self.rank == 0 else None
+            src = None
+            if via == "nccl":
+                if self.world == 1:
+                    src = g["send"].view(1, -1)
+                else:
+                    outl = [g["recv"][k][r] for r in range(self.world)] if self.rank == 0 else None
+                    dist.gather(g["send"], outl, dst=0, group=self.group)
+                    src = g["recv"][k] if self.rank == 0 else None
             done = torch.cuda.Event()
             done.record(self.s2)
+        used = 16 + nr.value * capi.FRAME_DTYPE.itemsize + nb.value
+        if via == "shm":
+            with torch.cuda.stream(g["copy"]):
+                g["copy"].wait_event(done)
+                g["mine"][k][:used].copy_(g["send"][:used], non_blocking=True)
+                g["ev"][k].record(g["copy"])
+            return k
         if self.rank != 0:
             return None
-        used = int((all_sizes[:, 0] * capi.FRAME_DTYPE.itemsize + all_sizes[:, 1]).max())
         with torch.cuda.stream(g["copy"]):
             g["copy"].wait_event(done)
             for r in range(self.world):              # (row by row: a strided 2-D D2H copy is 30x slower)
-                g["host"][k][r, :used].copy_(src[r, :used], non_blocking=True)
+                g["host"][k][r].copy_(src[r], non_blocking=True)
             g["ev"][k].record(g["copy"])
-        return (k, all_sizes)
+        return k
+
+    def _gather_release(self):
+        # registered host memory must be unregistered before it is unmapped (the address range may be handed out again)
+        g = getattr(self, "_g", None)
+        if g and g.get("mine"):
+            torch.cuda.synchronize(self.device)
+            for t in g["mine"]:
+                torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
+        self._g = {"cap": -1, "via": None}
+
+    def _shm_setup(self, cap):
+        import os
+        g = self._g
+        tag = "%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid() if self.world > 1 else os.getpid())
+        path = lambda r, k: "/dev/shm/b2_gather_%s_r%d_%d" % (tag, r, k)
+        g["mine"] = []
+        for k in range(2):
+            with open(path(self.rank, k), "wb") as f:
+                f.truncate(cap)
+            t = torch.from_file(path(self.rank, k), shared=True, size=cap, dtype=torch.uint8)
+            rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), cap, 0)
+            if int(rc) != 0:
+                raise RuntimeError("cudaHostRegister failed: %s" % rc)
+            g["mine"].append(t)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if self.rank == 0:
+            g["all"] = [[g["mine"][k] if r == 0 else torch.from_file(path(r, k), shared=True, size=cap, dtype=torch.uint8)
+                         for r in range(self.world)] for k in range(2)]
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for k in range(2):                               # the mappings keep the memory alive
+            os.unlink(path(self.rank, k))
 
     def gather_wait(self, ticket):
-        """rank 0: -> list over source ranks of (records, payload bytes) numpy views into pinned memory (valid until the
-        ticket after next); other ranks: None"""
+        """rank 0: -> list over source ranks of (records, payload bytes) numpy views into host memory (valid until the
+        next gather_wait); other ranks: None.  With via="shm" every rank must call it (it holds the barrier that tells
+        rank 0 that everybody's copy has landed)."""
         if ticket is None:
             return None
-        k, all_sizes = ticket
-        self._g["ev"][k].synchronize()
-        host = self._g["host"][k].numpy()
+        k = ticket
+        g = self._g
+        g["ev"][k].synchronize()
+        if g["via"] == "shm":
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            if self.rank != 0:
+                return None
+            rows = [t.numpy() for t in g["all"][k]]
+        else:
+            host = g["host"][k].numpy()
+            rows = [host[r] for r in range(self.world)]
         out = []
         isz = self.capi.FRAME_DTYPE.itemsize
-        for r in range(self.world):
-            nr, nb = int(all_sizes[r][0]), int(all_sizes[r][1])
-            out.append((host[r, :nr * isz].view(self.capi.FRAME_DTYPE), host[r, nr * isz:nr * isz + nb]))
+        for row in rows:
+            nr, nb = (int(v) for v in row[:16].view(np.uint64))
+            out.append((row[16:16 + nr * isz].view(self.capi.FRAME_DTYPE), row[16 + nr * isz:16 + nr * isz + nb]))
         return out
 
     def reset(self):
@@ -350,5 +402,6 @@ class ShardedRx:
     def close(self):
         if self.h:
             torch.cuda.synchronize(self.device)
+            self._gather_release()
             self.L.b2_mcrx_shard_destroy(self.h)
             self.h = None

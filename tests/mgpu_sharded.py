@@ -50,7 +50,8 @@ def main():
         for c in range(calls):
             rx.execute_device([b.data_ptr() for b in bufs[c * steps:(c + 1) * steps]])
             rx.poll_view()
-            res = rx.gather_wait(rx.gather_async(1 << 24))           # NCCL gather from device memory + D2H on rank 0
+            # both routes to rank 0's host memory: NCCL gather + rank 0's D2H, and every rank's own D2H into shared memory
+            res = rx.gather_wait(rx.gather_async(1 << 24, via=("nccl" if c == 0 else "shm")))
             if rank == 0:
                 for r_, p_ in res:
                     r_ = r_.copy()
