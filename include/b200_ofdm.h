@@ -156,10 +156,12 @@ int b2_mcrx_shard_poll(b2_mcrx_shard * q, b2_frame_rec * recs, size_t recs_cap, 
 int b2_mcrx_shard_poll_view(b2_mcrx_shard * q, const b2_frame_rec ** recs, size_t * n_recs,
                             const uint8_t ** payloads, size_t * n_payload_bytes);
 /* the frames of the call that just ended, still in DEVICE memory, packed for a collective: dst_dev receives
- * [uint64 n_recs, uint64 n_payload_bytes | n_recs records of sizeof(b2_frame_rec) | payload bytes], payload_offset
+ * [uint64 n_recs, n_payload_bytes, seq, 0 | n_recs records of sizeof(b2_frame_rec) | payload bytes] (seq: the caller's
+ * tag of this pack; a reader of a copy that lands body first, header last can poll it), payload_offset
  * relative to the payload part, records in this rank's callback order (completion index, then channel: sorted on the
  * device); asynchronous on stream_stage2 */
-int b2_mcrx_shard_pack_results(b2_mcrx_shard * q, void * dst_dev, size_t cap_bytes, size_t * n_recs, size_t * n_payload_bytes);
+int b2_mcrx_shard_pack_results(b2_mcrx_shard * q, void * dst_dev, size_t cap_bytes, uint64_t seq, size_t * n_recs, size_t * n_payload_bytes);
+#define B2_SHARD_PACK_HEADER 32
 /* on = 0: _end no longer brings this rank's frames to its own host memory (nor orders them there); they are taken from
  * device memory with _pack_results instead -- the mode of a box where one rank collects everybody's frames.  Default 1. */
 int b2_mcrx_shard_host_results(b2_mcrx_shard * q, int on);

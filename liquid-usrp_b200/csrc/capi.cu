@@ -1313,21 +1313,22 @@ extern "C" int b2_mcrx_shard_poll_view(b2_mcrx_shard * q, const b2_frame_rec ** 
     return q->core.poll_view(recs, n_recs, payloads, n_payload_bytes);
 }
 
-extern "C" int b2_mcrx_shard_pack_results(b2_mcrx_shard * q, void * dst_dev, size_t cap_bytes, size_t * n_recs, size_t * n_payload_bytes)
+extern "C" int b2_mcrx_shard_pack_results(b2_mcrx_shard * q, void * dst_dev, size_t cap_bytes, uint64_t seq, size_t * n_recs, size_t * n_payload_bytes)
 {
     if (!q || !dst_dev) return b2_fail(B2_ERR_ARG, "null argument");
     B2_CUDA(cudaSetDevice(q->device));
     SyncCore & c = q->core;
+    const size_t H = B2_SHARD_PACK_HEADER;
     const size_t nr = c.chunk ? std::min<size_t>(c.h_range[c.chunk].nrec, c.recs_cap) : 0;
     const size_t nb = c.chunk ? (size_t)c.last_used : 0;
-    if (16 + nr * sizeof(FrameRec) + nb > cap_bytes) return b2_fail(B2_ERR_OVERFLOW, "pack buffer too small (%zu records, %zu payload bytes)", nr, nb);
-    // header: the sizes travel with the data (no separate size exchange); h_counters is pinned
-    unsigned long long * hdr = (unsigned long long *)(c.h_counters + 4) ;
+    if (H + nr * sizeof(FrameRec) + nb > cap_bytes) return b2_fail(B2_ERR_OVERFLOW, "pack buffer too small (%zu records, %zu payload bytes)", nr, nb);
+    // header: the sizes travel with the data (no separate size exchange); h_counters is pinned (32 bytes)
+    unsigned long long * hdr = (unsigned long long *)c.h_counters;
     B2_CUDA(cudaStreamSynchronize(q->s2));                               // the previous header copy has been consumed
-    hdr[0] = nr; hdr[1] = nb;
-    B2_CUDA(cudaMemcpyAsync(dst_dev, hdr, 16, cudaMemcpyHostToDevice, q->s2));
-    if (nr) B2_CUDA(pack_sorted_launch(c.d_recs.as<FrameRec>(), (unsigned int)nr, (FrameRec *)((char *)dst_dev + 16), q->s2));
-    if (nb) B2_CUDA(cudaMemcpyAsync((char *)dst_dev + 16 + nr * sizeof(FrameRec), c.d_decoded.p, nb, cudaMemcpyDeviceToDevice, q->s2));
+    hdr[0] = nr; hdr[1] = nb; hdr[2] = seq; hdr[3] = 0;
+    B2_CUDA(cudaMemcpyAsync(dst_dev, hdr, H, cudaMemcpyHostToDevice, q->s2));
+    if (nr) B2_CUDA(pack_sorted_launch(c.d_recs.as<FrameRec>(), (unsigned int)nr, (FrameRec *)((char *)dst_dev + H), q->s2));
+    if (nb) B2_CUDA(cudaMemcpyAsync((char *)dst_dev + H + nr * sizeof(FrameRec), c.d_decoded.p, nb, cudaMemcpyDeviceToDevice, q->s2));
     if (n_recs) *n_recs = nr;
     if (n_payload_bytes) *n_payload_bytes = nb;
     return B2_OK;

@@ -25,7 +25,7 @@ namespace b2 {
 
 constexpr unsigned int A8_JB = 8;       // rows per round
 constexpr unsigned int A8_P = 14;       // taps per branch (m = 7, lib/multichannelrx.cc:89)
-constexpr unsigned int A8_OLD = A8_JB + 1;
+constexpr unsigned int A8_OLD = 2 * A8_JB + 1;   // row length of the output staging tile: two rounds of columns + 1 (bank skew)
 
 struct A8Layout { size_t off_bar, off_rw, off_tw, off_stage, off_a, off_b, off_out, total; };
 __host__ __device__ constexpr A8Layout a8_layout(unsigned int K)
@@ -149,22 +149,26 @@ __global__ void __launch_bounds__(K, 1) analyzer8_kernel(const AnalyzerParams p)
         else
             f8_run<K, 1, -1>(v, j, bufB + g * BUF, bufA + g * BUF, nullptr, [] { __syncthreads(); }, nullptr, tw);
 
-        // channels 0..N-1 -> out[c][col0 + block], via a transposed tile
+        // channels 0..N-1 -> out[c][col0 + block], via a transposed tile that collects TWO rounds: every channel then
+        // receives one contiguous 128-byte run per flush (full lines in HBM, and full-size packets when the run goes to a
+        // peer GPU over NVLink in the multi-GPU split)
+        const unsigned int half = k & 1u;
 #pragma unroll
-        for (unsigned int s = 0; s < 4; s++) outst[(j + s * T8) * A8_OLD + g] = v[s];
-        __syncthreads();
-        {
-            const size_t col = p.out_col0 + B0 + k * JB;
-            for (unsigned int e = r; e < N * (JB / 2); e += K) {
-                const unsigned int c = e / (JB / 2), q2 = (e % (JB / 2)) * 2;
-                if (q2 >= nb) continue;
+        for (unsigned int s = 0; s < 4; s++) outst[(j + s * T8) * A8_OLD + half * JB + g] = v[s];
+        if (half == 1u || k + 1 == nrounds) {
+            __syncthreads();
+            const unsigned int ncols = half * JB + nb;
+            const size_t col = p.out_col0 + B0 + (k - half) * JB;
+            for (unsigned int e = r; e < N * JB; e += K) {
+                const unsigned int c = e / JB, q2 = (e % JB) * 2;
+                if (q2 >= ncols) continue;
                 // (multi-GPU split: the run goes to the GPU that owns channel c)
                 cf * row = p.n_peer ? p.out_peer[c / p.chan_per_peer] + (size_t)(c % p.chan_per_peer) * p.out_stride
                                     : p.out + (size_t)c * p.out_stride;
                 cf * dst = row + col + q2;
                 const cf x0 = outst[c * A8_OLD + q2], x1 = outst[c * A8_OLD + q2 + 1];
-                if (q2 + 1 < nb && ((((size_t)dst) & 15) == 0)) *(float4 *)dst = make_float4(x0.x, x0.y, x1.x, x1.y);
-                else { dst[0] = x0; if (q2 + 1 < nb) dst[1] = x1; }
+                if (q2 + 1 < ncols && ((((size_t)dst) & 15) == 0)) *(float4 *)dst = make_float4(x0.x, x0.y, x1.x, x1.y);
+                else { dst[0] = x0; if (q2 + 1 < ncols) dst[1] = x1; }
             }
         }
         // the next round's outst / bufA writes come after its own barriers

@@ -152,6 +152,7 @@ class ShardedRx:
     round next), torch.distributed gather of the frame records at the end of a call.
     """
     SLOTS = 3
+    PACK_HEADER = 32
 
     def __init__(self, num_channels, M, cp_len, taper_len, chunk_blocks, steps_per_call, rank, world, device=0, group=None,
                  host_results=True):
@@ -310,8 +311,11 @@ class ShardedRx:
         nr, nb = C.c_size_t(0), C.c_size_t(0)
         k = g["k"] & 1
         g["k"] += 1
+        seq = g["k"]                                  # tag of this pack (1, 2, ...)
         with torch.cuda.stream(self.s2):
-            capi._check(self.L.b2_mcrx_shard_pack_results(self.h, C.c_void_p(g["send"].data_ptr()), cap_bytes, C.byref(nr), C.byref(nb)))
+            if g.get("last_ev") is not None:          # the previous pack has left the send buffer
+                self.s2.wait_event(g["last_ev"])
+            capi._check(self.L.b2_mcrx_shard_pack_results(self.h, C.c_void_p(g["send"].data_ptr()), cap_bytes, seq, C.byref(nr), C.byref(nb)))
             src = None
             if via == "nccl":
                 if self.world == 1:
@@ -322,13 +326,17 @@ class ShardedRx:
                     src = g["recv"][k] if self.rank == 0 else None
             done = torch.cuda.Event()
             done.record(self.s2)
-        used = 16 + nr.value * capi.FRAME_DTYPE.itemsize + nb.value
+        H = self.PACK_HEADER
+        used = H + nr.value * capi.FRAME_DTYPE.itemsize + nb.value
         if via == "shm":
             with torch.cuda.stream(g["copy"]):
                 g["copy"].wait_event(done)
-                g["mine"][k][:used].copy_(g["send"][:used], non_blocking=True)
+                # body first, header (with the tag rank 0 polls) last: copies of one stream land in order
+                g["mine"][k][H:used].copy_(g["send"][H:used], non_blocking=True)
+                g["mine"][k][:H].copy_(g["send"][:H], non_blocking=True)
                 g["ev"][k].record(g["copy"])
-            return k
+            g["last_ev"] = g["ev"][k]
+            return (k, seq)
         if self.rank != 0:
             return None
         with torch.cuda.stream(g["copy"]):
@@ -336,7 +344,8 @@ class ShardedRx:
             for r in range(self.world):              # (row by row: a strided 2-D D2H copy is 30x slower)
                 g["host"][k][r].copy_(src[r], non_blocking=True)
             g["ev"][k].record(g["copy"])
-        return k
+        g["last_ev"] = g["ev"][k]
+        return (k, seq)
 
     def _gather_release(self):
         # registered host memory must be unregistered before it is unmapped (the address range may be handed out again)
@@ -373,27 +382,33 @@ class ShardedRx:
 
     def gather_wait(self, ticket):
         """rank 0: -> list over source ranks of (records, payload bytes) numpy views into host memory (valid until the
-        next gather_wait); other ranks: None.  With via="shm" every rank must call it (it holds the barrier that tells
-        rank 0 that everybody's copy has landed)."""
+        gather_wait after next); other ranks: None.  With via="shm" rank 0 polls the tag every rank's copy writes last
+        (no collective, nobody else waits)."""
         if ticket is None:
             return None
-        k = ticket
+        k, seq = ticket
         g = self._g
-        g["ev"][k].synchronize()
         if g["via"] == "shm":
-            if self.world > 1:
-                dist.barrier(group=self.group)
             if self.rank != 0:
                 return None
+            import time
             rows = [t.numpy() for t in g["all"][k]]
+            t0 = time.perf_counter()
+            for row in rows:
+                tag = row[16:24].view(np.uint64)
+                while int(tag[0]) != seq:
+                    if time.perf_counter() - t0 > 30.0:
+                        raise RuntimeError("timed out waiting for a rank's frames in shared memory")
+                    time.sleep(0)
         else:
+            g["ev"][k].synchronize()
             host = g["host"][k].numpy()
             rows = [host[r] for r in range(self.world)]
         out = []
-        isz = self.capi.FRAME_DTYPE.itemsize
+        isz, H = self.capi.FRAME_DTYPE.itemsize, self.PACK_HEADER
         for row in rows:
             nr, nb = (int(v) for v in row[:16].view(np.uint64))
-            out.append((row[16:16 + nr * isz].view(self.capi.FRAME_DTYPE), row[16 + nr * isz:16 + nr * isz + nb]))
+            out.append((row[H:H + nr * isz].view(self.capi.FRAME_DTYPE), row[H + nr * isz:H + nr * isz + nb]))
         return out
 
     def reset(self):
