@@ -166,6 +166,8 @@ int b2_mcrx_shard_pack_results(b2_mcrx_shard * q, void * dst_dev, size_t cap_byt
  * device memory with _pack_results instead -- the mode of a box where one rank collects everybody's frames.  Default 1. */
 int b2_mcrx_shard_host_results(b2_mcrx_shard * q, int on);
 int b2_mcrx_shard_reset(b2_mcrx_shard * q);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): for plumbing that moves a pack into registered host memory */
+int b2_memcpy_async(void * dst, const void * src, size_t bytes, void * stream);
 
 /* ------------------------------------------------------------------ multichanneltx
  * replaces: multichanneltx::multichanneltx        lib/multichanneltx.cc:41-100

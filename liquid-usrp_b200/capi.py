@@ -93,6 +93,7 @@ _PROTOS = {
     "b2_mcrx_shard_poll": (C.c_int, [_vp, _vp, _sz, C.POINTER(_sz), _vp, _sz, C.POINTER(_sz)]),
     "b2_mcrx_shard_reset": (C.c_int, [_vp]),
     "b2_mcrx_shard_host_results": (C.c_int, [_vp, C.c_int]),
+    "b2_memcpy_async": (C.c_int, [_vp, _vp, _sz, _vp]),
     "b2_mcrx_shard_poll_view": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp), C.POINTER(_sz)]),
     "b2_mcrx_shard_pack_results": (C.c_int, [_vp, _vp, _sz, C.c_uint64, C.POINTER(_sz), C.POINTER(_sz)]),
 }

@@ -1354,3 +1354,11 @@ extern "C" int b2_mcrx_shard_reset(b2_mcrx_shard * q)
     B2_CUDA(cudaSetDevice(q->device));
     return q->core.reset_streams();
 }
+
+extern "C" int b2_memcpy_async(void * dst, const void * src, size_t bytes, void * stream)
+{
+    if (bytes == 0) return B2_OK;
+    if (!dst || !src) return b2_fail(B2_ERR_ARG, "null pointer");
+    B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return B2_OK;
+}

@@ -13,8 +13,7 @@
 //                 frame: lane L owns states 2L, 2L+1; decisions ballot-packed, 64 bit per step).
 //   CRC-32      : 32 lanes x bytewise CRC of a slice, slices merged with x^(8n) mod P products.
 #include <mutex>
-#include <thrust/sort.h>
-#include <thrust/execution_policy.h>
+#include <cub/device/device_radix_sort.cuh>
 #include "kernels.h"
 #include "fec.cuh"
 
@@ -743,24 +742,34 @@ __global__ void rec_permute_kernel(const FrameRec * recs, const unsigned int * i
 cudaError_t pack_sorted_launch(const FrameRec * recs, unsigned int n, FrameRec * dst, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    static thread_local unsigned long long * keys = nullptr;
-    static thread_local unsigned int * idx = nullptr;
-    static thread_local unsigned int cap = 0;
-    static thread_local int cap_dev = -1;
+    // scratch of the calling thread's device, grown on demand and never freed on the data path (no allocation, and
+    // therefore no device-wide synchronisation, once it has its size)
+    struct Scratch { unsigned long long * keys[2] = {nullptr, nullptr}; unsigned int * idx[2] = {nullptr, nullptr}; void * tmp = nullptr;
+                     size_t tmp_bytes = 0; unsigned int cap = 0; int dev = -1; };
+    static thread_local Scratch sc;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (n > cap || dev != cap_dev) {
-        if (keys) cudaFree(keys);
-        if (idx) cudaFree(idx);
-        cap = n + n / 4 + 1024; cap_dev = dev;
-        cudaError_t e = cudaMalloc(&keys, sizeof(unsigned long long) * cap);
-        if (e == cudaSuccess) e = cudaMalloc(&idx, sizeof(unsigned int) * cap);
-        if (e != cudaSuccess) { keys = nullptr; idx = nullptr; cap = 0; return e; }
+    if (n > sc.cap || dev != sc.dev) {
+        for (int i = 0; i < 2; i++) { if (sc.keys[i]) cudaFree(sc.keys[i]); if (sc.idx[i]) cudaFree(sc.idx[i]); sc.keys[i] = nullptr; sc.idx[i] = nullptr; }
+        if (sc.tmp) cudaFree(sc.tmp);
+        sc.tmp = nullptr; sc.cap = 0; sc.dev = dev;
+        const unsigned int cap = n + n / 4 + 1024;
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+            e = cudaMalloc(&sc.keys[i], sizeof(unsigned long long) * cap);
+            if (e == cudaSuccess) e = cudaMalloc(&sc.idx[i], sizeof(unsigned int) * cap);
+        }
+        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, sc.tmp_bytes, sc.keys[0], sc.keys[1], sc.idx[0], sc.idx[1], (int)cap, 0, 64, st);
+        if (e == cudaSuccess) e = cudaMalloc(&sc.tmp, sc.tmp_bytes);
+        if (e != cudaSuccess) return e;
+        sc.cap = cap;
     }
-    rec_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(recs, n, keys, idx);
-    thrust::sort_by_key(thrust::cuda::par_nosync.on(st), keys, keys + n, idx);
+    rec_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(recs, n, sc.keys[0], sc.idx[0]);
+    size_t tb = sc.tmp_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(sc.tmp, tb, sc.keys[0], sc.keys[1], sc.idx[0], sc.idx[1], (int)n, 0, 64, st);
+    if (e != cudaSuccess) return e;
     const unsigned int words = n * (unsigned int)(sizeof(FrameRec) / 4);
-    rec_permute_kernel<<<(words + 255) / 256, 256, 0, st>>>(recs, idx, n, dst);
+    rec_permute_kernel<<<(words + 255) / 256, 256, 0, st>>>(recs, sc.idx[1], n, dst);
     return cudaGetLastError();
 }
 

@@ -332,8 +332,9 @@ class ShardedRx:
             with torch.cuda.stream(g["copy"]):
                 g["copy"].wait_event(done)
                 # body first, header (with the tag rank 0 polls) last: copies of one stream land in order
-                g["mine"][k][H:used].copy_(g["send"][H:used], non_blocking=True)
-                g["mine"][k][:H].copy_(g["send"][:H], non_blocking=True)
+                cs = C.c_void_p(g["copy"].cuda_stream)
+                capi._check(self.L.b2_memcpy_async(C.c_void_p(g["mine"][k].data_ptr() + H), C.c_void_p(g["send"].data_ptr() + H), used - H, cs))
+                capi._check(self.L.b2_memcpy_async(C.c_void_p(g["mine"][k].data_ptr()), C.c_void_p(g["send"].data_ptr()), H, cs))
                 g["ev"][k].record(g["copy"])
             g["last_ev"] = g["ev"][k]
             return (k, seq)
