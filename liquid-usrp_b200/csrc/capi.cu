@@ -70,6 +70,7 @@ struct SyncCore {
     std::vector<uint8_t> view_payloads;
     RangeMark * h_range = nullptr;       // pinned copy of d_range
     cudaStream_t xstream = nullptr;      // device -> host copies of finished chunks
+    cudaStream_t mstream = nullptr;      // device -> host copies of the chunks' record counts
     std::vector<std::pair<unsigned long long, unsigned int>> order;
     void compact_pending();
     void process_chunk(unsigned int lo, unsigned int hi);
@@ -86,7 +87,7 @@ struct SyncCore {
     cudaStream_t dstreams[NDS] = {};     // frame is a long serial recursion: chunks must overlap)
     DevBuf d_range;                      // [chunks+1] record count after each chunk's synchroniser
     unsigned int range_cap = 0, chunk = 0, launches = 0;
-    struct ChunkEv { cudaEvent_t s0, s1, d0, d1, x; };
+    struct ChunkEv { cudaEvent_t s0, s1, d0, d1, x, m; };   // m: the chunk's record / payload counts have reached the host
     std::vector<ChunkEv> cev;            // sync begin/end, decode begin/end of each chunk
     bool timing = true;
     bool host_results = true;            // end_batch brings records + payloads to pinned host memory and orders them
@@ -228,6 +229,7 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     }
     dstream = dstreams[0];
     B2_CUDA(cudaStreamCreateWithFlags(&xstream, cudaStreamNonBlocking));
+    B2_CUDA(cudaStreamCreateWithFlags(&mstream, cudaStreamNonBlocking));
     range_cap = 4096;
     B2_TRY(d_range.alloc(sizeof(RangeMark) * (range_cap + 1)));
     B2_CUDA(cudaMallocHost(&h_range, sizeof(RangeMark) * (range_cap + 1)));
@@ -284,9 +286,11 @@ void SyncCore::destroy()
     if (h_payload) cudaFreeHost(h_payload);
     if (h_range) cudaFreeHost(h_range);
     if (xstream) cudaStreamDestroy(xstream);
+    if (mstream) cudaStreamDestroy(mstream);
+    mstream = nullptr;
     h_counters = nullptr; h_recs = nullptr; h_payload = nullptr; h_range = nullptr; xstream = nullptr;
     for (int i = 0; i < 5; i++) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; }
-    for (auto & e : cev) { cudaEventDestroy(e.s0); cudaEventDestroy(e.s1); cudaEventDestroy(e.d0); cudaEventDestroy(e.d1); cudaEventDestroy(e.x); }
+    for (auto & e : cev) { cudaEventDestroy(e.s0); cudaEventDestroy(e.s1); cudaEventDestroy(e.d0); cudaEventDestroy(e.d1); cudaEventDestroy(e.x); cudaEventDestroy(e.m); }
     cev.clear();
     for (unsigned int i = 0; i < NDS; i++) if (dstreams[i]) { cudaStreamDestroy(dstreams[i]); dstreams[i] = nullptr; }
     dstream = nullptr;
@@ -409,6 +413,7 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
         B2_CUDA(cudaEventCreate(&e.s0)); B2_CUDA(cudaEventCreate(&e.s1));
         B2_CUDA(cudaEventCreate(&e.d0)); B2_CUDA(cudaEventCreate(&e.d1));
         B2_CUDA(cudaEventCreateWithFlags(&e.x, cudaEventDisableTiming));
+        B2_CUDA(cudaEventCreateWithFlags(&e.m, cudaEventDisableTiming));
         cev.push_back(e);
     }
     ChunkEv & e = cev[chunk];
@@ -429,8 +434,12 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
     } else B2_CUDA(sync_launch(q, sync_threads, sync_smem, stream));
     RangeMark * range = d_range.as<RangeMark>() + chunk;
     B2_CUDA(record_mark_launch(d_counters.as<unsigned int>(), range + 1, stream, use_w ? 6 : 2));
-    B2_CUDA(cudaMemcpyAsync(h_range + chunk + 1, range + 1, sizeof(RangeMark), cudaMemcpyDeviceToHost, stream));
     B2_CUDA(cudaEventRecord(e.s1, stream));
+    // the counts go to the host on a stream of their own: a small D2H copy in the synchroniser's stream would queue
+    // behind whatever bulk D2H the copy engine is busy with (payloads of earlier chunks, a gather) and hold up the decode
+    B2_CUDA(cudaStreamWaitEvent(mstream, e.s1, 0));
+    B2_CUDA(cudaMemcpyAsync(h_range + chunk + 1, range + 1, sizeof(RangeMark), cudaMemcpyDeviceToHost, mstream));
+    B2_CUDA(cudaEventRecord(e.m, mstream));
     // decode of this chunk runs beside the synchroniser of the next one
     cudaStream_t ds = dstreams[chunk % NDS];
     B2_CUDA(cudaStreamWaitEvent(ds, e.s1, 0));
@@ -471,6 +480,7 @@ int SyncCore::end_batch()
     if (!host_results) {
         // the frames stay in device memory (b2_mcrx_shard_pack_results): wait for the last decode, keep the counts
         for (unsigned int i = 0; i < NDS && i < chunk; i++) B2_CUDA(cudaEventSynchronize(cev[chunk - 1 - i].d1));
+        B2_CUDA(cudaEventSynchronize(cev[chunk - 1].m));
         last_used = std::min(h_range[chunk].arena_used, out_cap);
         timing_stale = true;
         return collect();
@@ -479,6 +489,7 @@ int SyncCore::end_batch()
     for (unsigned int c = 0; c <= chunk; c++) {
         if (c < chunk) {
             B2_CUDA(cudaEventSynchronize(cev[c].d1));
+            B2_CUDA(cudaEventSynchronize(cev[c].m));
             const unsigned int lo = std::min(h_range[c].nrec, recs_cap), hi = std::min(h_range[c + 1].nrec, recs_cap);
             const unsigned long long ulo = std::min(h_range[c].arena_used, out_cap), uhi = std::min(h_range[c + 1].arena_used, out_cap);
             if (hi > lo) B2_CUDA(cudaMemcpyAsync(h_recs + lo, d_recs.as<FrameRec>() + lo, sizeof(FrameRec) * (hi - lo), cudaMemcpyDeviceToHost, xstream));
@@ -518,7 +529,8 @@ void SyncCore::fetch_timing()
 int SyncCore::collect()
 {
     // the overflow flag came back with the last chunk's mark; only the debug tap needs another trip
-    if (h_range[chunk].pad) return b2_fail(B2_ERR_OVERFLOW, (h_range[chunk].pad & 2u) ? "internal: synchroniser worker hand-off timed out"
+    // (bit 8: a frame larger than half the symbol arena was reported without its payload -- data, not an error)
+    if (h_range[chunk].pad & 7u) return b2_fail(B2_ERR_OVERFLOW, (h_range[chunk].pad & 2u) ? "internal: synchroniser worker hand-off timed out"
                                        : "frame output arena overflow: a frame larger than the per-call buffers completed; create the handle with a larger max_batch");
     if (!tap_cap) return B2_OK;
     B2_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));

@@ -153,6 +153,8 @@ class ShardedRx:
     """
     SLOTS = 3
     PACK_HEADER = 32
+    import os as _os
+    _dbg_nocopy = _os.environ.get("B2_DBG_NOCOPY") == "1"       # probe knob: packs leave the device without their body
 
     def __init__(self, num_channels, M, cp_len, taper_len, chunk_blocks, steps_per_call, rank, world, device=0, group=None,
                  host_results=True):
@@ -333,7 +335,11 @@ class ShardedRx:
                 g["copy"].wait_event(done)
                 # body first, header (with the tag rank 0 polls) last: copies of one stream land in order
                 cs = C.c_void_p(g["copy"].cuda_stream)
-                capi._check(self.L.b2_memcpy_async(C.c_void_p(g["mine"][k].data_ptr() + H), C.c_void_p(g["send"].data_ptr() + H), used - H, cs))
+                if self._dbg_nocopy:
+                    used = H
+                for o in range(H, used, 4 << 20):      # in pieces: small copies of other streams slip in between
+                    capi._check(self.L.b2_memcpy_async(C.c_void_p(g["mine"][k].data_ptr() + o), C.c_void_p(g["send"].data_ptr() + o),
+                                                       min(4 << 20, used - o), cs))
                 capi._check(self.L.b2_memcpy_async(C.c_void_p(g["mine"][k].data_ptr()), C.c_void_p(g["send"].data_ptr()), H, cs))
                 g["ev"][k].record(g["copy"])
             g["last_ev"] = g["ev"][k]
