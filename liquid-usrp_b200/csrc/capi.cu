@@ -392,12 +392,8 @@ int SyncCore::run(const cf * in, size_t in_stride, unsigned int nsamples, bool r
 int SyncCore::begin_batch()
 {
     compact_pending();                       // h_payload is about to be overwritten
-    if (use_w) {
-        // [2..3] is the allocation counter of the symbol ring: it keeps counting across batches
-        B2_CUDA(cudaMemsetAsync(d_counters.p, 0, 2 * sizeof(unsigned int), stream));
-        B2_CUDA(cudaMemsetAsync(d_counters.as<unsigned int>() + 4, 0, 4 * sizeof(unsigned int), stream));
-    } else B2_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(unsigned int), stream));
-    B2_CUDA(cudaMemsetAsync(d_range.p, 0, sizeof(RangeMark), stream));
+    // (frame-parallel kernel: counters[2..3] is the allocation counter of the symbol ring, it keeps counting across batches)
+    B2_CUDA(batch_reset_launch(d_counters.as<unsigned int>(), d_range.as<RangeMark>(), use_w ? 1 : 0, stream));
     memset(&h_range[0], 0, sizeof(RangeMark));
     chunk = 0; launches = 0;
     return B2_OK;
@@ -433,13 +429,11 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
         B2_CUDA(syncw_launch(q, stream));
     } else B2_CUDA(sync_launch(q, sync_threads, sync_smem, stream));
     RangeMark * range = d_range.as<RangeMark>() + chunk;
-    B2_CUDA(record_mark_launch(d_counters.as<unsigned int>(), range + 1, stream, use_w ? 6 : 2));
+    B2_CUDA(record_mark_launch(d_counters.as<unsigned int>(), range + 1, stream, use_w ? 6 : 2, h_range + chunk + 1));
     B2_CUDA(cudaEventRecord(e.s1, stream));
-    // the counts go to the host on a stream of their own: a small D2H copy in the synchroniser's stream would queue
-    // behind whatever bulk D2H the copy engine is busy with (payloads of earlier chunks, a gather) and hold up the decode
-    B2_CUDA(cudaStreamWaitEvent(mstream, e.s1, 0));
-    B2_CUDA(cudaMemcpyAsync(h_range + chunk + 1, range + 1, sizeof(RangeMark), cudaMemcpyDeviceToHost, mstream));
-    B2_CUDA(cudaEventRecord(e.m, mstream));
+    // (the mark kernel has written the counts into the pinned host copy itself: a small D2H copy would be a copy-engine
+    // operation and queue behind whatever bulk D2H is in flight -- payloads of earlier chunks, a gather)
+    B2_CUDA(cudaEventRecord(e.m, stream));
     // decode of this chunk runs beside the synchroniser of the next one
     cudaStream_t ds = dstreams[chunk % NDS];
     B2_CUDA(cudaStreamWaitEvent(ds, e.s1, 0));
@@ -1218,6 +1212,14 @@ extern "C" int b2_mcrx_shard_create(unsigned int N, unsigned int M, unsigned int
         if ((rc = q->core.init(M, cp, taper, p, q->cpp, q->row * steps_per_call, device, q->s2))) break;
         q->core.sp.chan_base = rank * q->cpp;                           // records carry the global channel index
         if (const char * e = getenv("B2_SHARD_COPY")) q->copy_mode = atoi(e) != 0;
+        // stage 1 is bound by NVLink when most of its output goes to peers: it does not need every SM, and the ones
+        // it leaves run the synchronisers of the previous step at full occupancy (B2_SHARD_AN_SMS overrides)
+        {
+            unsigned int an = q->chan->an_sms;
+            if (world >= 4 && an > 112) an = 112;
+            if (const char * e = getenv("B2_SHARD_AN_SMS")) { long v = atol(e); if (v >= 8 && v <= 1024) an = (unsigned int)v; }
+            if (an < q->chan->an_sms) q->chan->an_sms = an;
+        }
         if (q->copy_mode) {
             if ((rc = q->d_tile.alloc(sizeof(cf) * (size_t)N * q->tc))) break;
             B2_CUDA(cudaStreamCreateWithFlags(&q->cpy, cudaStreamNonBlocking));

@@ -244,7 +244,11 @@ cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t 
 // the synchroniser of a chunk and its decode so that chunk c decodes records [mark[c], mark[c+1])
 // records of a batch in callback order (completion index, then channel): device sort + permuting copy into dst
 cudaError_t pack_sorted_launch(const FrameRec * recs, unsigned int n, FrameRec * dst, cudaStream_t st);
-cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_out, cudaStream_t st, int used_at = 2);
+// host_out: the same mark written straight into (mapped) pinned host memory by the kernel -- no copy engine involved
+cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_out, cudaStream_t st, int used_at = 2, RangeMark * host_out = nullptr);
+// start of a batch: counters[0..1] and [4..7] (and [2..3] unless keep_ring) and the first mark to zero, as a kernel
+// (a cudaMemsetAsync of a few bytes is a copy-engine operation and waits behind any bulk copy in flight)
+cudaError_t batch_reset_launch(unsigned int * counters, RangeMark * mark0, int keep_ring, cudaStream_t st);
 
 } // namespace b2
 

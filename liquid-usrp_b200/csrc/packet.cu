@@ -710,16 +710,28 @@ __global__ void __launch_bounds__(PKF_WARPS * 32) packet_plain_kernel(const Pack
     }
 }
 
-__global__ void record_mark_kernel(const unsigned int * counters, RangeMark * mark_out, int used_at)
+__global__ void record_mark_kernel(const unsigned int * counters, RangeMark * mark_out, int used_at, RangeMark * host_out)
 {
     RangeMark m;
     m.nrec = counters[0]; m.pad = counters[1];           // pad: overflow flag so far
     m.arena_used = *(const unsigned long long *)(counters + used_at);   // bytes of decoded payload so far
     *mark_out = m;
+    if (host_out) { *host_out = m; __threadfence_system(); }
 }
-cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_out, cudaStream_t st, int used_at)
+cudaError_t record_mark_launch(const unsigned int * counters, RangeMark * mark_out, cudaStream_t st, int used_at, RangeMark * host_out)
 {
-    record_mark_kernel<<<1, 1, 0, st>>>(counters, mark_out, used_at);
+    record_mark_kernel<<<1, 1, 0, st>>>(counters, mark_out, used_at, host_out);
+    return cudaGetLastError();
+}
+__global__ void batch_reset_kernel(unsigned int * counters, RangeMark * mark0, int keep_ring)
+{
+    const unsigned int i = threadIdx.x;
+    if (i < 8 && !(keep_ring && (i == 2 || i == 3))) counters[i] = 0u;
+    if (i == 8) { RangeMark z; z.nrec = 0; z.pad = 0; z.arena_used = 0; *mark0 = z; }
+}
+cudaError_t batch_reset_launch(unsigned int * counters, RangeMark * mark0, int keep_ring, cudaStream_t st)
+{
+    batch_reset_kernel<<<1, 32, 0, st>>>(counters, mark0, keep_ring);
     return cudaGetLastError();
 }
 
