@@ -188,7 +188,8 @@ class MultichannelRx(_FrameSource):
     def __init__(self, num_channels, M, cp_len, taper_len, p=None, device=0, max_batch=0):
         self.N, self.M, self.cp, self.taper = num_channels, M, cp_len, taper_len
         h = _vp()
-        pp = None if p is None else np.ascontiguousarray(p, np.uint8).ctypes.data
+        p_arr = None if p is None else np.ascontiguousarray(p, np.uint8)      # kept alive until the call returns
+        pp = None if p_arr is None else p_arr.ctypes.data
         _check(lib().b2_mcrx_create(num_channels, M, cp_len, taper_len, pp, device, max_batch, C.byref(h)))
         self.h = h
 
@@ -241,7 +242,8 @@ class OfdmSync(_FrameSource):
     def __init__(self, M, cp_len, taper_len, p=None, streams=1, device=0, max_batch=0):
         self.M, self.cp, self.taper, self.streams = M, cp_len, taper_len, streams
         h = _vp()
-        pp = None if p is None else np.ascontiguousarray(p, np.uint8).ctypes.data
+        p_arr = None if p is None else np.ascontiguousarray(p, np.uint8)      # kept alive until the call returns
+        pp = None if p_arr is None else p_arr.ctypes.data
         _check(lib().b2_ofdmsync_create(M, cp_len, taper_len, pp, streams, device, max_batch, C.byref(h)))
         self.h = h
 
@@ -276,7 +278,8 @@ class MultichannelTx(_Handle):
     def __init__(self, num_channels, M, cp_len, taper_len, p=None, device=0):
         self.N, self.M, self.cp, self.taper = num_channels, M, cp_len, taper_len
         h = _vp()
-        pp = None if p is None else np.ascontiguousarray(p, np.uint8).ctypes.data
+        p_arr = None if p is None else np.ascontiguousarray(p, np.uint8)      # kept alive until the call returns
+        pp = None if p_arr is None else p_arr.ctypes.data
         _check(lib().b2_mctx_create(num_channels, M, cp_len, taper_len, pp, device, C.byref(h)))
         self.h = h
 
@@ -319,7 +322,8 @@ class OfdmGen(_Handle):
     def __init__(self, M, cp_len, taper_len, p=None, device=0):
         self.M, self.cp, self.taper = M, cp_len, taper_len
         h = _vp()
-        pp = None if p is None else np.ascontiguousarray(p, np.uint8).ctypes.data
+        p_arr = None if p is None else np.ascontiguousarray(p, np.uint8)      # kept alive until the call returns
+        pp = None if p_arr is None else p_arr.ctypes.data
         _check(lib().b2_ofdmgen_create(M, cp_len, taper_len, pp, device, C.byref(h)))
         self.h = h
 

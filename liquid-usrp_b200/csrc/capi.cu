@@ -206,7 +206,10 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     // arena of a batch: the symbols demapped inside the batch (<= one byte per sample) plus, per stream, one
     // frame that began in earlier batches and completes in this one (bounded here to 32 KB of symbol bytes;
     // B2_ERR_OVERFLOW reports a frame that does not fit)
-    arena_cap = (unsigned long long)streams * (tmax + 64 + std::min<size_t>(penc_cap, 32768)) + 16ull * recs_cap;
+    // (up to 64 MB of it: with few streams -- the single-link programs -- any legal frame fits; beyond that a frame
+    // that does not fit is reported without its payload)
+    const size_t carry = ((unsigned long long)streams * penc_cap <= (64ull << 20)) ? penc_cap : std::min<size_t>(penc_cap, 32768);
+    arena_cap = (unsigned long long)streams * (tmax + 64 + carry) + 16ull * recs_cap;
     // (frame-parallel kernel: a stretch whose prediction failed is demapped twice, once speculatively and once by
     // the stitcher, and the speculative copy's arena space is simply left unused)
     out_cap = arena_cap;

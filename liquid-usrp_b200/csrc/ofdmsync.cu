@@ -571,10 +571,13 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
             }
         } else {
             // byte j of the encoded payload collects the bits [8j, 8j+8) of the symbol stream
+            // (a frame without payload symbols -- length 0, no check, no FEC -- has nothing to pack: take = 0 or enc = 0
+            // would wrap j1 around and the loop below would never end; the frame completes with this symbol)
             const unsigned int bit0 = pstart * bps, nbits = take * bps;
-            unsigned int j0 = bit0 >> 3, j1 = (bit0 + nbits - 1) >> 3;
-            if (j1 >= enc) j1 = enc - 1;
-            for (unsigned int j = j0 + tid; j <= j1; j += nt) {
+            const bool nothing = (nbits == 0u || enc == 0u);
+            unsigned int j0 = bit0 >> 3, j1 = nothing ? 0u : (bit0 + nbits - 1) >> 3;
+            if (!nothing && j1 >= enc) j1 = enc - 1;
+            for (unsigned int j = j0 + tid; !nothing && j <= j1; j += nt) {
                 unsigned int lo = max(8 * j, bit0), hi = min(8 * j + 8, bit0 + nbits);     // bit range from this symbol
                 unsigned int d0 = div_bps(lo - bit0, bps), d1 = div_bps(hi - 1 - bit0, bps);
                 unsigned long long acc = 0;
@@ -598,17 +601,18 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
                 unsigned long long offb = 0;
                 unsigned int e2 = (emit == 2) ? S->payload_enc_len : 0u;
                 int ok = slot < p.recs_cap;
+                bool dropped = false;                   // the payload does not fit what is left of the arena: data, not an error
                 if (ok && e2) {
                     offb = atomicAdd((unsigned long long *)(p.counters + 2), (unsigned long long)((e2 + 15u) & ~15u));
-                    if (offb + e2 > p.arena_cap) ok = 0;
+                    if (offb + e2 > p.arena_cap) { dropped = true; e2 = 0; offb = 0; atomicOr(&p.counters[1], 8u); }
                 }
-                if (!ok) { atomicExch(&p.counters[1], 1u); red[115] = -1.f; }
+                if (!ok) { atomicOr(&p.counters[1], 1u); red[115] = -1.f; }
                 else {
                     FrameRec r;
                     r.channel = p.chan_base + sidx;
                     r.header_valid = (emit == 2);
                     r.payload_valid = 0;
-                    r.payload_len = (emit == 2) ? S->payload_len : 0u;
+                    r.payload_len = (emit == 2 && !dropped) ? S->payload_len : 0u;
                     for (int i = 0; i < 8; i++) r.header[i] = S->header_dec[i];
                     r.evm = S->evm_db;
                     r.rssi = -10.0f * log10f(S->g0);
@@ -622,9 +626,9 @@ __global__ void __launch_bounds__(256) sync_kernel(const SyncParams p)
                     r.complete_index = S->sample_index - 1;
                     r.payload_offset = offb;
                     p.recs[slot] = r;
-                    FrameAux a; a.enc_len = e2; a.sym_bps = 0; a.sym_off = offb;
+                    FrameAux a; a.enc_len = e2; a.sym_bps = dropped ? 0xffffffffu : 0u; a.sym_off = offb;
                     p.aux[slot] = a;
-                    red[115] = 1.f;
+                    red[115] = dropped ? 0.f : 1.f;
                     dsum[30] = __longlong_as_double((long long)offb);
                 }
             }

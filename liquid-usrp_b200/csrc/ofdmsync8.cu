@@ -1053,7 +1053,7 @@ __global__ void __launch_bounds__(M / 8, (M <= 1024 ? B2_S8_THREADS_PER_SM : 512
                 }
                 int ok = slot < p.recs_cap;
                 if (m2 && offb + ((m2 + 15u) & ~15u) > p.arena_cap) ok = 0;
-                if (!ok) { atomicExch(&p.counters[1], 1u); red[115] = -1.f; }
+                if (!ok) { atomicOr(&p.counters[1], 1u); red[115] = -1.f; }
                 else {
                     FrameRec r;
                     r.channel = p.chan_base + sidx;

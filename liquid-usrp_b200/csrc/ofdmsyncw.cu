@@ -749,8 +749,8 @@ __global__ void __launch_bounds__(WPC * 32, MINB) syncw_kernel(const SyncParams 
                                 a = shfl0(a);
                                 S->sym_abs = a; sym_off = shfl0(ph);
                             }
-                            // a frame without payload symbols is complete with its header (liquid would wait for ever)
-                            if (S->payload_mod_len == 0) emit = 2;
+                            // (a frame without payload symbols -- liquid would wait for ever -- completes with the next OFDM
+                            // symbol, as in the serial-chain kernels: take = 0 there)
                         } else emit = 1;
                         __syncwarp();
                     }

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <time.h>
 #include <vector>
 
 #include <liquid/liquid.h>
@@ -179,6 +180,7 @@ struct ofdmflexframesync_s {
     void * userdata;
     std::vector<std::complex<float> > pending;
     size_t batch;
+    long long first_ns, max_wait_ns;       // oldest staged sample / $B2_SYNC_MAX_LATENCY_MS (default 5 ms)
     float rssi, cfo;
 };
 
@@ -194,6 +196,8 @@ ofdmflexframesync ofdmflexframesync_create(unsigned int M, unsigned int cp, unsi
     }
     if (b2_ofdmsync_create(M, cp, taper, p, 1, env_device(), q->batch, &q->s) != B2_OK) die("ofdmflexframesync_create()");
     q->callback = callback; q->userdata = userdata;
+    q->first_ns = 0; q->max_wait_ns = 5000000ll;
+    if (const char * e = getenv("B2_SYNC_MAX_LATENCY_MS")) q->max_wait_ns = (long long)(atof(e) * 1e6);
     q->pending.reserve(q->batch);
     q->rssi = 0.0f; q->cfo = 0.0f;
     return q;
@@ -234,16 +238,27 @@ void ofdmflexframesync_reset(ofdmflexframesync q)
     ofdmflexframesync_flush(q);
     b2_ofdmsync_reset(q->s);
 }
+static inline long long b2_now_ns()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
 void ofdmflexframesync_execute(ofdmflexframesync q, liquid_float_complex * x, unsigned int n)
 {
+    if (n == 0) return;
+    if (q->pending.empty() && q->max_wait_ns > 0) q->first_ns = b2_now_ns();
     unsigned int i = 0;
     while (i < n) {
         size_t c = q->batch - q->pending.size();
         if (c > n - i) c = n - i;
         q->pending.insert(q->pending.end(), x + i, x + i + c);
         i += (unsigned int)c;
-        if (q->pending.size() >= q->batch) ofdmflexframesync_flush(q);
+        if (q->pending.size() >= q->batch) { ofdmflexframesync_flush(q); if (q->max_wait_ns > 0) q->first_ns = b2_now_ns(); }
     }
+    // liquid fires the callback inside this call; here samples are staged, but never for longer than the bound
+    // (a receive worker that feeds one sample per call, lib/ofdmtxrx.cc:620-626, still gets its batching)
+    if (!q->pending.empty() && q->max_wait_ns > 0 && b2_now_ns() - q->first_ns >= q->max_wait_ns) ofdmflexframesync_flush(q);
 }
 void ofdmflexframesync_print(ofdmflexframesync q) { (void)q; printf("ofdmflexframesync (b200)\n"); }
 float ofdmflexframesync_get_rssi(ofdmflexframesync q) { return q->rssi; }

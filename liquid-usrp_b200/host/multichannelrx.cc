@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <time.h>
 
 #include "b200_ofdm.h"
 #include "multichannelrx.h"
@@ -48,6 +49,9 @@ multichannelrx::multichannelrx(unsigned int _num_channels, unsigned int _M, unsi
     userdata.assign(_userdata, _userdata + num_channels);
     callback.assign(_callback, _callback + num_channels);
 
+    flush_min = 16384; max_wait_ns = 5000000ll; first_ns = 0;
+    if (const char * e = getenv("B2_MCRX_FLUSH_MIN")) { unsigned long v = strtoul(e, NULL, 10); if (v >= 1) flush_min = (unsigned int)v; }
+    if (const char * e = getenv("B2_MCRX_MAX_LATENCY_MS")) max_wait_ns = (long long)(atof(e) * 1e6);
     stage_cap = 1u << 20;
     if (const char * e = getenv("B2_MCRX_BATCH")) {
         unsigned long v = strtoul(e, NULL, 10);
@@ -96,8 +100,17 @@ void multichannelrx::Reset()
     }
 }
 
+static inline long long now_ns()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
+
 void multichannelrx::Execute(std::complex<float> * _x, unsigned int _num_samples)
 {
+    if (_num_samples == 0) return;
+    if (stage_len == 0 && max_wait_ns > 0) first_ns = now_ns();
     unsigned int i = 0;
     while (i < _num_samples) {
         unsigned int c = _num_samples - i;
@@ -106,8 +119,11 @@ void multichannelrx::Execute(std::complex<float> * _x, unsigned int _num_samples
         else memcpy(stage + stage_len, _x + i, sizeof(std::complex<float>) * c);
         stage_len += c;
         i += c;
-        if (stage_len == stage_cap) Flush();
+        if (stage_len == stage_cap) { Flush(); if (max_wait_ns > 0) first_ns = now_ns(); }
     }
+    // bounded callback latency: a call that is a packet by itself is processed now, and so is whatever has been waiting
+    // for longer than the bound (the one-sample-per-call pattern of src/multichannel_rx.cc:211 keeps its batching)
+    if (stage_len && (_num_samples >= flush_min || (max_wait_ns > 0 && now_ns() - first_ns >= max_wait_ns))) Flush();
 }
 
 void multichannelrx::Flush()

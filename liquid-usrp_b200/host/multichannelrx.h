@@ -46,7 +46,8 @@ public:
     // extension: process everything pushed so far and deliver the pending callbacks
     void Flush();
     // extension: wideband samples accumulated before an automatic flush (default 2^20,
-    // or $B2_MCRX_BATCH)
+    // or $B2_MCRX_BATCH); Execute also flushes at the end of a call of >= $B2_MCRX_FLUSH_MIN samples and when
+    // the oldest staged sample is older than $B2_MCRX_MAX_LATENCY_MS
     void SetBatchSize(unsigned int _num_samples);
 
 private:
@@ -61,6 +62,10 @@ private:
     std::vector<framesync_callback> callback;
     std::complex<float> * stage;         // pinned host staging buffer
     unsigned int stage_len, stage_cap;
+    // callbacks fire inside Execute in the reference; here samples are staged, so a call flushes when it is long
+    // enough to be worth a launch by itself, or when the oldest staged sample has waited max_wait_ns
+    unsigned int flush_min;              // $B2_MCRX_FLUSH_MIN, default 16384 samples
+    long long max_wait_ns, first_ns;     // $B2_MCRX_MAX_LATENCY_MS, default 5 ms (0: only the batch size counts)
 };
 
 #endif // __MULTICHANNELRX_H__

@@ -35,7 +35,15 @@ multichanneltxrx::multichanneltxrx(unsigned int _num_channels, unsigned int _M, 
     pthread_create(&tx_process, NULL, multichanneltxrx_tx_worker, (void *)this);
 
     rx_running = false; rx_thread_running = true;
-    pthread_mutex_init(&rx_mutex, NULL);
+    // recursive: the receive worker delivers the frame callbacks with the lock held, and a callback may well call
+    // stop_rx() / reset_rx() (the reference takes no lock there at all, lib/multichanneltxrx.cc:613)
+    {
+        pthread_mutexattr_t attr;
+        pthread_mutexattr_init(&attr);
+        pthread_mutexattr_settype(&attr, PTHREAD_MUTEX_RECURSIVE);
+        pthread_mutex_init(&rx_mutex, &attr);
+        pthread_mutexattr_destroy(&attr);
+    }
     pthread_cond_init(&rx_cond, NULL);
     pthread_create(&rx_process, NULL, multichanneltxrx_rx_worker, (void *)this);
 }

@@ -19,7 +19,7 @@ EXACT = ("channel", "header_valid", "payload_valid", "payload_len", "header", "m
 
 @pytest.fixture(scope="module")
 def b2lib():
-    return McLib(os.path.join(ROOT, "liquid-usrp_b200", "libliquidusrp_b200.so"))
+    return McLib(os.path.join(ROOT, "tests", "shim", "libmcshim_b200.so"))
 
 
 @pytest.mark.parametrize("cfg", [(8, 64, 16, 4, MOD_QPSK, FEC_NONE, FEC_HAMMING128, 150),

@@ -341,6 +341,45 @@ def test_stagewise_and_sharded_world1_equal_monolithic():
     assert_frames_equal(fo, po, fg, pg)
 
 
+def test_frame_without_payload_symbols_on_every_synchroniser():
+    """payload_len 0 with check NONE and no FEC: a legal header announcing ZERO payload symbols (the frame generator of
+    this library emits it; liquid's synchroniser would wait for ever).  Every synchroniser kernel -- frame-parallel,
+    serial-chain, generic -- must complete the frame with the first OFDM symbol after the header, not hang, and carry on
+    with the next frame."""
+    from b2 import pkg
+    LIQUID_CRC_NONE, LIQUID_CRC_32 = 1, 6
+    for M, cp, taper in ((512, 64, 16), (64, 16, 4)):
+        gen = pkg.OfdmGen(M, cp, taper)
+        parts = [np.zeros(700, np.complex64)]
+        for k, (plen, check) in enumerate(((0, LIQUID_CRC_NONE), (40, LIQUID_CRC_32), (0, LIQUID_CRC_NONE))):
+            hdr = np.arange(8, dtype=np.uint8) + k
+            nsym = gen.assemble(hdr, np.arange(plen, dtype=np.uint8), check, FEC_NONE, FEC_NONE, MOD_QPSK)
+            x, last = gen.write(nsym + 2)
+            parts += [x * 0.5, np.zeros(3 * (M + cp) + 17 * k, np.complex64)]
+        gen.close()
+        x = np.concatenate(parts)
+        results = []
+        for env in ({}, {"B2_SYNC_LEGACY": "1"}, {"B2_SYNC_GENERIC": "1"}):
+            os.environ.update(env)
+            try:
+                rx = pkg.OfdmSync(M, cp, taper, streams=1)
+                for c in (x[:len(x) // 3], x[len(x) // 3:]):
+                    rx.execute(c)
+                fr, pl = rx.poll()
+                rx.close()
+            finally:
+                for k_ in env:
+                    os.environ.pop(k_, None)
+            assert len(fr) == 3, (M, env, len(fr))
+            assert list(fr["header_valid"]) == [1, 1, 1] and list(fr["payload_len"]) == [0, 40, 0]
+            assert int(fr["payload_valid"][1]) == 1 and np.array_equal(pl[:40], np.arange(40, dtype=np.uint8))
+            assert [int(h[0]) for h in fr["header"]] == [0, 1, 2]
+            results.append(fr)
+        for other in results[1:]:
+            for name in ("detect_index", "complete_index", "payload_len", "header"):
+                assert np.array_equal(results[0][name], other[name]), (M, name)
+
+
 def sharded_chunks(x, K, tc, steps, rank, world, halo):
     """device tensors [halo | chunk] of the chunks rank, rank + world, ... of stream x (zeros before the stream)"""
     import torch
