@@ -184,6 +184,9 @@ int b2_mctx_create(unsigned int num_channels, unsigned int M, unsigned int cp_le
                    const unsigned char * p, int device, b2_mctx ** out);
 int b2_mctx_destroy(b2_mctx * q);
 int b2_mctx_reset(b2_mctx * q);
+/* move the NCO by n_samples output samples (negative: back).  multichanneltx::Reset leaves the NCO alone
+ * (lib/multichanneltx.cc:135): a caller that generated ahead and throws samples away at a reset takes them back here. */
+int b2_mctx_nco_advance(b2_mctx * q, int64_t n_samples);
 int b2_mctx_is_ready(b2_mctx * q, unsigned int channel, int * ready);
 int b2_mctx_update(b2_mctx * q, unsigned int channel, const unsigned char * header,
                    const unsigned char * payload, unsigned int payload_len, int mod, int fec0, int fec1);

@@ -62,6 +62,7 @@ _PROTOS = {
     "b2_mctx_create": (C.c_int, [C.c_uint, C.c_uint, C.c_uint, C.c_uint, _vp, C.c_int, C.POINTER(_vp)]),
     "b2_mctx_destroy": (C.c_int, [_vp]),
     "b2_mctx_reset": (C.c_int, [_vp]),
+    "b2_mctx_nco_advance": (C.c_int, [_vp, C.c_int64]),
     "b2_mctx_is_ready": (C.c_int, [_vp, C.c_uint, C.POINTER(C.c_int)]),
     "b2_mctx_update": (C.c_int, [_vp, C.c_uint, _vp, _vp, C.c_uint, C.c_int, C.c_int, C.c_int]),
     "b2_mctx_generate": (C.c_int, [_vp, _vp, _sz]),

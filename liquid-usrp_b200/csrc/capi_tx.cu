@@ -302,6 +302,13 @@ extern "C" int b2_mctx_reset(b2_mctx * q)
     return B2_OK;
 }
 
+extern "C" int b2_mctx_nco_advance(b2_mctx * q, int64_t n_samples)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    q->nco_theta += (uint32_t)((uint64_t)n_samples) * q->nco_dtheta;       // uint32 phase: exact, wraps
+    return B2_OK;
+}
+
 extern "C" int b2_mctx_is_ready(b2_mctx * q, unsigned int channel, int * ready)
 {
     if (!q || !ready) return b2_fail(B2_ERR_ARG, "null argument");

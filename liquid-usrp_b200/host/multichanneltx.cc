@@ -41,8 +41,12 @@ multichanneltx::~multichanneltx() { b2_mctx_destroy(tx); }
 
 void multichanneltx::Reset()
 {
+    // samples generated ahead of the caller are dropped: the NCO, which a reset leaves alone (lib/multichanneltx.cc:135),
+    // goes back to the phase of the last sample actually handed out
+    const long long ahead = (long long)fifo.size() - (long long)fifo_pos;
     fifo.clear();
     fifo_pos = 0;
+    if (ahead > 0) b2_mctx_nco_advance(tx, -ahead);
     if (b2_mctx_reset(tx) != B2_OK) {
         fprintf(stderr, "error: multichanneltx::Reset(), %s\n", b2_last_error());
         throw 0;

@@ -91,6 +91,9 @@ class McTx:
     def __del__(self):
         self.close()
 
+    def reset(self):
+        self.L.mcshim_tx_reset(self.h)
+
     def is_ready(self, c):
         return self.L.mcshim_tx_is_ready(self.h, c)
 
