@@ -50,11 +50,15 @@ WORKLOAD_64 = dict(name="multichannelrx N=64 M=256 cp=32 taper=8 qam16 fec0=conv
                    N=64, M=256, cp=32, taper=8, payload=1200, mod="qam16", bps=4, fec0="v27", nd=178)
 B_ALG_PATH = 16.10          # 8 B in + 4 B channelizer out + 4 B sync in + 0.10 B payload, per wideband sample
 B_ALG = {"analyzer_kernel": 12.0, "sync_kernel": 4.10, "packet_decode_kernel": 0.20}
-# DRAM traffic measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one --set full capture per kernel,
-# profiles/r01_{analyzer8,sync8,decode}_pipelined.txt: a 33,554,432-sample chunk of this workload), as bytes per wideband
-# sample; bench reports it per launch of the average chunk of the step, like `achieved`
-TRAFFIC_PER_SAMPLE = {"analyzer_kernel": (272.111360e6 + 109.252096e6) / 33554432, "sync_kernel": (137.936896e6 + 9.240832e6) / 33554432,
-                      "packet_decode_kernel": 4.816384e6 / 33554432}
+# DRAM traffic per wideband sample measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one --set full capture
+# per kernel): read from the summary tools/ncu_traffic.py writes next to the captures it was computed from, so that it
+# cannot go stale silently -- no file, no claim (traffic: null)
+def traffic_per_sample():
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return {k: float(v["dram_bytes_per_sample"]) for k, v in json.load(f)["kernels"].items()}
+    except Exception:
+        return {}
 
 
 def peaks():
@@ -242,6 +246,78 @@ def measure_config64(args, local_rank, pkg, barrier):
     return {"workload": w["name"], "value": n_step * steps / dt / 1e6, "unit": "Msamples/s", "ms_per_step": 1e3 * dt / steps,
             "samples_per_step": n_step, "steps": steps,
             "kernels_ms_per_step": {"analyzer_kernel": kt[0], "sync_kernel": kt[1], "packet_decode_kernel": kt[2], "call": kt[3]}}
+
+
+def measure_tx(args, local_rank, pkg, barrier, cpu=True):
+    """the transmit mirror (multichanneltx, lib/multichanneltx.cc:165-242) at the headline shape: every channel re-armed
+    at each frame boundary through b2_mctx_update_many, samples left in device memory.  Extra leg, reported under "tx"."""
+    import torch
+    import refmc
+    w = WORKLOAD
+    N, M, cp, taper = w["N"], w["M"], w["cp"], w["taper"]
+    K, W = 2 * N, M + cp
+    nsym = 3 + -(-288 // w["nd"]) + -(-(-(-8 * (w["payload"] + 4) // w["bps"])) // w["nd"]) + 1
+    calls = nsym * W                                   # GenerateSamples calls (blocks of 2N samples) per frame period
+    tx = pkg.MultichannelTx(N, M, cp, taper, device=local_rank)
+    rng = np.random.default_rng(7)
+    payloads = rng.integers(0, 256, (N, w["payload"]), dtype=np.uint8)
+    headers = rng.integers(0, 256, (N, 8), dtype=np.uint8)
+    chans = np.arange(N, dtype=np.uint32)
+    out = torch.empty(calls * K * 2, dtype=torch.float32, device="cuda")
+    frames = max(8, args.steps)
+    kt = np.zeros(4)
+    for f in range(3 + frames):
+        if f == 3:
+            barrier()
+            t0 = time.perf_counter()
+            kt[:] = 0
+        took = tx.update_many(chans, headers, payloads, refmc.MOD_QAM64, refmc.FEC_NONE, refmc.FEC_NONE)
+        assert took == N, took
+        tx.generate_device(out.data_ptr(), calls)
+        kt += np.array(tx.last_timing())
+    barrier()
+    dt = time.perf_counter() - t0
+    tx.close()
+    # what was generated is a frame per channel: the receiver under test decodes them
+    rx = pkg.MultichannelRx(N, M, cp, taper, device=local_rank, max_batch=calls * K)
+    x = out.view(-1, 2)
+    rx.execute_device((x * (1.0 / N)).contiguous().data_ptr(), calls * K)
+    rx.execute_device(torch.zeros(4 * W * K * 2, dtype=torch.float32, device="cuda").data_ptr(), 4 * W * K)
+    recs, pl = rx.poll()
+    rx.close()
+    assert len(recs) == N and int(recs["payload_valid"].min()) == 1, (len(recs),)
+    c = int(recs["channel"][5]); o = int(recs["payload_offset"][5])
+    assert np.array_equal(pl[o:o + w["payload"]], payloads[c])
+    n = frames * calls * K
+    kern_ms = float(kt[:3].sum()) / frames
+    peak, _src = peaks()
+    res = {"workload": "multichanneltx N=%d M=%d cp=%d qam64 payload=%dB, every channel re-armed at each frame boundary, samples left on the device" % (N, M, cp, w["payload"]),
+           "value": n / dt / 1e6, "unit": "Msamples/s", "ms_per_frame_period": 1e3 * dt / frames, "samples_per_frame_period": calls * K,
+           "kernels_ms_per_frame_period": kern_ms,
+           "roofline": {"bound": "hbm", "alg_bytes_per_sample": 16.0, "achieved": calls * K * 16.0 / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None,
+                        "peak": peak, "unit": "GB/s", "frac": (calls * K * 16.0 / (kern_ms * 1e-3) / 1e9 / peak) if kern_ms > 0 else None,
+                        "note": "kernels only (packet encode + frame generator + synthesis bank / NCO); SURVEY.md 8d: 16 B per wideband output sample"}}
+    if cpu:
+        # the reference's lib/multichanneltx.cc over the oracle, one transmitter per host core, ~5 s
+        cores = cpu_cores()
+        L = refmc.ref_lib()
+        counts = [0] * cores
+
+        def work(i, until):
+            t = refmc.McTx(L, N, M, cp, taper)
+            while time.perf_counter() < until:
+                t.run(W * 4, w["payload"], refmc.MOD_QAM64, refmc.FEC_NONE, refmc.FEC_NONE, seed=0xB2000000 + i, gain=1.0 / N)
+                counts[i] += W * 4 * K
+            t.close()
+        tc0 = time.perf_counter()
+        ths = [threading.Thread(target=work, args=(i, tc0 + 5.0)) for i in range(cores)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        res["cpu_baseline"] = {"value": sum(counts) / (time.perf_counter() - tc0) / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+                               "sample": "~5 s of the reference's lib/multichanneltx.cc (unmodified) over the oracle, one transmitter per host core"}
+    return res
 
 
 METRIC = "complex Msamples/s through multichannelrx (64ch OFDM) at 1/2/4/8 GPU vs CPU"
@@ -466,7 +542,8 @@ def run_single(args, rank, local_rank, world, period, expected, flen, extras=Tru
     def roof(i):
         ach = n_step * B_ALG[names[i]] / (kt_avg[i] * 1e-3) / 1e9
         return {"alg_bytes_per_sample": B_ALG[names[i]], "launches_per_step": nchunks, "avg_launch_ms": kt_avg[i] / nchunks,
-                "achieved": ach, "frac": ach / peak, "traffic": TRAFFIC_PER_SAMPLE[names[i]] * n_step / nchunks}
+                "achieved": ach, "frac": ach / peak, "traffic": (traffic[names[i]] * n_step / nchunks) if names[i] in traffic else None}
+    traffic = traffic_per_sample()
     per_kernel = {names[i]: roof(i) for i in range(3)}
     achieved = per_kernel[names[dom]]["achieved"]
     line = {"metric": METRIC, "value": total / dt / 1e6, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -485,13 +562,31 @@ def run_single(args, rank, local_rank, world, period, expected, flen, extras=Tru
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": per_kernel[names[dom]]["traffic"], "peak_source": peak_src,
                          "alg_bytes_per_sample": B_ALG[names[dom]],
-                         "note": "the dominant kernel is the per-channel synchroniser, 256 serial chains bound by event latency, not by HBM (DESIGN.md)",
+                         "note": "kernels of successive chunks share the SMs, so the per-kernel times are inflated by the overlap; 'path' is the whole call (DESIGN.md 6)",
                          "kernels": per_kernel,
                          "path": {"alg_bytes_per_sample": B_ALG_PATH, "achieved": n_step * B_ALG_PATH / (kt_avg[3] * 1e-3) / 1e9,
                                   "frac": n_step * B_ALG_PATH / (kt_avg[3] * 1e-3) / 1e9 / peak}},
             "clocks": clk.summary()}
+    if extras and args.seconds > 0:
+        clk2 = Clocks(local_rank)
+        clk2.start()
+        barrier()
+        ts = time.perf_counter()
+        k = 0
+        while time.perf_counter() - ts < args.seconds:
+            rx.execute_device(d_x.data_ptr(), n_step)
+            rx.poll_view()
+            k += 1
+        barrier()
+        dts = time.perf_counter() - ts
+        clk2.stop_flag = True
+        clk2.join()
+        line["sustained"] = {"seconds": dts, "steps": k, "value": n_step * k / dts / 1e6, "unit": "Msamples/s", "clocks": clk2.summary(),
+                             "note": "the same device-resident step back to back for >= --seconds"}
     if extras and not args.no_config64 and world == 1:
         line["config64"] = measure_config64(args, local_rank, pkg, barrier)
+    if extras and not args.no_tx and world == 1:
+        line["tx"] = measure_tx(args, local_rank, pkg, barrier, cpu=not args.no_cpu)
     if args.receivers > 1:
         rxs = [rx] + [pkg.MultichannelRx(w["N"], w["M"], w["cp"], w["taper"], device=local_rank, max_batch=n_step) for _ in range(args.receivers - 1)]
 
@@ -541,6 +636,8 @@ def main():
                     "GPUs (the headline; independent replicas are reported alongside), replicas = independent receivers only")
     ap.add_argument("--gather", default="shm", choices=["shm", "nccl"], help="N > 1: how the decoded frames reach rank 0's host memory: shm = every rank "
                     "over its own PCIe link into shared host memory, nccl = NCCL gather over NVLink to rank 0's GPU, then rank 0's PCIe link")
+    ap.add_argument("--no-tx", action="store_true", help="skip the extra transmit (multichanneltx) leg")
+    ap.add_argument("--seconds", type=float, default=2.0, help="extra leg: run the device-resident step back to back for this long and report the sustained rate and clocks under 'sustained'")
     ap.add_argument("--no-config64", action="store_true", help="skip the extra 64-channel (BASELINE configs[2]) leg")
     ap.add_argument("--receivers", type=int, default=1, help="extra leg: R independent receivers sharing this GPU (reported under "
                     "'multi_receiver', never as the headline): shows that one receiver is bound by its 256 serial chains")

@@ -190,6 +190,13 @@ int b2_mctx_nco_advance(b2_mctx * q, int64_t n_samples);
 int b2_mctx_is_ready(b2_mctx * q, unsigned int channel, int * ready);
 int b2_mctx_update(b2_mctx * q, unsigned int channel, const unsigned char * header,
                    const unsigned char * payload, unsigned int payload_len, int mod, int fec0, int fec1);
+/* multichanneltx::UpdateData (lib/multichanneltx.cc:165-189) for n channels in one call -- what the loop of
+ * src/multichannel_tx.cc:166-185 does at a frame boundary: headers is n x 8 bytes, payloads the n payloads back to
+ * back (payload_lens[i] bytes each).  Channels that are not ready are skipped like UpdateData skips them; *n_updated
+ * (nullable) counts the ones taken. */
+int b2_mctx_update_many(b2_mctx * q, unsigned int n, const unsigned int * channels, const unsigned char * headers,
+                        const unsigned char * payloads, const unsigned int * payload_lens, int mod, int fec0, int fec1,
+                        unsigned int * n_updated);
 /* produce the next n_calls * 2N wideband samples (n_calls consecutive GenerateSamples calls with
  * no UpdateData in between) into host memory */
 int b2_mctx_generate(b2_mctx * q, float * out_host, size_t n_calls);

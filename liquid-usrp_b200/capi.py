@@ -65,6 +65,7 @@ _PROTOS = {
     "b2_mctx_nco_advance": (C.c_int, [_vp, C.c_int64]),
     "b2_mctx_is_ready": (C.c_int, [_vp, C.c_uint, C.POINTER(C.c_int)]),
     "b2_mctx_update": (C.c_int, [_vp, C.c_uint, _vp, _vp, C.c_uint, C.c_int, C.c_int, C.c_int]),
+    "b2_mctx_update_many": (C.c_int, [_vp, C.c_uint, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint)]),
     "b2_mctx_generate": (C.c_int, [_vp, _vp, _sz]),
     "b2_mctx_generate_device": (C.c_int, [_vp, _vp, _sz]),
     "b2_mctx_calls_to_boundary": (C.c_int, [_vp, C.POINTER(_sz)]),
@@ -296,6 +297,22 @@ class MultichannelTx(_Handle):
         header = np.ascontiguousarray(header, np.uint8)
         payload = np.ascontiguousarray(payload, np.uint8)
         _check(lib().b2_mctx_update(self.h, channel, header.ctypes.data, payload.ctypes.data, len(payload), mod, fec0, fec1))
+
+    def update_many(self, channels, headers, payloads, mod, fec0, fec1):
+        """UpdateData for many channels in one call: headers [n, 8] uint8, payloads a list of uint8 arrays (or an [n, len]
+        array); channels that are not ready are skipped.  Returns the number of channels taken."""
+        channels = np.ascontiguousarray(channels, np.uint32)
+        headers = np.ascontiguousarray(headers, np.uint8).reshape(len(channels), 8)
+        if isinstance(payloads, np.ndarray) and payloads.ndim == 2:
+            lens = np.full(len(channels), payloads.shape[1], np.uint32)
+            flat = np.ascontiguousarray(payloads, np.uint8).reshape(-1)
+        else:
+            lens = np.array([len(p) for p in payloads], np.uint32)
+            flat = np.concatenate([np.asarray(p, np.uint8) for p in payloads]) if len(payloads) else np.zeros(0, np.uint8)
+        n = C.c_uint(0)
+        _check(lib().b2_mctx_update_many(self.h, len(channels), channels.ctypes.data, headers.ctypes.data,
+                                         flat.ctypes.data if len(flat) else None, lens.ctypes.data, mod, fec0, fec1, C.byref(n)))
+        return n.value
 
     def generate(self, n_calls):
         out = np.zeros(n_calls * 2 * self.N, np.complex64)

@@ -327,6 +327,30 @@ extern "C" int b2_mctx_update(b2_mctx * q, unsigned int channel, const unsigned 
     return q->bank.assemble(channel, header, payload, payload_len, CRC_32, fec0, fec1, mod, nullptr);   // CRC-32 always (:184)
 }
 
+extern "C" int b2_mctx_update_many(b2_mctx * q, unsigned int n, const unsigned int * channels, const unsigned char * headers,
+                                   const unsigned char * payloads, const unsigned int * payload_lens, int mod, int fec0, int fec1,
+                                   unsigned int * n_updated)
+{
+    if (!q) return b2_fail(B2_ERR_ARG, "null handle");
+    if (n_updated) *n_updated = 0;
+    if (n == 0) return B2_OK;
+    if (!channels || !headers || !payload_lens) return b2_fail(B2_ERR_ARG, "null argument");
+    B2_CUDA(cudaSetDevice(q->device));
+    size_t off = 0;
+    unsigned int taken = 0;
+    for (unsigned int i = 0; i < n; i++) {
+        const unsigned int c = channels[i], len = payload_lens[i];
+        if (c >= q->N) return b2_fail(B2_ERR_ARG, "invalid channel id %u", c);
+        if (!q->bank.ch[c].assembled) {
+            B2_TRY(q->bank.assemble(c, headers + 8 * (size_t)i, payloads ? payloads + off : nullptr, len, CRC_32, fec0, fec1, mod, nullptr));
+            taken++;
+        }
+        off += len;
+    }
+    if (n_updated) *n_updated = taken;
+    return B2_OK;
+}
+
 extern "C" int b2_mctx_calls_to_boundary(b2_mctx * q, size_t * n_calls)
 {
     if (!q || !n_calls) return b2_fail(B2_ERR_ARG, "null argument");
