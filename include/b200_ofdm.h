@@ -126,11 +126,13 @@ int b2_mcrx_sync_device(b2_mcrx * q, const float * in_dev, size_t n, size_t in_s
  *   stage 2  ofdmflexframesync + packet decode (lib/multichannelrx.cc:193-194), sharded over CHANNELS: the rank owns
  *            channels [rank N/world, (rank+1) N/world) for all time and runs them over `world` exchanged chunks per step
  * The caller (one per rank, e.g. liquid-usrp_b200/sharded.py over torch.distributed) provides the two CUDA streams
- * and the only cross-rank ordering the data path needs: after stage1(step) a barrier among the ranks on stream_stage1
- * (a one-word NCCL all-reduce), which stage2(step) must wait for; and stage1(step + B2_SHARD_SLOTS - 1) must not
- * start before every rank's stage2(step) is done (join that barrier only behind the own stage2(step - ...) event). */
+ * and the only cross-rank ordering the data path needs: a barrier among the ranks behind stage1(step) (a one-word
+ * NCCL all-reduce), which stage2(step) must wait for; and, the exchange buffer having B2_SHARD_SLOTS slots,
+ * stage1(step + B2_SHARD_SLOTS - 1) must not start before every rank's stage2(step) is done.  A rank that joins
+ * barrier(j) only behind its own stage2(j - B2_SHARD_SLOTS + 2) gets that from barrier(step + B2_SHARD_SLOTS - 2)
+ * -- one step of slack, so stage 1 never waits for the barrier of its own step. */
 typedef struct b2_mcrx_shard_s b2_mcrx_shard;
-#define B2_SHARD_SLOTS 3
+#define B2_SHARD_SLOTS 4
 #define B2_SHARD_HALO_BLOCKS 13     /* taps per branch - 1 of the receive bank (m = 7, lib/multichannelrx.cc:89) */
 /* steps_per_call: steps (of world chunks each) between _begin and _end, sizes the frame output */
 int b2_mcrx_shard_create(unsigned int num_channels, unsigned int M, unsigned int cp_len, unsigned int taper_len,

@@ -151,7 +151,7 @@ class ShardedRx:
     the stage-1 stream (everybody's stores of the step have landed / everybody is done with the slot that comes
     round next), torch.distributed gather of the frame records at the end of a call.
     """
-    SLOTS = 3
+    SLOTS = 4
     PACK_HEADER = 32
     import os as _os
     _dbg_nocopy = _os.environ.get("B2_DBG_NOCOPY") == "1"       # probe knob: packs leave the device without their body
@@ -186,6 +186,8 @@ class ShardedRx:
             dist.barrier(group=group)
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.step = 0                                  # steps since the stream began
+        self.s3 = torch.cuda.Stream(device=self.device)          # the per-step barrier (does not hold stage 1 up)
+        self.ev_stage1 = [torch.cuda.Event() for _ in range(steps_per_call)]
         self.ev_ready = [torch.cuda.Event() for _ in range(steps_per_call)]
         self.ev_done = [torch.cuda.Event() for _ in range(steps_per_call)]
 
@@ -200,27 +202,43 @@ class ShardedRx:
         capi._check(L.b2_mcrx_shard_begin(self.h))
         for i in range(self.steps):
             with torch.cuda.stream(self.s1):
+                if self.world > 1 and i >= 2:
+                    # slot (i % SLOTS) was read by stage 2 of step i - SLOTS: barrier(i - 2), which every rank joined
+                    # behind its own stage 2 of step i - SLOTS, has completed
+                    self.s1.wait_event(self.ev_ready[i - 2])
                 capi._check(L.b2_mcrx_shard_stage1(self.h, C.c_void_p(int(chunk_ptrs[i])), self.step))
-                if self.world > 1:
-                    # the slot that step + 1 will write must have been read by everybody: join the barrier only
-                    # behind the own stage 2 of the step that used it
-                    if i >= self.SLOTS - 1:
-                        self.s1.wait_event(self.ev_done[i - (self.SLOTS - 1)])
-                    dist.all_reduce(self.flag, group=self.group)
-                self.ev_ready[i].record(self.s1)
+                self.ev_stage1[i].record(self.s1)
+            self._barrier(i)
             with torch.cuda.stream(self.s2):
                 self.s2.wait_event(self.ev_ready[i])
                 capi._check(L.b2_mcrx_shard_stage2(self.h, self.step))
                 self.ev_done[i].record(self.s2)
             self.step += 1
         capi._check(L.b2_mcrx_shard_end(self.h))       # host waits for stage 2 of every step
-        # the next call's first stage 1 may overwrite a slot only after the slowest rank's stage 2
+        self._end_of_call(cur)
+
+    def _end_of_call(self, cur):
+        # the next call's first stage 1 may overwrite a slot only after the slowest rank's last stage 2
         if self.world > 1:
-            with torch.cuda.stream(self.s1):
-                self.s1.wait_event(self.ev_done[self.steps - 1])
+            with torch.cuda.stream(self.s3):
+                self.s3.wait_event(self.ev_done[self.steps - 1])
                 dist.all_reduce(self.flag, group=self.group)
+            self.s1.wait_stream(self.s3)
         cur.wait_stream(self.s1)
         cur.wait_stream(self.s2)
+        cur.wait_stream(self.s3)
+
+    def _barrier(self, i):
+        """barrier(i) on its own stream: everybody's stage 1 of step i has landed (joined behind the own stage 1), and --
+        joined behind the own stage 2 of step i - SLOTS + 2 -- everybody is done with the slot that step i + 2 overwrites"""
+        with torch.cuda.stream(self.s3):
+            self.s3.wait_event(self.ev_stage1[i])
+            if self.world > 1:
+                j = i - (self.SLOTS - 2)
+                if j >= 0:
+                    self.s3.wait_event(self.ev_done[j])
+                dist.all_reduce(self.flag, group=self.group)
+            self.ev_ready[i].record(self.s3)
 
     def execute_host(self, host_chunks):
         """the same call fed from PINNED HOST memory: host_chunks[i] is a pinned uint8/float32/complex64 tensor holding
@@ -247,25 +265,20 @@ class ShardedRx:
                 self._hev_copied[b].record(self._hcopy)
             with torch.cuda.stream(self.s1):
                 self.s1.wait_event(self._hev_copied[b])
+                if self.world > 1 and i >= 2:
+                    self.s1.wait_event(self.ev_ready[i - 2])
                 capi._check(L.b2_mcrx_shard_stage1(self.h, C.c_void_p(self._hbuf[b].data_ptr()), self.step))
                 self._hev_used[b].record(self.s1)
                 self._hused[b] = True
-                if self.world > 1:
-                    if i >= self.SLOTS - 1:
-                        self.s1.wait_event(self.ev_done[i - (self.SLOTS - 1)])
-                    dist.all_reduce(self.flag, group=self.group)
-                self.ev_ready[i].record(self.s1)
+                self.ev_stage1[i].record(self.s1)
+            self._barrier(i)
             with torch.cuda.stream(self.s2):
                 self.s2.wait_event(self.ev_ready[i])
                 capi._check(L.b2_mcrx_shard_stage2(self.h, self.step))
                 self.ev_done[i].record(self.s2)
             self.step += 1
         capi._check(L.b2_mcrx_shard_end(self.h))
-        if self.world > 1:
-            with torch.cuda.stream(self.s1):
-                self.s1.wait_event(self.ev_done[self.steps - 1])
-                dist.all_reduce(self.flag, group=self.group)
-        cur.wait_stream(self.s1); cur.wait_stream(self.s2)
+        self._end_of_call(cur)
 
     def poll(self):
         C, capi = self.C, self.capi
