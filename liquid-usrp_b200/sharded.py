@@ -140,6 +140,34 @@ class ShardedMultichannelRx:
         self.sync.close()
 
 
+PACK_HEADER = 32           # B2_SHARD_PACK_HEADER: uint64 n_recs, n_payload_bytes, tag, 0
+
+
+def chunk_of(step, rank, world):
+    """absolute index of the stream chunk rank `rank` channelizes in step `step` (chunks are dealt round-robin)"""
+    return step * world + rank
+
+
+def parse_pack(row, frame_dtype):
+    """one rank's pack [n_recs, n_payload_bytes, tag, 0 | records | payload bytes] (uint8 array) -> (records, payloads, tag)"""
+    nr, nb, tag = (int(v) for v in row[:24].view(np.uint64))
+    isz = frame_dtype.itemsize
+    return row[PACK_HEADER:PACK_HEADER + nr * isz].view(frame_dtype), row[PACK_HEADER + nr * isz:PACK_HEADER + nr * isz + nb], tag
+
+
+def step_dependencies(steps, slots):
+    """the stream-ordering rules of one call as data, for every step i: what stage 1, the barrier and stage 2 of the step
+    wait for (beyond the order of their own streams).  ShardedRx.execute_* issue exactly these waits; the CPU test
+    replays them against random kernel durations and checks that no exchange slot is overwritten before every rank has
+    read it, and that nobody reads a slot before every rank has written it."""
+    deps = []
+    for i in range(steps):
+        deps.append({"stage1": [("barrier", i - 2)] if i >= 2 else [],
+                     "barrier": [("stage1", i)] + ([("stage2", i - (slots - 2))] if i - (slots - 2) >= 0 else []),
+                     "stage2": [("barrier", i)]})
+    return deps
+
+
 class ShardedRx:
     """one rank of a multichannelrx spread over `world` GPUs (one process each).
 
@@ -424,12 +452,7 @@ class ShardedRx:
             g["ev"][k].synchronize()
             host = g["host"][k].numpy()
             rows = [host[r] for r in range(self.world)]
-        out = []
-        isz, H = self.capi.FRAME_DTYPE.itemsize, self.PACK_HEADER
-        for row in rows:
-            nr, nb = (int(v) for v in row[:16].view(np.uint64))
-            out.append((row[H:H + nr * isz].view(self.capi.FRAME_DTYPE), row[H + nr * isz:H + nr * isz + nb]))
-        return out
+        return [parse_pack(row, self.capi.FRAME_DTYPE)[:2] for row in rows]
 
     def reset(self):
         self.capi._check(self.L.b2_mcrx_shard_reset(self.h))
