@@ -279,6 +279,7 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     decode_grid = sms * 2;
     vit_ctas = (unsigned int)sms * 12;
     B2_TRY(d_vit.alloc(sizeof(uint2) * (size_t)vit_ctas * vit_steps));
+    if (packet_decode_prepare() != cudaSuccess) return b2_fail(B2_ERR_NOMEM, "could not allocate the Viterbi workspace: %s", cudaGetErrorString(cudaGetLastError()));
     return reset_state();
 }
 

@@ -240,6 +240,8 @@ struct PacketParams {
     unsigned int vit_local_ctas;
 };
 cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t st);
+// device-wide Viterbi workspace of the calling thread's device (once; called when a handle is created)
+cudaError_t packet_decode_prepare();
 // mark_out = {counters[0], counters[2..3]} (records / arena bytes so far), one thread; runs between
 // the synchroniser of a chunk and its decode so that chunk c decodes records [mark[c], mark[c+1])
 // records of a batch in callback order (completion index, then channel): device sort + permuting copy into dst

@@ -789,6 +789,29 @@ struct VitWorkspace { uint2 * ws = nullptr; int * locks = nullptr; size_t stride
 static VitWorkspace g_vit[16];
 static std::mutex g_vit_mutex;
 
+// Viterbi decision workspace for frames whose trellis does not fit a CTA's own region (> 2 KB conv-coded payloads):
+// 8 bytes per trellis step per slot, sized for the largest packet (also covers v27 as outer code over an inner code),
+// 16 slots shared by the handles of a device (a CTA claims one for the duration of a frame).  Allocated when the first
+// handle of the device is created -- not on the data path.
+cudaError_t packet_decode_prepare()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) dev = 0;
+    std::lock_guard<std::mutex> guard(g_vit_mutex);
+    VitWorkspace & g = g_vit[dev];
+    if (g.ws) return cudaSuccess;
+    const size_t steps = 8ull * (65535 + 4 + 2) * 2 + 64;
+    const unsigned int slots = 16;
+    cudaError_t e = cudaMalloc(&g.ws, (size_t)slots * steps * sizeof(uint2));
+    if (e != cudaSuccess) { g.ws = nullptr; return e; }
+    e = cudaMalloc(&g.locks, slots * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(g.locks, 0, slots * sizeof(int));
+    if (e != cudaSuccess) { cudaFree(g.ws); g.ws = nullptr; return e; }
+    g.stride = steps; g.slots = slots;
+    return cudaSuccess;
+}
+
 cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t st)
 {
     int dev = 0;
@@ -796,13 +819,13 @@ cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t 
     if (dev < 0 || dev >= 16) dev = 0;
     VitWorkspace w;
     {
+        cudaError_t pe = packet_decode_prepare();        // (a no-op after the handle's creation)
+        if (pe != cudaSuccess) return pe;
         std::lock_guard<std::mutex> guard(g_vit_mutex);
         VitWorkspace & g = g_vit[dev];
         if (!g.ws) {
-            // Viterbi decision workspace: 8 bytes per trellis step per slot, sized for the largest packet
-            // (also covers v27 as outer code over an inner code); allocated once per device, never moved
             const size_t steps = 8ull * (65535 + 4 + 2) * 2 + 64;
-            const unsigned int slots = 128;
+            const unsigned int slots = 16;
             cudaError_t e = cudaMalloc(&g.ws, (size_t)slots * steps * sizeof(uint2));
             if (e != cudaSuccess) { g.ws = nullptr; return e; }
             e = cudaMalloc(&g.locks, slots * sizeof(int));
