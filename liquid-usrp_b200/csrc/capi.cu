@@ -44,7 +44,7 @@ struct SyncCore {
     unsigned long long stream_pos = 0;   // samples per stream given to the synchroniser so far
     size_t penc_cap = 0;
     // outputs
-    DevBuf d_recs, d_aux, d_arena, d_scratch, d_decoded, d_counters, d_vit;
+    DevBuf d_recs, d_aux, d_arena, d_scratch, d_decoded, d_counters, d_vit, d_crc;
     unsigned int vit_ctas = 0, vit_steps = 16384;     // per-CTA Viterbi decision regions of the general decode kernel
     unsigned int recs_cap = 0;
     unsigned long long arena_cap = 0;
@@ -222,6 +222,8 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     B2_TRY(d_recs.alloc(sizeof(FrameRec) * recs_cap)); B2_TRY(d_aux.alloc(sizeof(FrameAux) * recs_cap));
     B2_TRY(d_arena.alloc(arena_cap)); B2_TRY(d_scratch.alloc(arena_cap)); B2_TRY(d_decoded.alloc(out_cap));
     B2_TRY(d_counters.alloc(8 * sizeof(unsigned int)));
+    B2_TRY(d_crc.alloc(8 * sizeof(unsigned int)));
+    B2_CUDA(cudaMemset(d_crc.p, 0, 8 * sizeof(unsigned int)));
     B2_CUDA(cudaMallocHost(&h_counters, 8 * sizeof(unsigned int)));
     B2_CUDA(cudaMallocHost(&h_recs, sizeof(FrameRec) * recs_cap));
     B2_CUDA(cudaMallocHost(&h_payload, out_cap));
@@ -447,6 +449,7 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
     // every decode stream has its own share of the Viterbi regions (launches on different streams overlap)
     pp.vit_local_ctas = vit_ctas / NDS; pp.vit_local_steps = vit_steps;
     pp.vit_local = d_vit.as<uint2>() + (size_t)(chunk % NDS) * pp.vit_local_ctas * vit_steps;
+    pp.crc_cache = d_crc.as<unsigned int>();
     if (timing) B2_CUDA(cudaEventRecord(e.d0, ds));
     B2_CUDA(packet_decode_launch(pp, decode_grid, ds));
     B2_CUDA(cudaEventRecord(e.d1, ds));

@@ -238,6 +238,7 @@ struct PacketParams {
     uint2 * vit_local;               // Viterbi decisions: vit_local_ctas regions of vit_local_steps trellis steps,
     unsigned int vit_local_steps;    // one per CTA of the general decode kernel (null: device-wide slots only)
     unsigned int vit_local_ctas;
+    unsigned int * crc_cache;        // [8] device words: [0] = 1 + per of the cached constants (0: empty), [1..5] = x^(8 per 2^l) mod P
 };
 cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t st);
 // device-wide Viterbi workspace of the calling thread's device (once; called when a handle is created)

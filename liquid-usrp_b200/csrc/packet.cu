@@ -653,11 +653,18 @@ __global__ void __launch_bounds__(PKF_WARPS * 32) packet_plain_kernel(const Pack
         unsigned int per0 = 0;
         const unsigned int r0 = p.range[0].nrec;
         if (r0 < nrec) per0 = p.recs[r0].payload_len / 32;
-        uint32_t xp = crc_x8n(per0);
+        // ... and kept in device memory from one launch to the next (every CTA that misses computes the same words)
+        const bool hit = p.crc_cache && __ldcg(p.crc_cache) == per0 + 1u;
+        if (hit) {
+            if (lane < 5) xps[lane] = __ldcg(p.crc_cache + 1 + lane);
+        } else {
+            uint32_t xp = crc_x8n(per0);
 #pragma unroll
-        for (int l = 0; l < 5; l++) {
-            if (lane == 0) xps[l] = xp;
-            xp = crc_multmodp(xp, xp);
+            for (int l = 0; l < 5; l++) {
+                if (lane == 0) { xps[l] = xp; if (p.crc_cache) p.crc_cache[1 + l] = xp; }
+                xp = crc_multmodp(xp, xp);
+            }
+            if (lane == 0 && p.crc_cache) { __threadfence(); p.crc_cache[0] = per0 + 1u; }
         }
         if (lane == 0) xps_per = per0;
     }

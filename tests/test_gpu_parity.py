@@ -544,10 +544,11 @@ def test_two_devices_in_one_process():
 
 
 def test_worker_pairs_under_corruption():
-    """frame-pipelined worker pairs of the register-resident synchroniser (two CTAs per channel on alternate
-    frames): long runs of back-to-back frames with OFDM symbols wiped at random places -- lost preambles, invalid
-    headers (the speculative worker has to return its hand-off), failed CRCs -- plus noise, fed in ragged calls.
-    Records must equal the oracle's, and the serial (one worker) configuration's."""
+    """speculative workers of the synchronisers (frame-parallel kernel: workers starting at predicted frame boundaries;
+    serial-chain kernel: worker pairs on alternate frames): long runs of back-to-back frames with OFDM symbols wiped at
+    random places -- lost preambles, invalid headers, failed CRCs, i.e. predictions that do not hold and stretches the
+    stitcher has to redo serially -- plus noise, fed in ragged calls.  Records must equal the oracle's in every
+    configuration."""
     from b2 import pkg
     rng = np.random.default_rng(21)
     for case in ((8, 256, 32, 8, MOD_QPSK, FEC_NONE, FEC_HAMMING128, 150, 9, 0.02),
@@ -572,12 +573,15 @@ def test_worker_pairs_under_corruption():
             c = int(min(left, rng.integers(1, 40000)))
             chunks.append(c)
             left -= c
-        for workers in ("2", "1"):
-            os.environ["B2_SYNC_WORKERS"] = workers
+        # frame-parallel kernel with its default number of workers per channel, with 3, and serial (1); then the
+        # serial-chain kernel of round 1 with and without its worker pairs
+        for env in ({}, {"B2_SYNC_K": "3"}, {"B2_SYNC_K": "1"}, {"B2_SYNC_LEGACY": "1", "B2_SYNC_WORKERS": "2"}, {"B2_SYNC_LEGACY": "1", "B2_SYNC_WORKERS": "1"}):
+            os.environ.update(env)
             try:
                 fg, pg, _ = run_gpu(case, x)
                 assert_frames_equal(fo, po, fg, pg)
                 fg, pg, _ = run_gpu(case, x, chunks)
                 assert_frames_equal(fo, po, fg, pg)
             finally:
-                os.environ.pop("B2_SYNC_WORKERS", None)
+                for k_ in env:
+                    os.environ.pop(k_, None)
