@@ -696,11 +696,18 @@ extern "C" int b2_mcrx_create(unsigned int N, unsigned int M, unsigned int cp, u
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         if (q->part.ok) sms = (int)q->part.big_sms;
+        if (const char * e = getenv("B2_AN_SMS")) { long v = atol(e); if (v >= 8 && v < sms) sms = (int)v; }
         int per_sm = std::max(1, (int)((227 * 1024) / (q->an_smem + 1024)));
         q->an_grid = sms * std::min(per_sm, 2);
         q->an_sms = (unsigned int)sms;
+        // (experiment knob B2_SYNC_PRIORITY=1: the synchroniser launches, which depend on each other through the carried
+        // state, on a high-priority stream -- measured: no gain, the long-lived channelizer CTAs hold their SMs anyway)
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        const bool prio = getenv("B2_SYNC_PRIORITY") != nullptr && atoi(getenv("B2_SYNC_PRIORITY")) != 0;
         if (cudaStreamCreateWithFlags(&q->cstream, cudaStreamNonBlocking) != cudaSuccess ||
-            (!q->sstream && cudaStreamCreateWithFlags(&q->sstream, cudaStreamNonBlocking) != cudaSuccess) ||
+            (!q->sstream && (prio ? cudaStreamCreateWithPriority(&q->sstream, cudaStreamNonBlocking, prio_hi)
+                                  : cudaStreamCreateWithFlags(&q->sstream, cudaStreamNonBlocking)) != cudaSuccess) ||
             cudaEventCreate(&q->ev_begin) != cudaSuccess || cudaEventCreate(&q->ev_end) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaStreamCreate failed"); break; }
         // chunk of the pipeline: long enough to amortise launches, short enough to overlap stages
         q->chunk_blocks = std::max(64u, (1u << 25) / K);
