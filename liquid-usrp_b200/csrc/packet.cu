@@ -178,8 +178,8 @@ __device__ void golay2412_decode_block(const uint8_t * enc, uint8_t * dec, unsig
 // bit, so a step costs ONE shuffle (the lanes swap the slot they do not work on) and the new pair stays
 // in the lane that computed it.  The traceback walks in the same rotated domain (see below).
 
-__device__ void viterbi27_decode(const uint8_t * enc, uint8_t * dec, unsigned int n, uint2 * decisions,
-                                 uint2 * stage, unsigned int tid, bool in_smem)
+// add-compare-select recursion of the whole frame by warp 0: decisions[t] = the 64 survivor choices of step t
+__device__ void viterbi27_acs(const uint8_t * enc, unsigned int n, uint2 * decisions, unsigned int tid)
 {
     const unsigned int nbits = 8 * n + 6;
     if (tid < 32) {
@@ -244,6 +244,12 @@ __device__ void viterbi27_decode(const uint8_t * enc, uint8_t * dec, unsigned in
                 if (t0 + tm < nbits) step(tm, t0 + tm);
         }
     }
+}
+
+// exact traceback from the terminated end state (one thread: the chain is dependent from step to step)
+__device__ void viterbi27_traceback(uint8_t * dec, unsigned int n, const uint2 * decisions, uint2 * stage, unsigned int tid, bool in_smem)
+{
+    const unsigned int nbits = 8 * n + 6;
     for (unsigned int i = tid; i < n; i += PK_THREADS) dec[i] = 0;
     __syncthreads();
     // traceback, in the rotated lane domain: the lane y of the current state stays in place from one step to
@@ -304,6 +310,152 @@ __device__ void viterbi27_decode(const uint8_t * enc, uint8_t * dec, unsigned in
     __syncthreads();
 }
 
+__device__ void viterbi27_decode(const uint8_t * enc, uint8_t * dec, unsigned int n, uint2 * decisions,
+                                 uint2 * stage, unsigned int tid, bool in_smem)
+{
+    viterbi27_acs(enc, n, decisions, tid);
+    viterbi27_traceback(dec, n, decisions, stage, tid, in_smem);
+}
+
+// ------------------------------------------------------------------ speculative traceback, one short walk per thread
+// The exact traceback is ONE thread following 8n + 6 dependent steps (a quarter of the decoder's instructions, at 1/32 of a
+// warp's width).  Survivor paths of a K = 7 code merge within a few constraint lengths, so `nth` threads each take a
+// byte-aligned slice of the steps [lo, keep_hi): thread th starts VIT_TB_OV steps above its slice from an arbitrary state
+// (state 0; the true end state where that point is the terminated end of the frame), walks down discarding bits until it
+// reaches its slice -- by then it is on the maximum-likelihood path with overwhelming probability -- and keeps the bits of
+// its slice.  SPECULATIVE like the segmented recursion below: the caller keeps the result only if the CRC-32 passes.
+// Decision of step t at dsrc[t - base] (global memory, read through L2: other threads of the CTA wrote them).
+constexpr unsigned int VIT_TB_OV = 128;
+__device__ void viterbi27_traceback_spec(const uint2 * dsrc, unsigned int base, unsigned int lo, unsigned int keep_hi, unsigned int hi,
+                                         uint8_t * dec, unsigned int wlimit, unsigned int th, unsigned int nth)
+{
+    const unsigned int sl = (((keep_hi - lo) + nth - 1u) / nth + 7u) & ~7u;
+    const unsigned int a = lo + th * sl;
+    if (a >= keep_hi) return;
+    const unsigned int b = min(keep_hi, a + sl);
+    const unsigned int S = min(hi, b + VIT_TB_OV);
+    unsigned int y = 0, slot = 0, pb = (5u - S % 5u) % 5u, acc = 0;
+    auto one = [&](const uint2 d) {
+        const unsigned int bit = ((slot ? d.y : d.x) >> y) & 1u;
+        const unsigned int old = (y >> pb) & 1u;
+        y = (y & ~(1u << pb)) | (bit << pb);
+        slot = old;
+        pb = (pb == 4u) ? 0u : pb + 1u;
+    };
+    unsigned int t = S;
+    while (t & 7u) {                             // only from the unaligned end of the frame: flush bits, no data
+        --t;
+        one(__ldcg(dsrc + (t - base)));
+    }
+    while (t > a) {
+        uint2 d[8];
+#pragma unroll
+        for (unsigned int k = 0; k < 8; k++) d[k] = __ldcg(dsrc + (t - 1u - k - base));
+        acc = 0;
+#pragma unroll
+        for (unsigned int k = 0; k < 8; k++) {
+            acc |= slot << k;
+            one(d[k]);
+        }
+        t -= 8;
+        if (t < b && t < wlimit) dec[t >> 3] = (uint8_t)acc;
+    }
+}
+
+// ------------------------------------------------------------------ the same decoder, four trellis segments at once
+// A conv-coded 1200-byte frame is a 9 638-step dependent chain (0.68 ms on one warp), and since the frame-parallel
+// synchroniser it is what bounds the conv-coded configuration.  Survivor paths of a K = 7 code merge within a few
+// constraint lengths, so the four warps of the CTA each take a quarter of the trellis: warp p runs the add-compare-select
+// recursion from VIT_OV steps before its segment (all path metrics equal: after the overlap the metric DIFFERENCES, and
+// with them the decisions, are those of the full recursion) to VIT_OV steps behind it, and traces back from an arbitrary
+// state at the end of that overlap (after which the path has merged with the maximum-likelihood one), keeping only the
+// bits of its own segment.  "Merged" is overwhelmingly likely, not certain -- so the result is SPECULATIVE: the caller keeps
+// it only if the packet's CRC-32 passes and otherwise runs the exact full-frame decoder above, which makes the output
+// identical to libfec's except for a CRC collision.  Packets without a CRC always take the exact decoder.
+constexpr unsigned int VIT_OV = 160;                 // overlap on either side of a segment: 23 constraint lengths, a multiple of 80
+
+// true: dec holds the speculative decode; false: the frame does not fit this formulation (too short / workspace too small)
+__device__ bool viterbi27_decode_par(const uint8_t * enc, uint8_t * dec, unsigned int n, uint2 * decisions, size_t cap,
+                                     unsigned int tid)
+{
+    constexpr unsigned int NWP = PK_THREADS / 32;
+    const unsigned int nbits = 8 * n + 6;
+    // segments are multiples of 80 steps: whole groups of five trellis phases, whole 32-bit words of received pairs, whole bytes
+    const unsigned int seg = ((nbits + NWP - 1) / NWP + 79u) / 80u * 80u;
+    if (seg < 4 * VIT_OV || (size_t)NWP * (seg + 2 * VIT_OV) > cap) return false;
+    const unsigned int wp = tid >> 5, L = tid & 31u;
+    const unsigned int a = wp * seg, b = min(nbits, a + seg);
+    const bool active = a < nbits;
+    const unsigned int s0 = (wp == 0 || !active) ? 0u : a - VIT_OV;              // first / one-past-last step of this warp's recursion
+    const unsigned int e0 = !active ? 0u : ((b == nbits || b + VIT_OV >= nbits) ? nbits : b + VIT_OV);
+    uint2 * dloc = decisions + (size_t)wp * (seg + 2 * VIT_OV);                   // decisions of step t at dloc[t - s0]
+    if (active) {
+        unsigned int exw[5];
+#pragma unroll
+        for (unsigned int tm = 0; tm < 5; tm++) {
+            const unsigned int lbv = (L >> (4u - tm)) & 1u;
+            unsigned int j = lbv;
+#pragma unroll
+            for (unsigned int k = 1; k <= 4; k++) j |= ((L >> ((k - 1u + 5u - tm) % 5u)) & 1u) << k;
+            const unsigned int reg = j << 1;
+            exw[tm] = (((unsigned int)__popc(reg & 0x4f) & 1u) << 1) | ((unsigned int)__popc(reg & 0x6d) & 1u);
+        }
+        // the encoder starts in state 0; a segment that starts inside the frame knows nothing: all metrics equal
+        unsigned int me = (wp == 0) ? ((L == 0) ? 0u : 63u) : 0u, mo = (wp == 0) ? 63u : 0u;
+        const uint32_t * e32 = (const uint32_t *)enc;
+        const unsigned int wmax = (2u * nbits + 31u) / 32u - 1u;
+        unsigned int widx = s0 / 16u;                                            // s0 is a multiple of 16 pairs
+        unsigned long long buf = __brev(__byte_perm(e32[min(widx, wmax)], 0u, 0x0123u));
+        unsigned int avail = 16;
+        widx++;
+        uint32_t nxt = e32[min(widx, wmax)];
+        auto step = [&](const unsigned int tm, const unsigned int tt) {
+            const unsigned int r = (unsigned int)buf & 3u;
+            buf >>= 2;
+            const unsigned int lbv = (L >> (4u - tm)) & 1u;
+            const unsigned int recv = __shfl_xor_sync(0xffffffffu, lbv ? me : mo, 16u >> tm);
+            const unsigned int m_lo = lbv ? recv : me, m_hi = lbv ? mo : recv;
+            const unsigned int x = 255u * __popc(exw[tm] ^ r), y = 510u - x;
+            unsigned int m0 = m_lo + x, m1 = m_hi + y;
+            const unsigned int d_e = m1 < m0;
+            me = min(m0, m1);
+            m0 = m_lo + y; m1 = m_hi + x;
+            const unsigned int d_o = m1 < m0;
+            mo = min(m0, m1);
+            const unsigned int be = __ballot_sync(0xffffffffu, d_e), bo = __ballot_sync(0xffffffffu, d_o);
+            if (L == 0) dloc[tt - s0] = make_uint2(be, bo);
+        };
+        unsigned int t0 = s0;
+        for (; t0 + 5 <= e0; t0 += 5) {
+            const bool ref = avail < 5;
+            const unsigned long long add = (unsigned long long)__brev(__byte_perm(nxt, 0u, 0x0123u)) << (2u * avail);
+            buf |= ref ? add : 0ull;
+            avail += ref ? 16u : 0u;
+            widx += ref ? 1u : 0u;
+            const uint32_t ld = e32[min(widx, wmax)];
+            nxt = ref ? ld : nxt;
+            avail -= 5;
+#pragma unroll
+            for (unsigned int tm = 0; tm < 5; tm++) step(tm, t0 + tm);
+        }
+        if (t0 < e0) {                       // fewer than five steps left: only at the very end of the frame
+            if (avail < 5) buf |= (unsigned long long)__brev(__byte_perm(nxt, 0u, 0x0123u)) << (2u * avail);
+#pragma unroll
+            for (unsigned int tm = 0; tm < 4; tm++)
+                if (t0 + tm < e0) step(tm, t0 + tm);
+        }
+    }
+    for (unsigned int i = tid; i < n; i += PK_THREADS) dec[i] = 0;
+    __syncthreads();
+    if (active) {
+        // traceback of [a, e0), bits of [a, b) kept: the warp's 32 lanes each walk a slice (see above)
+        __syncwarp();
+        viterbi27_traceback_spec(dloc, s0, a, min(b, nbits), e0, dec, min(b, 8u * n), L, 32u);
+    }
+    __syncthreads();
+    return true;
+}
+
 // ------------------------------------------------------------------ CRC-32 (reflected 0xEDB88320)
 __device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b)
 {
@@ -359,7 +511,9 @@ __device__ uint32_t crc32_warp(const uint8_t * m, unsigned int n, unsigned int l
 }
 
 // ------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketParams p, uint2 * vit_ws, size_t vit_ws_stride,
+// 8 CTAs per SM: two launches of successive chunks (4 CTAs per SM each, capi.cu) stay resident together; tighter register
+// budgets (10, 12 CTAs per SM) measured slower on the conv-coded configuration -- the recursion's code quality wins.
+__global__ void __launch_bounds__(PK_THREADS, 8) packet_decode_kernel(const PacketParams p, uint2 * vit_ws, size_t vit_ws_stride,
                                                                       int * vit_locks, unsigned int vit_slots)
 {
     __shared__ unsigned int scratch[PK_THREADS / 32];
@@ -431,7 +585,34 @@ __global__ void __launch_bounds__(PK_THREADS) packet_decode_kernel(const PacketP
             __syncthreads();
             if (fec0 == 6) hamming128_decode_block(s1out, D, n0, tid);
             else if (fec0 == 7) golay2412_decode_block(s1out, D, n0, tid);
-            else if (8ull * n0 + 6 <= ws_cap) viterbi27_decode(s1out, D, n0, ws, stage, tid, false);
+            else if (8ull * n0 + 6 <= ws_cap) {
+                // speculative decode first, kept only if the CRC confirms it.  A launch with at most one frame per CTA is bound
+                // by the latency of one frame: four trellis segments at once (13 % more work).  A launch with more frames than
+                // CTAs is bound by instruction throughput: the exact recursion, and a traceback spread over all threads.
+                // If the CRC fails, the exact traceback (over the decisions already there) or the exact decoder follows.
+                bool done = false, have_acs = false;
+                if (crc_len && p.vit_parallel) {
+                    if (!((nrec - p.range[0].nrec) <= gridDim.x && viterbi27_decode_par(s1out, D, n0, ws, ws_cap, tid))) {
+                        viterbi27_acs(s1out, n0, ws, tid);
+                        __syncthreads();
+                        viterbi27_traceback_spec(ws, 0, 0, 8u * n0 + 6u, 8u * n0 + 6u, D, 8u * n0, tid, PK_THREADS);
+                        __syncthreads();
+                        have_acs = true;
+                    }
+                    if (tid < 32) {
+                        const uint32_t c = crc32_warp(D, plen, tid);
+                        if (tid == 0) {
+                            const uint32_t key = ((uint32_t)D[plen] << 24) | ((uint32_t)D[plen + 1] << 16) | ((uint32_t)D[plen + 2] << 8) | D[plen + 3];
+                            s_valid = (c == key);
+                        }
+                    }
+                    __syncthreads();
+                    done = (s_valid != 0);
+                    __syncthreads();
+                }
+                if (!done && have_acs) viterbi27_traceback(D, n0, ws, stage, tid, false);
+                else if (!done) viterbi27_decode(s1out, D, n0, ws, stage, tid, false);
+            }
             else ok = 0;
         } else {
             for (unsigned int i = tid; i < n0; i += PK_THREADS) D[i] = s1out[i];
@@ -830,16 +1011,6 @@ cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t 
         if (pe != cudaSuccess) return pe;
         std::lock_guard<std::mutex> guard(g_vit_mutex);
         VitWorkspace & g = g_vit[dev];
-        if (!g.ws) {
-            const size_t steps = 8ull * (65535 + 4 + 2) * 2 + 64;
-            const unsigned int slots = 16;
-            cudaError_t e = cudaMalloc(&g.ws, (size_t)slots * steps * sizeof(uint2));
-            if (e != cudaSuccess) { g.ws = nullptr; return e; }
-            e = cudaMalloc(&g.locks, slots * sizeof(int));
-            if (e == cudaSuccess) e = cudaMemset(g.locks, 0, slots * sizeof(int));
-            if (e != cudaSuccess) { cudaFree(g.ws); g.ws = nullptr; return e; }
-            g.stride = steps; g.slots = slots;
-        }
         w = g;
     }
     packet_plain_kernel<<<grid, PKF_WARPS * 32, 0, st>>>(p);
