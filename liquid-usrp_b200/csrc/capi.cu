@@ -45,6 +45,7 @@ struct SyncCore {
     size_t penc_cap = 0;
     // outputs
     DevBuf d_recs, d_aux, d_arena, d_scratch, d_decoded, d_counters, d_vit, d_crc;
+    unsigned int vit_mode = 1;           // conv-coded decode: 0 exact only, 1 speculative first (auto), 2 speculative traceback only (env B2_VIT_MODE)
     unsigned int vit_ctas = 0, vit_steps = 16384;     // per-CTA Viterbi decision regions of the general decode kernel
     unsigned int recs_cap = 0;
     unsigned long long arena_cap = 0;
@@ -280,6 +281,8 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     decode_grid = sms * 2;
     vit_ctas = (unsigned int)sms * 12;
+    if (getenv("B2_VIT_SERIAL")) vit_mode = 0;
+    if (const char * e = getenv("B2_VIT_MODE")) { int v = atoi(e); if (v >= 0 && v <= 2) vit_mode = (unsigned int)v; }
     if (const char * e = getenv("B2_VIT_CTAS")) { int v = atoi(e); if (v >= 3 && v <= 48) vit_ctas = (unsigned int)(sms * v); }   // per SM, over the NDS decode streams
     B2_TRY(d_vit.alloc(sizeof(uint2) * (size_t)vit_ctas * vit_steps));
     if (packet_decode_prepare() != cudaSuccess) return b2_fail(B2_ERR_NOMEM, "could not allocate the Viterbi workspace: %s", cudaGetErrorString(cudaGetLastError()));
@@ -451,8 +454,7 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
     pp.vit_local_ctas = vit_ctas / NDS; pp.vit_local_steps = vit_steps;
     pp.vit_local = d_vit.as<uint2>() + (size_t)(chunk % NDS) * pp.vit_local_ctas * vit_steps;
     pp.crc_cache = d_crc.as<unsigned int>();
-    static const bool vit_serial = getenv("B2_VIT_SERIAL") != nullptr;
-    pp.vit_parallel = vit_serial ? 0u : 1u;
+    pp.vit_parallel = vit_mode;
     if (timing) B2_CUDA(cudaEventRecord(e.d0, ds));
     B2_CUDA(packet_decode_launch(pp, decode_grid, ds));
     B2_CUDA(cudaEventRecord(e.d1, ds));

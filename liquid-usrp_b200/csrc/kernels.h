@@ -238,7 +238,8 @@ struct PacketParams {
     uint2 * vit_local;               // Viterbi decisions: vit_local_ctas regions of vit_local_steps trellis steps,
     unsigned int vit_local_steps;    // one per CTA of the general decode kernel (null: device-wide slots only)
     unsigned int vit_local_ctas;
-    unsigned int vit_parallel;       // 1: conv-coded frames with a CRC try the four-segment decoder first (B2_VIT_SERIAL=1: off)
+    unsigned int vit_parallel;       // conv-coded frames with a CRC: 0 exact decoder only; 1 speculative decode first (segmented recursion
+                                     // where the launch is latency-bound, else thread-parallel traceback); 2 thread-parallel traceback only
     unsigned int * crc_cache;        // [8] device words: [0] = 1 + per of the cached constants (0: empty), [1..5] = x^(8 per 2^l) mod P
 };
 cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t st);

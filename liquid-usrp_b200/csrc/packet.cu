@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(PK_THREADS, 8) packet_decode_kernel(const Pack
                 // If the CRC fails, the exact traceback (over the decisions already there) or the exact decoder follows.
                 bool done = false, have_acs = false;
                 if (crc_len && p.vit_parallel) {
-                    if (!((nrec - p.range[0].nrec) <= gridDim.x && viterbi27_decode_par(s1out, D, n0, ws, ws_cap, tid))) {
+                    if (!(p.vit_parallel == 1 && (nrec - p.range[0].nrec) <= gridDim.x && viterbi27_decode_par(s1out, D, n0, ws, ws_cap, tid))) {
                         viterbi27_acs(s1out, n0, ws, tid);
                         __syncthreads();
                         viterbi27_traceback_spec(ws, 0, 0, 8u * n0 + 6u, 8u * n0 + 6u, D, 8u * n0, tid, PK_THREADS);

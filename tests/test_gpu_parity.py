@@ -193,6 +193,32 @@ def test_reset_mid_stream_matches_oracle(name, frac):
     assert_frames_equal(fo, po, fg, pg)
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_conv_decode_modes_with_corrupted_frames(mode, monkeypatch):
+    """conv-coded frames through the exact decoder (0), the speculative decode (1: segmented recursion, a launch with few
+    frames) and the thread-parallel speculative traceback alone (2: what a launch with more frames than CTAs takes);
+    clean, noisy and CRC-failing frames -- the failing ones fall back to the exact decoder, so every payload byte,
+    valid or not, equals the oracle's"""
+    monkeypatch.setenv("B2_VIT_MODE", mode)
+    nbad = 0
+    for name in ("c3_16ch_qam16_v27", "noisy_v27", "n5_m96_v27"):
+        case = CASES[name]
+        x = make_input(case).copy()
+        N = case[0]
+        # wipe part of the payloads: a long gap (CRC fails on several channels) and a short one (the Viterbi decoder
+        # corrects most of it)
+        p0 = int(len(x) * 0.35)
+        x[p0:p0 + N * 200] = 0
+        p0 = int(len(x) * 0.8)
+        x[p0:p0 + N * 100] = 0
+        fo, po, _ = run_oracle(case, x)
+        fg, pg, _ = run_gpu(case, x)
+        assert len(fo) > 0 and int(fo["header_valid"].sum()) > 0
+        nbad += int(((fo["header_valid"] == 1) & (fo["payload_valid"] == 0)).sum())
+        assert_frames_equal(fo, po, fg, pg)
+    assert nbad >= 3            # the fallback was exercised
+
+
 def test_idle_channels_corruption_and_noise_only():
     N, M, cp, taper = 4, 64, 16, 4
     case = (N, M, cp, taper)
