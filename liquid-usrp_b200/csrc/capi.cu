@@ -280,10 +280,13 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     decode_grid = sms * 2;
-    vit_ctas = (unsigned int)sms * 12;
+    // Viterbi decision regions (16 384 steps = 128 KB each), one per CTA of the general decode kernel.  A launch takes a third
+    // of them (the decode streams rotate): 4 per SM, so that the launches of two successive chunks stay resident together;
+    // a handle with few streams never has that many frames in one launch and gets fewer (32 per stream)
+    vit_ctas = NDS * std::min((unsigned int)sms * 4u, std::max(32u, 32u * streams));
     if (getenv("B2_VIT_SERIAL")) vit_mode = 0;
     if (const char * e = getenv("B2_VIT_MODE")) { int v = atoi(e); if (v >= 0 && v <= 2) vit_mode = (unsigned int)v; }
-    if (const char * e = getenv("B2_VIT_CTAS")) { int v = atoi(e); if (v >= 3 && v <= 48) vit_ctas = (unsigned int)(sms * v); }   // per SM, over the NDS decode streams
+    if (const char * e = getenv("B2_VIT_CTAS")) { int v = atoi(e); if (v >= 3 && v <= 96) vit_ctas = (unsigned int)(sms * v) / NDS * NDS; }   // per SM, over the NDS decode streams
     B2_TRY(d_vit.alloc(sizeof(uint2) * (size_t)vit_ctas * vit_steps));
     if (packet_decode_prepare() != cudaSuccess) return b2_fail(B2_ERR_NOMEM, "could not allocate the Viterbi workspace: %s", cudaGetErrorString(cudaGetLastError()));
     return reset_state();
