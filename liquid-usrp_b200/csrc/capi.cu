@@ -46,6 +46,7 @@ struct SyncCore {
     // outputs
     DevBuf d_recs, d_aux, d_arena, d_scratch, d_decoded, d_counters, d_vit, d_crc;
     unsigned int vit_mode = 1;           // conv-coded decode: 0 exact only, 1 speculative first (auto), 2 speculative traceback only (env B2_VIT_MODE)
+    unsigned int vit_split = 0;          // frames per launch up to which the decode kernel's 128-thread shape works
     unsigned int vit_ctas = 0, vit_steps = 16384;     // per-CTA Viterbi decision regions of the general decode kernel
     unsigned int recs_cap = 0;
     unsigned long long arena_cap = 0;
@@ -281,12 +282,13 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     decode_grid = sms * 2;
     // Viterbi decision regions (16 384 steps = 128 KB each), one per CTA of the general decode kernel.  A launch takes a third
-    // of them (the decode streams rotate): 4 per SM, so that the launches of two successive chunks stay resident together;
-    // a handle with few streams never has that many frames in one launch and gets fewer (32 per stream)
-    vit_ctas = NDS * std::min((unsigned int)sms * 4u, std::max(32u, 32u * streams));
+    // of them (the decode streams rotate): up to 16 one-warp CTAs per SM in its 32-thread shape, 4 per SM in the 128-thread
+    // one; a handle with few streams never has that many frames in one launch and gets fewer (32 per stream)
+    vit_ctas = NDS * std::min((unsigned int)sms * 16u, std::max(32u, 32u * streams));
+    vit_split = std::min(vit_ctas / NDS, (unsigned int)sms * 4u);
     if (getenv("B2_VIT_SERIAL")) vit_mode = 0;
     if (const char * e = getenv("B2_VIT_MODE")) { int v = atoi(e); if (v >= 0 && v <= 2) vit_mode = (unsigned int)v; }
-    if (const char * e = getenv("B2_VIT_CTAS")) { int v = atoi(e); if (v >= 3 && v <= 96) vit_ctas = (unsigned int)(sms * v) / NDS * NDS; }   // per SM, over the NDS decode streams
+    if (const char * e = getenv("B2_VIT_CTAS")) { int v = atoi(e); if (v >= 3 && v <= 96) { vit_ctas = (unsigned int)(sms * v) / NDS * NDS; vit_split = std::min(vit_ctas / NDS, (unsigned int)sms * 4u); } }   // per SM, over the NDS decode streams
     B2_TRY(d_vit.alloc(sizeof(uint2) * (size_t)vit_ctas * vit_steps));
     if (packet_decode_prepare() != cudaSuccess) return b2_fail(B2_ERR_NOMEM, "could not allocate the Viterbi workspace: %s", cudaGetErrorString(cudaGetLastError()));
     return reset_state();
@@ -454,14 +456,14 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
     pp.recs = d_recs.as<FrameRec>(); pp.aux = d_aux.as<FrameAux>(); pp.range = range;
     pp.arena = d_arena.as<uint8_t>(); pp.scratch = d_scratch.as<uint8_t>(); pp.decoded = d_decoded.as<uint8_t>();
     // every decode stream has its own share of the Viterbi regions (launches on different streams overlap)
-    pp.vit_local_ctas = vit_ctas / NDS; pp.vit_local_steps = vit_steps;
+    pp.vit_local_ctas = vit_ctas / NDS; pp.vit_local_steps = vit_steps; pp.vit_split = vit_split;
     pp.vit_local = d_vit.as<uint2>() + (size_t)(chunk % NDS) * pp.vit_local_ctas * vit_steps;
     pp.crc_cache = d_crc.as<unsigned int>();
     pp.vit_parallel = vit_mode;
     if (timing) B2_CUDA(cudaEventRecord(e.d0, ds));
     B2_CUDA(packet_decode_launch(pp, decode_grid, ds));
     B2_CUDA(cudaEventRecord(e.d1, ds));
-    chunk++; launches += 4;                  // synchroniser, record mark, two decode kernels
+    chunk++; launches += 5;                  // synchroniser, record mark, three decode kernels (one shape of the general one returns at once)
     return B2_OK;
 }
 

@@ -71,7 +71,7 @@ __device__ __forceinline__ unsigned int block_excl_scan(unsigned int v, unsigned
     if (lane == 31) scratch[wid] = x;
     __syncthreads();
     unsigned int base = 0, tot = 0;
-    for (unsigned int w = 0; w < PK_THREADS / 32; w++) {
+    for (unsigned int w = 0; w < blockDim.x / 32; w++) {
         unsigned int s = scratch[w];
         if (w < wid) base += s;
         tot += s;
@@ -112,7 +112,7 @@ __device__ void deinterleave_pass(uint8_t * x, unsigned int n, unsigned int Mi, 
             }
         }
         count += tot;
-        base += PK_THREADS * 4;
+        base += blockDim.x * 4;
         __syncthreads();
     }
 }
@@ -140,7 +140,7 @@ __device__ __forceinline__ unsigned int hamming128_decode(unsigned int r)
 __device__ void hamming128_decode_block(const uint8_t * enc, uint8_t * dec, unsigned int n, unsigned int tid)
 {
     unsigned int pairs = n / 2;
-    for (unsigned int k = tid; k < pairs; k += PK_THREADS) {
+    for (unsigned int k = tid; k < pairs; k += blockDim.x) {
         unsigned int e0 = enc[3 * k], e1 = enc[3 * k + 1], e2 = enc[3 * k + 2];
         dec[2 * k] = (uint8_t)hamming128_decode((e0 << 4) | (e1 >> 4));
         dec[2 * k + 1] = (uint8_t)hamming128_decode(((e1 & 0x0f) << 8) | e2);
@@ -153,7 +153,7 @@ __device__ void hamming128_decode_block(const uint8_t * enc, uint8_t * dec, unsi
 __device__ void golay2412_decode_block(const uint8_t * enc, uint8_t * dec, unsigned int n, unsigned int tid)
 {
     unsigned int groups = n / 3, r = n % 3;
-    for (unsigned int k = tid; k < groups; k += PK_THREADS) {
+    for (unsigned int k = tid; k < groups; k += blockDim.x) {
         const uint8_t * e = enc + 6 * k;
         unsigned int s0 = golay2412_decode(((unsigned int)e[0] << 16) | ((unsigned int)e[1] << 8) | e[2]);
         unsigned int s1 = golay2412_decode(((unsigned int)e[3] << 16) | ((unsigned int)e[4] << 8) | e[5]);
@@ -247,10 +247,11 @@ __device__ void viterbi27_acs(const uint8_t * enc, unsigned int n, uint2 * decis
 }
 
 // exact traceback from the terminated end state (one thread: the chain is dependent from step to step)
-__device__ void viterbi27_traceback(uint8_t * dec, unsigned int n, const uint2 * decisions, uint2 * stage, unsigned int tid, bool in_smem)
+__device__ void viterbi27_traceback(uint8_t * dec, unsigned int n, const uint2 * decisions, uint2 * stage, unsigned int tid, bool in_smem,
+                                    unsigned int tb_steps = PK_TB_STEPS)
 {
     const unsigned int nbits = 8 * n + 6;
-    for (unsigned int i = tid; i < n; i += PK_THREADS) dec[i] = 0;
+    for (unsigned int i = tid; i < n; i += blockDim.x) dec[i] = 0;
     __syncthreads();
     // traceback, in the rotated lane domain: the lane y of the current state stays in place from one step to
     // the next except for ONE bit (position pb, advancing with the step) that is replaced by the decision bit,
@@ -298,9 +299,9 @@ __device__ void viterbi27_traceback(uint8_t * dec, unsigned int n, const uint2 *
         hi = 0;
     }
     while (hi > 0) {
-        unsigned int lo = hi > PK_TB_STEPS ? ((hi - PK_TB_STEPS + 7u) & ~7u) : 0;     // chunks end on byte boundaries
+        unsigned int lo = hi > tb_steps ? ((hi - tb_steps + 7u) & ~7u) : 0;     // chunks end on byte boundaries
         __syncthreads();
-        for (unsigned int i = lo + tid; i < hi; i += PK_THREADS) stage[i - lo] = decisions[i];
+        for (unsigned int i = lo + tid; i < hi; i += blockDim.x) stage[i - lo] = decisions[i];
         __syncthreads();
         // every `lo` is a multiple of 8, so a decoded byte never straddles two chunks; the flush bits
         // (t >= 8n) of the first chunk carry no data
@@ -311,10 +312,10 @@ __device__ void viterbi27_traceback(uint8_t * dec, unsigned int n, const uint2 *
 }
 
 __device__ void viterbi27_decode(const uint8_t * enc, uint8_t * dec, unsigned int n, uint2 * decisions,
-                                 uint2 * stage, unsigned int tid, bool in_smem)
+                                 uint2 * stage, unsigned int tid, bool in_smem, unsigned int tb_steps = PK_TB_STEPS)
 {
     viterbi27_acs(enc, n, decisions, tid);
-    viterbi27_traceback(dec, n, decisions, stage, tid, in_smem);
+    viterbi27_traceback(dec, n, decisions, stage, tid, in_smem, tb_steps);
 }
 
 // ------------------------------------------------------------------ speculative traceback, one short walk per thread
@@ -445,7 +446,7 @@ __device__ bool viterbi27_decode_par(const uint8_t * enc, uint8_t * dec, unsigne
                 if (t0 + tm < e0) step(tm, t0 + tm);
         }
     }
-    for (unsigned int i = tid; i < n; i += PK_THREADS) dec[i] = 0;
+    for (unsigned int i = tid; i < n; i += blockDim.x) dec[i] = 0;
     __syncthreads();
     if (active) {
         // traceback of [a, e0), bits of [a, b) kept: the warp's 32 lanes each walk a slice (see above)
@@ -511,16 +512,28 @@ __device__ uint32_t crc32_warp(const uint8_t * m, unsigned int n, unsigned int l
 }
 
 // ------------------------------------------------------------------ kernel
-// 8 CTAs per SM: two launches of successive chunks (4 CTAs per SM each, capi.cu) stay resident together; tighter register
-// budgets (10, 12 CTAs per SM) measured slower on the conv-coded configuration -- the recursion's code quality wins.
-__global__ void __launch_bounds__(PK_THREADS, 8) packet_decode_kernel(const PacketParams p, uint2 * vit_ws, size_t vit_ws_stride,
-                                                                      int * vit_locks, unsigned int vit_slots)
+// Two shapes of the same kernel are launched per chunk, and the device-side frame count of the launch decides which one works
+// (the other returns at once):
+//   NT = 128  a launch with at most one frame per CTA is bound by the LATENCY of a frame: four warps per frame, the
+//             segmented recursion for conv-coded frames.  64 registers, 8 CTAs per SM (tighter budgets measured slower).
+//   NT = 32   a launch with more frames than that is bound by how many trellis recursions run side by side -- each is one
+//             warp's dependent chain at a quarter of an instruction per cycle, and in the 128-thread shape the other three
+//             warps of the CTA only hold registers meanwhile.  One warp per frame, up to 32 CTAs per SM.
+template <unsigned int NT>
+__global__ void __launch_bounds__(NT, NT == 32 ? 24 : 8) packet_decode_kernel(const PacketParams p, uint2 * vit_ws, size_t vit_ws_stride,
+                                                                               int * vit_locks, unsigned int vit_slots)
 {
-    __shared__ unsigned int scratch[PK_THREADS / 32];
-    __shared__ uint2 stage[PK_TB_STEPS];
+    constexpr unsigned int TB_STEPS = NT == 32 ? 512u : PK_TB_STEPS;         // traceback staging chunk of the exact decoder
+    __shared__ unsigned int scratch[NT / 32];
+    __shared__ uint2 stage[TB_STEPS];
     __shared__ int s_valid;
     const unsigned int tid = threadIdx.x;
     const unsigned int nrec = p.range[1].nrec;
+    {
+        const unsigned int nfr = nrec - p.range[0].nrec;
+        const bool wide = p.vit_parallel == 2 || (p.vit_parallel == 1 && nfr > p.vit_split);     // the NT = 32 shape works
+        if (wide != (NT == 32)) return;
+    }
     for (unsigned int ri = p.range[0].nrec + blockIdx.x; ri < nrec; ri += gridDim.x) {
         FrameRec * rec = p.recs + ri;
         if (!rec->header_valid) continue;
@@ -562,9 +575,9 @@ __global__ void __launch_bounds__(PK_THREADS, 8) packet_decode_kernel(const Pack
         if (sym_bps) {
             // the arena holds demapped symbols: pack them, then work in place as before
             const unsigned int mod_len = (8 * e1 + sym_bps - 1) / sym_bps;
-            pack_symbols(A, mod_len, sym_bps, (uint32_t *)Bf, nullptr, e1, tid, PK_THREADS);
+            pack_symbols(A, mod_len, sym_bps, (uint32_t *)Bf, nullptr, e1, tid, blockDim.x);
             __syncthreads();
-            for (unsigned int i = tid; i < (e1 + 3) / 4; i += PK_THREADS) ((uint32_t *)A)[i] = ((const uint32_t *)Bf)[i];
+            for (unsigned int i = tid; i < (e1 + 3) / 4; i += blockDim.x) ((uint32_t *)A)[i] = ((const uint32_t *)Bf)[i];
             __syncthreads();
         }
         // stage 1 (outer code)
@@ -574,7 +587,7 @@ __global__ void __launch_bounds__(PK_THREADS, 8) packet_decode_kernel(const Pack
             __syncthreads();
             if (fec1 == 6) hamming128_decode_block(A, Bf, e0, tid);
             else if (fec1 == 7) golay2412_decode_block(A, Bf, e0, tid);
-            else if (8ull * e0 + 6 <= ws_cap) viterbi27_decode(A, Bf, e0, ws, stage, tid, false);
+            else if (8ull * e0 + 6 <= ws_cap) viterbi27_decode(A, Bf, e0, ws, stage, tid, false, TB_STEPS);
             else ok = 0;
             s1out = Bf;
             __syncthreads();
@@ -586,16 +599,20 @@ __global__ void __launch_bounds__(PK_THREADS, 8) packet_decode_kernel(const Pack
             if (fec0 == 6) hamming128_decode_block(s1out, D, n0, tid);
             else if (fec0 == 7) golay2412_decode_block(s1out, D, n0, tid);
             else if (8ull * n0 + 6 <= ws_cap) {
-                // speculative decode first, kept only if the CRC confirms it.  A launch with at most one frame per CTA is bound
-                // by the latency of one frame: four trellis segments at once (13 % more work).  A launch with more frames than
-                // CTAs is bound by instruction throughput: the exact recursion, and a traceback spread over all threads.
+                // speculative decode first, kept only if the CRC confirms it.  The 128-thread shape (a launch bound by the
+                // latency of one frame) runs four trellis segments at once (13 % more work); the 32-thread shape the exact
+                // recursion; both with the traceback spread over all threads.
                 // If the CRC fails, the exact traceback (over the decisions already there) or the exact decoder follows.
                 bool done = false, have_acs = false;
                 if (crc_len && p.vit_parallel) {
-                    if (!(p.vit_parallel == 1 && (nrec - p.range[0].nrec) <= gridDim.x && viterbi27_decode_par(s1out, D, n0, ws, ws_cap, tid))) {
+                    bool segmented = false;
+                    if constexpr (NT == 128) {
+                        if (p.vit_parallel == 1) segmented = viterbi27_decode_par(s1out, D, n0, ws, ws_cap, tid);
+                    }
+                    if (!segmented) {
                         viterbi27_acs(s1out, n0, ws, tid);
                         __syncthreads();
-                        viterbi27_traceback_spec(ws, 0, 0, 8u * n0 + 6u, 8u * n0 + 6u, D, 8u * n0, tid, PK_THREADS);
+                        viterbi27_traceback_spec(ws, 0, 0, 8u * n0 + 6u, 8u * n0 + 6u, D, 8u * n0, tid, blockDim.x);
                         __syncthreads();
                         have_acs = true;
                     }
@@ -610,12 +627,11 @@ __global__ void __launch_bounds__(PK_THREADS, 8) packet_decode_kernel(const Pack
                     done = (s_valid != 0);
                     __syncthreads();
                 }
-                if (!done && have_acs) viterbi27_traceback(D, n0, ws, stage, tid, false);
-                else if (!done) viterbi27_decode(s1out, D, n0, ws, stage, tid, false);
-            }
-            else ok = 0;
+                if (!done && have_acs) viterbi27_traceback(D, n0, ws, stage, tid, false, TB_STEPS);
+                else if (!done) viterbi27_decode(s1out, D, n0, ws, stage, tid, false, TB_STEPS);
+            }            else ok = 0;
         } else {
-            for (unsigned int i = tid; i < n0; i += PK_THREADS) D[i] = s1out[i];
+            for (unsigned int i = tid; i < n0; i += blockDim.x) D[i] = s1out[i];
         }
         __syncthreads();
         if (tid < 32) {
@@ -674,7 +690,7 @@ __device__ void fec_encode_block(unsigned int scheme, const uint8_t * dec, uint8
 {
     if (scheme == 6) {                                  // Hamming(12,8): 2 bytes -> 3 bytes
         unsigned int pairs = n / 2;
-        for (unsigned int k = tid; k < pairs; k += PK_THREADS) {
+        for (unsigned int k = tid; k < pairs; k += blockDim.x) {
             unsigned int m0 = hamming128_encode(dec[2 * k]), m1 = hamming128_encode(dec[2 * k + 1]);
             enc[3 * k] = (m0 >> 4) & 0xff;
             enc[3 * k + 1] = ((m0 << 4) & 0xf0) | ((m1 >> 8) & 0x0f);
@@ -687,7 +703,7 @@ __device__ void fec_encode_block(unsigned int scheme, const uint8_t * dec, uint8
         }
     } else if (scheme == 7) {                           // Golay(24,12): 3 bytes -> 6 bytes
         unsigned int groups = n / 3, r = n % 3;
-        for (unsigned int k = tid; k < groups; k += PK_THREADS) {
+        for (unsigned int k = tid; k < groups; k += blockDim.x) {
             unsigned int s0 = ((unsigned int)dec[3 * k] << 4) | (dec[3 * k + 1] >> 4);
             unsigned int s1 = (((unsigned int)dec[3 * k + 1] & 0x0f) << 8) | dec[3 * k + 2];
             unsigned int v0 = golay2412_encode(s0), v1 = golay2412_encode(s1);
@@ -702,7 +718,7 @@ __device__ void fec_encode_block(unsigned int scheme, const uint8_t * dec, uint8
         }
     } else if (scheme == 11) {                          // conv r1/2 K=7: output byte j <- input bits 4j .. 4j+3
         unsigned int nbits = 8 * n + 6, nout = (2 * nbits + 7) / 8;
-        for (unsigned int j = tid; j < nout; j += PK_THREADS) {
+        for (unsigned int j = tid; j < nout; j += blockDim.x) {
             unsigned int v = 0;
             for (unsigned int q = 0; q < 4; q++) {
                 unsigned int t = 4 * j + q;
@@ -722,7 +738,7 @@ __device__ void fec_encode_block(unsigned int scheme, const uint8_t * dec, uint8
             enc[j] = (uint8_t)v;
         }
     } else {
-        for (unsigned int i = tid; i < n; i += PK_THREADS) enc[i] = dec[i];
+        for (unsigned int i = tid; i < n; i += blockDim.x) enc[i] = dec[i];
     }
 }
 
@@ -756,7 +772,7 @@ __global__ void __launch_bounds__(PK_THREADS) packet_encode_kernel(const EncodeP
         {
             const uint8_t mask[4] = {0xb4, 0x6a, 0x8b, 0x45};
             uint8_t * hm = p.header_mod + (size_t)job.slot * 288;
-            for (unsigned int i = tid; i < 288; i += PK_THREADS) {
+            for (unsigned int i = tid; i < 288; i += blockDim.x) {
                 unsigned int byte = hbuf[1][i >> 3] ^ mask[(i >> 3) & 3];
                 hm[i] = (byte >> (7 - (i & 7))) & 1u;
             }
@@ -768,7 +784,7 @@ __global__ void __launch_bounds__(PK_THREADS) packet_encode_kernel(const EncodeP
         uint8_t * A = p.work0 + (size_t)job.slot * p.work_stride;
         uint8_t * B = p.work1 + (size_t)job.slot * p.work_stride;
         const uint8_t * msg = p.payloads + job.payload_offset;
-        for (unsigned int i = tid; i < plen; i += PK_THREADS) A[i] = msg[i];
+        for (unsigned int i = tid; i < plen; i += blockDim.x) A[i] = msg[i];
         __syncthreads();
         if (crc_len && tid < 32) {
             uint32_t c = crc32_warp(A, plen, tid);
@@ -786,7 +802,7 @@ __global__ void __launch_bounds__(PK_THREADS) packet_encode_kernel(const EncodeP
         // repack e1 bytes into bps-bit symbols, MSB first, zero padded
         const unsigned int bps = job.bps, nsym = (8 * e1 + bps - 1) / bps;
         uint8_t * pm = p.payload_mod + (size_t)job.slot * p.mod_stride;
-        for (unsigned int s = tid; s < nsym; s += PK_THREADS) {
+        for (unsigned int s = tid; s < nsym; s += blockDim.x) {
             unsigned int v = 0;
             for (unsigned int b = 0; b < bps; b++) {
                 unsigned int bit = s * bps + b;
@@ -1014,9 +1030,10 @@ cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t 
         w = g;
     }
     packet_plain_kernel<<<grid, PKF_WARPS * 32, 0, st>>>(p);
-    // the general kernel keeps one warp per CTA busy in the Viterbi recursion: many small CTAs per SM
+    // the general kernel in its two shapes (one of them returns at once, see above): a region of the workspace per CTA
     const int ggrid = p.vit_local ? (int)p.vit_local_ctas : grid;
-    packet_decode_kernel<<<ggrid, PK_THREADS, 0, st>>>(p, w.ws, w.stride, w.locks, w.slots);
+    packet_decode_kernel<128><<<p.vit_local ? (int)p.vit_split : grid, 128, 0, st>>>(p, w.ws, w.stride, w.locks, w.slots);
+    packet_decode_kernel<32><<<ggrid, 32, 0, st>>>(p, w.ws, w.stride, w.locks, w.slots);
     return cudaGetLastError();
 }
 
