@@ -531,7 +531,7 @@ extern "C" int b2_msresamp_create(float rate, float As, int device, b2_msresamp 
     int rc = B2_OK;
     do {
         if (cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = b2_fail(B2_ERR_CUDA, "cudaStreamCreate failed"); break; }
-        if ((rc = q->t_h.upload(resamp_prototype(rate, As, q->m, 1u << q->npfb_bits)))) break;
+        if ((rc = q->t_h.upload(resamp_prototype(rate, As, q->m, 1u << q->npfb_bits))) != B2_OK) break;
         q->step = (unsigned long long)llrint(4294967296.0 / (double)rate);
         q->x_cap = ((size_t)1 << 20);
         q->y_cap = (size_t)(q->x_cap * 2.1) + 64;
