@@ -1,6 +1,9 @@
-"""print the essentials of the last JSON line on stdin (bench.py output)"""
+"""print the essentials of the last JSON line of bench.py's output: python tools/benchline.py FILE   (or on stdin: ... | benchline.py -)"""
 import json, sys
-lines = [l for l in sys.stdin.read().splitlines() if l.startswith("{")]
+if len(sys.argv) < 2:
+    sys.exit(__doc__)               # never sit waiting on a terminal's stdin
+text = sys.stdin.read() if sys.argv[1] == "-" else open(sys.argv[1]).read()
+lines = [l for l in text.splitlines() if l.startswith("{")]
 d = json.loads(lines[-1])
 out = "value %.1f GS/s  e2e %.2f GS/s  ms/step %.3f" % (d["value"] / 1e3, d["e2e"]["value"] / 1e3, d["ms_per_step"])
 if "replicas" in d:
