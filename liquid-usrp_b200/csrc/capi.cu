@@ -47,6 +47,7 @@ struct SyncCore {
     DevBuf d_recs, d_aux, d_arena, d_scratch, d_decoded, d_counters, d_vit, d_crc;
     unsigned int vit_mode = 1;           // conv-coded decode: 0 exact only, 1 speculative first (auto), 2 speculative traceback only (env B2_VIT_MODE)
     unsigned int vit_split = 0;          // frames per launch up to which the decode kernel's 128-thread shape works
+    unsigned int vit_grid128 = 0, vit_sms = 148;
     unsigned int vit_ctas = 0, vit_steps = 16384;     // per-CTA Viterbi decision regions of the general decode kernel
     unsigned int recs_cap = 0;
     unsigned long long arena_cap = 0;
@@ -285,10 +286,14 @@ int SyncCore::init(unsigned int M, unsigned int cp, unsigned int taper, const un
     // of them (the decode streams rotate): up to 16 one-warp CTAs per SM in its 32-thread shape, 4 per SM in the 128-thread
     // one; a handle with few streams never has that many frames in one launch and gets fewer (32 per stream)
     vit_ctas = NDS * std::min((unsigned int)sms * 16u, std::max(32u, 32u * streams));
-    vit_split = std::min(vit_ctas / NDS, (unsigned int)sms * 4u);
+    vit_sms = (unsigned int)sms;
     if (getenv("B2_VIT_SERIAL")) vit_mode = 0;
     if (const char * e = getenv("B2_VIT_MODE")) { int v = atoi(e); if (v >= 0 && v <= 2) vit_mode = (unsigned int)v; }
-    if (const char * e = getenv("B2_VIT_CTAS")) { int v = atoi(e); if (v >= 3 && v <= 96) { vit_ctas = (unsigned int)(sms * v) / NDS * NDS; vit_split = std::min(vit_ctas / NDS, (unsigned int)sms * 4u); } }   // per SM, over the NDS decode streams
+    if (const char * e = getenv("B2_VIT_CTAS")) { int v = atoi(e); if (v >= 3 && v <= 96) vit_ctas = (unsigned int)(sms * v) / NDS * NDS; }   // per SM, over the NDS decode streams
+    // the 128-thread shape runs 4 CTAs per SM; the one-warp shape takes over only where it has more CTAs than that to offer
+    // (with as many or fewer -- a handle with few streams -- it would be the same frames at a quarter of the width)
+    vit_grid128 = std::min(vit_ctas / NDS, vit_sms * 4u);
+    vit_split = (vit_ctas / NDS > vit_grid128) ? vit_grid128 : 0xffffffffu;
     B2_TRY(d_vit.alloc(sizeof(uint2) * (size_t)vit_ctas * vit_steps));
     if (packet_decode_prepare() != cudaSuccess) return b2_fail(B2_ERR_NOMEM, "could not allocate the Viterbi workspace: %s", cudaGetErrorString(cudaGetLastError()));
     return reset_state();
@@ -456,7 +461,7 @@ int SyncCore::launch_chunk(const cf * in, size_t in_stride, unsigned int nsample
     pp.recs = d_recs.as<FrameRec>(); pp.aux = d_aux.as<FrameAux>(); pp.range = range;
     pp.arena = d_arena.as<uint8_t>(); pp.scratch = d_scratch.as<uint8_t>(); pp.decoded = d_decoded.as<uint8_t>();
     // every decode stream has its own share of the Viterbi regions (launches on different streams overlap)
-    pp.vit_local_ctas = vit_ctas / NDS; pp.vit_local_steps = vit_steps; pp.vit_split = vit_split;
+    pp.vit_local_ctas = vit_ctas / NDS; pp.vit_local_steps = vit_steps; pp.vit_split = vit_split; pp.vit_grid128 = vit_grid128;
     pp.vit_local = d_vit.as<uint2>() + (size_t)(chunk % NDS) * pp.vit_local_ctas * vit_steps;
     pp.crc_cache = d_crc.as<unsigned int>();
     pp.vit_parallel = vit_mode;

@@ -238,7 +238,8 @@ struct PacketParams {
     uint2 * vit_local;               // Viterbi decisions: vit_local_ctas regions of vit_local_steps trellis steps,
     unsigned int vit_local_steps;    // one per CTA of the general decode kernel (null: device-wide slots only)
     unsigned int vit_local_ctas;
-    unsigned int vit_split;          // launches with at most this many frames take the 128-thread shape of the general kernel (= its grid)
+    unsigned int vit_split;          // launches with at most this many frames take the 128-thread shape of the general kernel
+    unsigned int vit_grid128;        // grid of that shape (the one-warp shape gets vit_local_ctas CTAs)
     unsigned int vit_parallel;       // conv-coded frames with a CRC: 0 exact decoder only; 1 speculative decode first (segmented recursion
                                      // where the launch is latency-bound, else thread-parallel traceback); 2 thread-parallel traceback only
     unsigned int * crc_cache;        // [8] device words: [0] = 1 + per of the cached constants (0: empty), [1..5] = x^(8 per 2^l) mod P

@@ -1032,7 +1032,7 @@ cudaError_t packet_decode_launch(const PacketParams & p, int grid, cudaStream_t 
     packet_plain_kernel<<<grid, PKF_WARPS * 32, 0, st>>>(p);
     // the general kernel in its two shapes (one of them returns at once, see above): a region of the workspace per CTA
     const int ggrid = p.vit_local ? (int)p.vit_local_ctas : grid;
-    packet_decode_kernel<128><<<p.vit_local ? (int)p.vit_split : grid, 128, 0, st>>>(p, w.ws, w.stride, w.locks, w.slots);
+    packet_decode_kernel<128><<<p.vit_local ? (int)p.vit_grid128 : grid, 128, 0, st>>>(p, w.ws, w.stride, w.locks, w.slots);
     packet_decode_kernel<32><<<ggrid, 32, 0, st>>>(p, w.ws, w.stride, w.locks, w.slots);
     return cudaGetLastError();
 }
