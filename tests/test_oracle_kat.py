@@ -83,6 +83,33 @@ def test_conv27_corrects_scattered_errors():
     assert list(bits[:, 0]) == ga and list(bits[:, 1]) == gb
 
 
+def test_conv27_against_an_independent_numpy_decoder():
+    """the oracle's r1/2 K=7 codec against the textbook numpy model in tools/vit_merge_stats.py (state = shift register,
+    Hamming branch metrics, strict-less tie-break): same code bits, same decoded bytes under 2 % channel bit errors"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import vit_merge_stats as V
+    rng = np.random.default_rng(17)
+    for n in (5, 64, 150):
+        m = rng.integers(0, 256, n, dtype=np.uint8)
+        nbits = 8 * n + 6
+        msgbits = np.concatenate([np.unpackbits(m), np.zeros(6, np.uint8)]).astype(np.int64)
+        pairs = V.encode(msgbits)                                 # (c(0x6d) << 1) | c(0x4f) per input bit
+        e = orc.fec_encode(FEC_CONV_V27, m)
+        ebits = np.unpackbits(e)[:2 * nbits].reshape(nbits, 2)
+        assert np.array_equal((ebits[:, 0].astype(np.int64) << 1) | ebits[:, 1], pairs)
+        flips = (rng.random(2 * nbits) < 0.02).astype(np.uint8)
+        rxbits = np.unpackbits(e).copy()
+        rxbits[:2 * nbits] ^= flips
+        dec_oracle = orc.fec_decode(FEC_CONV_V27, n, np.packbits(rxbits))
+        rx = (rxbits[:2 * nbits].reshape(nbits, 2)[:, 0].astype(np.int64) << 1) | rxbits[:2 * nbits].reshape(nbits, 2)[:, 1]
+        start = np.full(V.NS, 63, np.int64); start[0] = 0
+        dec, _ = V.acs(rx, 0, nbits, start)
+        bits = V.traceback(dec, 0, nbits, 0, 0)[:8 * n]
+        assert np.array_equal(np.packbits(bits), dec_oracle)
+        assert np.array_equal(dec_oracle, m)
+
+
 @pytest.mark.parametrize("n", [2, 3, 16, 36, 100, 255, 1204, 1806, 2410])
 def test_interleaver_is_a_bit_permutation_and_inverts(n):
     rng = np.random.default_rng(n)
