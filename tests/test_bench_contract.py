@@ -28,6 +28,17 @@ def test_reference_arm_prints_the_contract_line():
     assert d["config"]["frames_decoded"] > 0
 
 
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29643", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+
+
 def test_product_arm_refuses_to_run_without_a_gpu():
     import torch
     if torch.cuda.is_available():
